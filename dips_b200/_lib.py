@@ -1,0 +1,79 @@
+"""ctypes loader for libdips_b200.so.  There is no fallback: if the library is missing or cannot be loaded the import of
+anything that needs it raises, loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libdips_b200.so")
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32),
+        ("format", C.c_int32), ("mode", C.c_int32), ("chroma", C.c_int32), ("threshold", C.c_uint32),
+        ("colorize", C.c_int32), ("filter", C.c_int32), ("sigmoid_scalar", C.c_float), ("spatial_window", C.c_int32),
+        ("reserved", C.c_uint32 * 4),
+    ]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("frame_index", C.c_uint64), ("sad", C.c_uint64), ("count", C.c_uint64)]
+
+
+# every symbol include/dips_b200.h declares: name -> (restype, argtypes)
+_vp, _u64, _u32, _i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+SYMBOLS = {
+    "dipsb_abi_version": (_i32, []),
+    "dipsb_default_config": (None, [C.POINTER(Config)]),
+    "dipsb_create": (_i32, [C.POINTER(Config), C.POINTER(_vp)]),
+    "dipsb_destroy": (None, [_vp]),
+    "dipsb_last_error": (C.c_char_p, [_vp]),
+    "dipsb_reset": (_i32, [_vp]),
+    "dipsb_set_threshold": (_i32, [_vp, _u32]),
+    "dipsb_set_stream": (_i32, [_vp, _vp]),
+    "dipsb_synchronize": (_i32, [_vp]),
+    "dipsb_prime_device": (_i32, [_vp, _vp]),
+    "dipsb_prime_median4_device": (_i32, [_vp, _vp, _u64]),
+    "dipsb_prime_host": (_i32, [_vp, _vp]),
+    "dipsb_state_plane_device": (_i32, [_vp, C.POINTER(_vp)]),
+    "dipsb_mark_state_valid": (_i32, [_vp, _i32]),
+    "dipsb_get_state_plane": (_i32, [_vp, _vp]),
+    "dipsb_run_clip_device": (_i32, [_vp, _vp, _u64, _u64, _u64]),
+    "dipsb_run_clip_host": (_i32, [_vp, _vp, _u64, _u64, _u64]),
+    "dipsb_push_frame": (_i32, [_vp, _vp, _u32, _u32, _u32, _i32, _vp, C.POINTER(FrameStats)]),
+    "dipsb_snapshot": (_i32, [_vp]),
+    "dipsb_frames_processed": (_u64, [_vp]),
+    "dipsb_get_accumulators": (_i32, [_vp, _vp, _vp]),
+    "dipsb_set_accumulators": (_i32, [_vp, _vp, _vp]),
+    "dipsb_accumulators_device": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
+    "dipsb_get_scalars": (_i32, [_vp, _u64, _u64, _vp, _vp]),
+    "dipsb_get_intensity_map": (_i32, [_vp, _u64, _vp]),
+    "dipsb_get_frame_means": (_i32, [_vp, _u64, _u64, _vp]),
+    "dipsb_synth_fill_device": (_i32, [_i32, _vp, _u64, _u64, _u32, _u32, _i32, _u64, _i32, _vp]),
+    "dipsb_launch_count": (_u64, []),
+    "dipsb_last_plan": (_i32, [_vp, C.POINTER(_u32 * 8)]),
+    "dipsb_enable_timing": (_i32, [_vp, _i32]),
+    "dipsb_clip_kernel_time": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "dipsb_set_tuning": (_i32, [_vp, _u32, _u32, _u32]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library and bind every declared symbol (raises if the .so or a symbol is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise ImportError(
+                f"{SO} is missing: build it with `python -m dips_b200._build` (or __graft_entry__.build()); "
+                "dips_b200 has no CPU or PyTorch fallback")
+        lib = C.CDLL(SO)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)      # AttributeError if the export is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

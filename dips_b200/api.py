@@ -1,0 +1,220 @@
+"""Python host layer over the C ABI (include/dips_b200.h).  One `Context` == one `dipsb_ctx`.
+
+Every method is a 1:1 call into libdips_b200.so; arrays cross the boundary as raw pointers (numpy for host memory,
+integer device addresses -- e.g. `torch.Tensor.data_ptr()` -- for device memory).  Nothing here computes pixels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+FMT_RGB8, FMT_RGBX8, FMT_BGR8, FMT_BGRX8 = 0, 1, 2, 3
+MODE_OVERALL, MODE_PERFRAME = 0, 1
+CHROMA_NONE, CHROMA_RED, CHROMA_GREEN, CHROMA_BLUE = 0, 1, 2, 3
+FILTER_SIGMOID, FILTER_INV_SIGMOID, FILTER_NONE = 0, 1, 255
+SYNTH_UNIFORM, SYNTH_SCENE = 0, 1
+OK, NOT_READY = 0, 1
+
+
+class DipsError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"dips_b200 error {code}: {message}")
+        self.code = code
+
+
+def bytes_per_pixel(fmt: int) -> int:
+    return 3 if fmt in (FMT_RGB8, FMT_BGR8) else 4
+
+
+def launch_count() -> int:
+    return int(_lib.load().dipsb_launch_count())
+
+
+def synth_fill_device(device: int, d_dst: int, first_frame: int, n_frames: int, width: int, height: int, fmt: int,
+                      seed: int = 0x44695073, profile: int = SYNTH_SCENE, stream: int = 0) -> None:
+    rc = _lib.load().dipsb_synth_fill_device(device, d_dst, first_frame, n_frames, width, height, fmt, seed, profile,
+                                             stream)
+    if rc != 0:
+        raise DipsError(rc, _lib.load().dipsb_last_error(None).decode())
+
+
+def _host_ptr(a: np.ndarray) -> int:
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return a.ctypes.data
+
+
+class Context:
+    """Owner of one dipsb_ctx.  Mirrors the reference's ComputeState / DiPsCompute lifetime (create once per clip
+    geometry and property set; dips/src/gpu/mod.rs:59, dips_alt/src/dips_compute/mod.rs:270)."""
+
+    def __init__(self, width: int, height: int, fmt: int = FMT_RGBX8, mode: int = MODE_OVERALL, threshold: int = 0,
+                 chroma: int = CHROMA_NONE, device: int = 0, colorize: bool = False, filt: int = FILTER_NONE,
+                 sigmoid_scalar: float = 5.0, spatial_window: int = 1):
+        self._lib = _lib.load()
+        cfg = _lib.Config()
+        self._lib.dipsb_default_config(C.byref(cfg))
+        cfg.device, cfg.width, cfg.height, cfg.format, cfg.mode = device, width, height, fmt, mode
+        cfg.chroma, cfg.threshold, cfg.colorize, cfg.filter = chroma, threshold, int(colorize), filt
+        cfg.sigmoid_scalar, cfg.spatial_window = sigmoid_scalar, spatial_window
+        h = C.c_void_p()
+        rc = self._lib.dipsb_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise DipsError(rc, self._lib.dipsb_last_error(None).decode())
+        self._h = h
+        self.width, self.height, self.fmt, self.mode = width, height, fmt, mode
+        self.npx = width * height
+        self.bpp = bytes_per_pixel(fmt)
+        self.frame_bytes = self.npx * self.bpp
+
+    # -- plumbing ---------------------------------------------------------------------------------------------
+    def _ck(self, rc: int) -> int:
+        if rc < 0:
+            raise DipsError(rc, self._lib.dipsb_last_error(self._h).decode())
+        return rc
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.dipsb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self) -> None:
+        self._ck(self._lib.dipsb_reset(self._h))
+
+    def set_threshold(self, tau: int) -> None:
+        self._ck(self._lib.dipsb_set_threshold(self._h, tau))
+
+    def set_stream(self, stream: int) -> None:
+        self._ck(self._lib.dipsb_set_stream(self._h, stream))
+
+    def synchronize(self) -> None:
+        self._ck(self._lib.dipsb_synchronize(self._h))
+
+    def set_tuning(self, stages: int = 0, tile_px: int = 0, segments: int = 0) -> None:
+        self._ck(self._lib.dipsb_set_tuning(self._h, stages, tile_px, segments))
+
+    def enable_timing(self, on: bool = True) -> None:
+        self._ck(self._lib.dipsb_enable_timing(self._h, int(on)))
+
+    def clip_kernel_time(self):
+        """(total milliseconds, launches) of the clip kernel since the last call; synchronises."""
+        ms, n = C.c_double(), C.c_uint64()
+        self._ck(self._lib.dipsb_clip_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def last_plan(self) -> dict:
+        out = (C.c_uint32 * 8)()
+        self._ck(self._lib.dipsb_last_plan(self._h, C.byref(out)))
+        return dict(tiles=out[0], segments=out[1], threads=out[2], stages=out[3], blocks_per_sm=out[4],
+                    tile_px=out[5], smem_bytes=out[6], tma_path=bool(out[7]))
+
+    # -- state plane ------------------------------------------------------------------------------------------
+    def prime_device(self, d_frame: int) -> None:
+        self._ck(self._lib.dipsb_prime_device(self._h, d_frame))
+
+    def prime_median4_device(self, d_frames: int, stride: int) -> None:
+        self._ck(self._lib.dipsb_prime_median4_device(self._h, d_frames, stride))
+
+    def prime_host(self, frame: np.ndarray) -> None:
+        frame = np.ascontiguousarray(frame, dtype=np.uint8)
+        if frame.size != self.frame_bytes:
+            raise ValueError("frame size mismatch")
+        self._ck(self._lib.dipsb_prime_host(self._h, _host_ptr(frame)))
+
+    def state_plane_device(self) -> int:
+        p = C.c_void_p()
+        self._ck(self._lib.dipsb_state_plane_device(self._h, C.byref(p)))
+        return int(p.value)
+
+    def mark_state_valid(self, valid: bool = True) -> None:
+        self._ck(self._lib.dipsb_mark_state_valid(self._h, int(valid)))
+
+    def get_state_plane(self) -> np.ndarray:
+        out = np.empty(self.npx, np.uint16)
+        self._ck(self._lib.dipsb_get_state_plane(self._h, _host_ptr(out)))
+        return out
+
+    # -- batch ------------------------------------------------------------------------------------------------
+    def run_clip_device(self, d_frames: int, n_frames: int, stride: int | None = None, first_frame: int = 0) -> None:
+        self._ck(self._lib.dipsb_run_clip_device(self._h, d_frames, n_frames, stride or self.frame_bytes, first_frame))
+
+    def run_clip_host(self, frames, n_frames: int | None = None, stride: int | None = None, first_frame: int = 0) -> None:
+        """frames: numpy uint8 array [n, frame_bytes] or a raw host address (then n_frames is required)."""
+        if isinstance(frames, np.ndarray):
+            if frames.dtype != np.uint8 or not frames.flags["C_CONTIGUOUS"]:
+                raise ValueError("frames must be a C-contiguous uint8 array")
+            n = frames.shape[0] if n_frames is None else n_frames
+            st = stride or (frames.strides[0] if frames.ndim > 1 else self.frame_bytes)
+            ptr = _host_ptr(frames)
+        else:
+            ptr, n, st = int(frames), int(n_frames), stride or self.frame_bytes
+        self._ck(self._lib.dipsb_run_clip_host(self._h, ptr, n, st, first_frame))
+
+    # -- streaming --------------------------------------------------------------------------------------------
+    def push_frame(self, frame: np.ndarray, fmt: int | None = None, want_rgba: bool = True, stride: int | None = None):
+        """Returns (status, rgba or None, (frame_index, sad, count)).  status NOT_READY == passthrough frame."""
+        fmt = self.fmt if fmt is None else fmt
+        frame = np.ascontiguousarray(frame, dtype=np.uint8)
+        stride = stride or self.width * bytes_per_pixel(fmt)
+        if frame.size < stride * self.height:
+            raise ValueError("frame smaller than height*stride")
+        out = np.empty(self.npx * 4, np.uint8) if want_rgba else None
+        st = _lib.FrameStats()
+        rc = self._ck(self._lib.dipsb_push_frame(self._h, _host_ptr(frame), self.width, self.height, stride, fmt,
+                                                 _host_ptr(out) if want_rgba else None, C.byref(st)))
+        return rc, out, (int(st.frame_index), int(st.sad), int(st.count))
+
+    def snapshot(self) -> None:
+        self._ck(self._lib.dipsb_snapshot(self._h))
+
+    # -- results ----------------------------------------------------------------------------------------------
+    @property
+    def frames_processed(self) -> int:
+        return int(self._lib.dipsb_frames_processed(self._h))
+
+    def get_accumulators(self):
+        s = np.empty(self.npx, np.uint32)
+        c = np.empty(self.npx, np.uint32)
+        self._ck(self._lib.dipsb_get_accumulators(self._h, _host_ptr(s), _host_ptr(c)))
+        return s, c
+
+    def set_accumulators(self, acc_sum: np.ndarray, acc_cnt: np.ndarray) -> None:
+        s = np.ascontiguousarray(acc_sum, dtype=np.uint32)
+        c = np.ascontiguousarray(acc_cnt, dtype=np.uint32)
+        if s.size != self.npx or c.size != self.npx:
+            raise ValueError("accumulator size mismatch")
+        self._ck(self._lib.dipsb_set_accumulators(self._h, _host_ptr(s), _host_ptr(c)))
+
+    def accumulators_device(self):
+        """(device address, n_elems): one u32[2*n_elems] buffer, sum plane then count plane, internal tile order."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._lib.dipsb_accumulators_device(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def get_scalars(self, first: int, n: int):
+        sad = np.empty(n, np.uint64)
+        cnt = np.empty(n, np.uint64)
+        self._ck(self._lib.dipsb_get_scalars(self._h, first, n, _host_ptr(sad), _host_ptr(cnt)))
+        return sad, cnt
+
+    def get_intensity_map(self, n_eff: int) -> np.ndarray:
+        out = np.empty(self.npx, np.float32)
+        self._ck(self._lib.dipsb_get_intensity_map(self._h, n_eff, _host_ptr(out)))
+        return out
+
+    def get_frame_means(self, first: int, n: int) -> np.ndarray:
+        out = np.empty(n, np.float32)
+        self._ck(self._lib.dipsb_get_frame_means(self._h, first, n, _host_ptr(out)))
+        return out

@@ -1,0 +1,708 @@
+// api.cu -- the C ABI of libdips_b200.so (include/dips_b200.h): context, planning, launches, copies.
+// Host-side runtime only; the device code is in clip_kernel.cu / aux_kernels.cu.  No CPU fallback anywhere: every
+// result is produced by a CUDA kernel, and dipsb_create fails when there is no usable device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/dips_b200.h"
+#include "dipsb_internal.h"
+
+namespace dipsb {
+uint64_t launch_count_value();
+}
+using namespace dipsb;
+
+struct dipsb_ctx {
+    dipsb_config cfg;
+    Geometry g;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    uint16_t* state[2] = {nullptr, nullptr};   // u16[n_elems] each, zero padded past npx
+    int state_cur = 0;
+    bool state_valid = false;
+    bool snapshot_pending = false;
+    uint32_t* acc = nullptr;                   // u32[2*n_elems]: sum plane then count plane, internal order
+    uint32_t* planar = nullptr;                // u32[2*npx] scratch for get/set in pixel order
+    uint64_t* d_sad = nullptr;                 // per logical frame index
+    uint64_t* d_cnt = nullptr;
+    uint64_t scal_cap = 0, scal_hi = 0;
+    uint32_t* partials = nullptr;
+    uint64_t partial_cap = 0;                  // in u32 words
+    uint64_t frames_processed = 0;
+    uint64_t stream_index = 0;                 // logical index of the next pushed frame
+    // streaming staging
+    uint8_t* d_frame = nullptr; size_t d_frame_bytes = 0;
+    uint8_t* d_rgba = nullptr;
+    uint8_t* h_pin = nullptr; size_t h_pin_bytes = 0;   // pinned bounce buffer (frame in / rgba out)
+    uint64_t* h_stat = nullptr;                          // pinned [2]
+    // host clip staging
+    uint8_t* h_chunk[2] = {nullptr, nullptr};
+    uint8_t* d_chunk[2] = {nullptr, nullptr};
+    size_t chunk_bytes = 0;
+    uint32_t tune_stages = 0, tune_tile_px = 0, tune_segments = 0;
+    uint32_t last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;              // start/stop pairs around clip kernel launches
+    size_t tev_used = 0;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int32_t fail(dipsb_ctx* c, int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CK(c, call)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail((c), DIPSB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+static int bpp_of(int format) { return (format == DIPSB_FMT_RGB8 || format == DIPSB_FMT_BGR8) ? 3 : 4; }
+
+static int chan_byte_of(int format, int chroma) {
+    if (chroma == DIPSB_CHROMA_NONE) return -1;
+    const bool bgr = (format == DIPSB_FMT_BGR8 || format == DIPSB_FMT_BGRX8);
+    const int rgb_index = chroma - 1;  // 0 R, 1 G, 2 B
+    return bgr ? 2 - rgb_index : rgb_index;
+}
+
+// ---- planning ------------------------------------------------------------------------------------------------------
+// Pick block size (=> tile), pipeline depth and residency so that (a) the tiles fill the resident slots of the 148 SMs
+// in whole waves, (b) at least ~64 KB of frame bytes are in flight per SM, (c) as many threads as possible are resident.
+static void plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_tile_px) {
+    double best_score = -1.0;
+    uint32_t best_thr = 256, best_stages = 4, best_occ = 1;
+    const uint32_t thr_lo = force_tile_px ? 32 : 128, thr_hi = force_tile_px ? 1024 : 512;
+    for (uint32_t thr = thr_lo; thr <= thr_hi; thr += 32) {
+        if (force_tile_px && thr * kPxPerThread != force_tile_px) continue;
+        uint32_t stages = force_stages ? force_stages : 3;
+        int occ = clip_occupancy(g, thr, stages);
+        if (occ <= 0) continue;
+        if (!force_stages) {
+            const uint64_t tile_bytes = (uint64_t)thr * kPxPerThread * g.bpp;
+            while (stages < (uint32_t)kMaxStages && (uint64_t)occ * (stages - 1) * tile_bytes < 64 * 1024 &&
+                   clip_occupancy(g, thr, stages + 1) == occ)
+                ++stages;
+        }
+        const uint64_t slots = (uint64_t)occ * g.num_sms;
+        const uint64_t tiles = (g.npx + (uint64_t)thr * kPxPerThread - 1) / ((uint64_t)thr * kPxPerThread);
+        double util = 1.0;
+        if (tiles >= slots) {
+            const uint64_t waves = (tiles + slots - 1) / slots;
+            util = (double)tiles / (double)(waves * slots);
+        }
+        const double resident = std::min(1.0, (double)(occ * thr) / 1024.0);
+        // utilisation dominates (2 % buckets), then resident threads, then a mild preference for larger tiles
+        const double score = (double)(int)(util * 50.0) * 100.0 + resident * 10.0 + (double)thr / 1024.0;
+        if (score > best_score) { best_score = score; best_thr = thr; best_stages = stages; best_occ = (uint32_t)occ; }
+    }
+    g.threads = best_thr;
+    g.tile_px = best_thr * kPxPerThread;
+    g.n_tiles = (uint32_t)((g.npx + g.tile_px - 1) / g.tile_px);
+    g.n_elems = (uint64_t)g.n_tiles * g.tile_px;
+    g.stages = best_stages;
+    g.blocks_per_sm = best_occ;
+}
+
+static uint32_t plan_segments(const dipsb_ctx* c, uint64_t n_frames) {
+    if (c->tune_segments) return (uint32_t)std::min<uint64_t>(c->tune_segments, n_frames);
+    const uint64_t slots = (uint64_t)c->g.blocks_per_sm * c->g.num_sms;
+    if (c->g.n_tiles >= slots) return 1;
+    uint64_t segs = slots / c->g.n_tiles;                 // fill the resident slots once
+    const uint64_t by_len = std::max<uint64_t>(1, n_frames / 32);   // keep segments >= 32 frames (flush + ref overhead)
+    segs = std::min(segs, by_len);
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(segs, n_frames));
+}
+
+// ---- lifetime ------------------------------------------------------------------------------------------------------
+extern "C" int32_t dipsb_abi_version(void) { return DIPSB_ABI_VERSION; }
+
+extern "C" void dipsb_default_config(dipsb_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = (uint32_t)sizeof *cfg;
+    cfg->format = DIPSB_FMT_RGBX8;
+    cfg->mode = DIPSB_MODE_OVERALL;
+    cfg->chroma = DIPSB_CHROMA_NONE;
+    cfg->filter = DIPSB_FILTER_NONE;       // DiPsProperties::new(): Unfiltered, sensitivity 5, window 1 (dips/src/lib.rs:75-86)
+    cfg->sigmoid_scalar = 5.0f;
+    cfg->spatial_window = 1;
+}
+
+static void free_all(dipsb_ctx* c) {
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 2; ++k) {
+        if (c->state[k]) cudaFree(c->state[k]);
+        if (c->ev_copy[k]) cudaEventDestroy(c->ev_copy[k]);
+        if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+        if (c->h_chunk[k]) cudaFreeHost(c->h_chunk[k]);
+        if (c->d_chunk[k]) cudaFree(c->d_chunk[k]);
+    }
+    cudaFree(c->acc); cudaFree(c->planar); cudaFree(c->d_sad); cudaFree(c->d_cnt); cudaFree(c->partials);
+    cudaFree(c->d_frame); cudaFree(c->d_rgba);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_stat) cudaFreeHost(c->h_stat);
+    for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+}
+
+static int32_t alloc_planes(dipsb_ctx* c) {
+    const Geometry& g = c->g;
+    for (int k = 0; k < 2; ++k) {
+        CK(c, cudaMalloc(&c->state[k], g.n_elems * sizeof(uint16_t)));
+        CK(c, cudaMemsetAsync(c->state[k], 0, g.n_elems * sizeof(uint16_t), c->stream));
+    }
+    CK(c, cudaMalloc(&c->acc, 2 * g.n_elems * sizeof(uint32_t)));
+    CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
+    CK(c, cudaMalloc(&c->planar, 2 * g.npx * sizeof(uint32_t)));
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(dipsb_config))
+        return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: struct_size %u != %zu", cfg->struct_size, sizeof(dipsb_config));
+    if (cfg->width == 0 || cfg->height == 0) return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: empty frame");
+    if (cfg->format < 0 || cfg->format > 3) return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: bad format %d", cfg->format);
+    if (cfg->mode != DIPSB_MODE_OVERALL && cfg->mode != DIPSB_MODE_PERFRAME)
+        return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: bad mode %d", cfg->mode);
+    if (cfg->chroma < 0 || cfg->chroma > 3) return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: bad chroma %d", cfg->chroma);
+    if (cfg->spatial_window != 1 && cfg->spatial_window != 0)
+        return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: spatial_window %d not implemented (only 1)", cfg->spatial_window);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, DIPSB_ERR_CUDA, "dipsb_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: device %d of %d", cfg->device, ndev);
+
+    dipsb_ctx* c = new (std::nothrow) dipsb_ctx();
+    if (!c) return fail(nullptr, DIPSB_ERR_NOMEM, "dipsb_create: out of host memory");
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(c->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, DIPSB_ERR_CUDA, "dipsb_create: cudaSetDevice/GetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+        delete c;
+        return fail(nullptr, DIPSB_ERR_CUDA, "dipsb_create: device sm_%d%d is not Blackwell (sm_100a required)", prop.major, prop.minor);
+    }
+    Geometry& g = c->g;
+    g.width = cfg->width; g.height = cfg->height; g.npx = (uint64_t)cfg->width * cfg->height;
+    g.format = cfg->format; g.bpp = bpp_of(cfg->format); g.chan_byte = chan_byte_of(cfg->format, cfg->chroma);
+    g.num_sms = (uint32_t)prop.multiProcessorCount;
+    plan_geometry(g, 0, 0);
+    int32_t rc = DIPSB_OK;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        rc = fail(nullptr, DIPSB_ERR_CUDA, "dipsb_create: stream creation failed");
+    c->stream = c->own_stream;
+    for (int k = 0; k < 2 && rc == DIPSB_OK; ++k)
+        if (cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(nullptr, DIPSB_ERR_CUDA, "dipsb_create: event creation failed");
+    if (rc == DIPSB_OK) rc = alloc_planes(c);
+    if (rc == DIPSB_OK && cudaMallocHost(&c->h_stat, 2 * sizeof(uint64_t)) != cudaSuccess)
+        rc = fail(c, DIPSB_ERR_NOMEM, "dipsb_create: pinned allocation failed");
+    if (rc != DIPSB_OK) {
+        g_create_err = c->err.empty() ? g_create_err : c->err;
+        free_all(c);
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return DIPSB_OK;
+}
+
+extern "C" void dipsb_destroy(dipsb_ctx* c) {
+    if (!c) return;
+    free_all(c);
+    delete c;
+}
+
+extern "C" const char* dipsb_last_error(const dipsb_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int32_t dipsb_reset(dipsb_ctx* c) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const Geometry& g = c->g;
+    CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
+    for (int k = 0; k < 2; ++k) CK(c, cudaMemsetAsync(c->state[k], 0, g.n_elems * sizeof(uint16_t), c->stream));
+    if (c->scal_cap) {
+        CK(c, cudaMemsetAsync(c->d_sad, 0, c->scal_cap * sizeof(uint64_t), c->stream));
+        CK(c, cudaMemsetAsync(c->d_cnt, 0, c->scal_cap * sizeof(uint64_t), c->stream));
+    }
+    c->state_valid = false; c->snapshot_pending = false; c->state_cur = 0;
+    c->frames_processed = 0; c->stream_index = 0; c->scal_hi = 0;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_set_threshold(dipsb_ctx* c, uint32_t threshold) {
+    if (!c) return DIPSB_ERR_INVALID;
+    c->cfg.threshold = threshold;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_set_stream(dipsb_ctx* c, void* stream) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));   // keep ordering of already issued work
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_synchronize(dipsb_ctx* c) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile_px, uint32_t segments) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (stages > (uint32_t)kMaxStages || (stages && stages < 2)) return fail(c, DIPSB_ERR_INVALID, "set_tuning: stages %u outside [2,%d]", stages, kMaxStages);
+    if (tile_px && (tile_px % (32 * kPxPerThread) || tile_px < 32u * kPxPerThread || tile_px > 1024u * kPxPerThread))
+        return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u must be a multiple of %d in [%d, %d]", tile_px, 32 * kPxPerThread, 32 * kPxPerThread, 1024 * kPxPerThread);
+    const bool regeo = (stages != c->tune_stages) || (tile_px != c->tune_tile_px);
+    c->tune_segments = segments;
+    if (!regeo) return DIPSB_OK;
+    if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_tuning: geometry can only change on a fresh or reset context");
+    CK(c, cudaStreamSynchronize(c->stream));
+    Geometry g = c->g;
+    if (tile_px) {
+        g.threads = tile_px / kPxPerThread;
+        if (clip_occupancy(g, g.threads, stages ? stages : 3) <= 0) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u do not fit", tile_px, stages);
+    }
+    plan_geometry(g, stages, tile_px);
+    if (clip_occupancy(g, g.threads, g.stages) <= 0) return fail(c, DIPSB_ERR_INVALID, "set_tuning: configuration does not fit in shared memory");
+    for (int k = 0; k < 2; ++k) { cudaFree(c->state[k]); c->state[k] = nullptr; }
+    cudaFree(c->acc); c->acc = nullptr;
+    cudaFree(c->planar); c->planar = nullptr;
+    c->g = g;
+    c->tune_stages = stages; c->tune_tile_px = tile_px;
+    c->state_valid = false;
+    return alloc_planes(c);
+}
+
+extern "C" int32_t dipsb_last_plan(const dipsb_ctx* c, uint32_t out[8]) {
+    if (!c || !out) return DIPSB_ERR_INVALID;
+    memcpy(out, c->last_plan, sizeof c->last_plan);
+    out[0] = c->g.n_tiles; out[2] = c->g.threads; out[3] = c->g.stages; out[4] = c->g.blocks_per_sm; out[5] = c->g.tile_px;
+    out[6] = (uint32_t)clip_smem_bytes(c->g, c->g.stages);
+    return DIPSB_OK;
+}
+
+// ---- state plane ---------------------------------------------------------------------------------------------------
+extern "C" int32_t dipsb_prime_device(dipsb_ctx* c, const void* d_frame) {
+    if (!c || !d_frame) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, launch_prime(c->g, (const uint8_t*)d_frame, c->state[c->state_cur], c->stream));
+    c->state_valid = true;
+    c->snapshot_pending = false;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_prime_median4_device(dipsb_ctx* c, const void* d_frames, uint64_t stride) {
+    if (!c || !d_frames) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (stride < c->g.npx * c->g.bpp) return fail(c, DIPSB_ERR_INVALID, "prime_median4: stride smaller than a frame");
+    CK(c, launch_prime_median4(c->g, (const uint8_t*)d_frames, stride, c->state[c->state_cur], c->stream));
+    c->state_valid = true;
+    c->snapshot_pending = false;
+    return DIPSB_OK;
+}
+
+static int32_t ensure_frame_staging(dipsb_ctx* c, size_t in_bytes) {
+    const size_t rgba = c->g.npx * 4;
+    const size_t need_pin = std::max(in_bytes, rgba);
+    if (c->d_frame_bytes < in_bytes) {
+        cudaFree(c->d_frame); c->d_frame = nullptr;
+        CK(c, cudaMalloc(&c->d_frame, in_bytes));
+        c->d_frame_bytes = in_bytes;
+    }
+    if (!c->d_rgba) CK(c, cudaMalloc(&c->d_rgba, rgba));
+    if (c->h_pin_bytes < need_pin) {
+        if (c->h_pin) cudaFreeHost(c->h_pin);
+        c->h_pin = nullptr;
+        CK(c, cudaMallocHost(&c->h_pin, need_pin));
+        c->h_pin_bytes = need_pin;
+    }
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_prime_host(dipsb_ctx* c, const uint8_t* frame) {
+    if (!c || !frame) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const size_t fb = c->g.npx * c->g.bpp;
+    int32_t rc = ensure_frame_staging(c, fb);
+    if (rc) return rc;
+    memcpy(c->h_pin, frame, fb);
+    CK(c, cudaMemcpyAsync(c->d_frame, c->h_pin, fb, cudaMemcpyHostToDevice, c->stream));
+    rc = dipsb_prime_device(c, c->d_frame);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_state_plane_device(dipsb_ctx* c, void** d_state) {
+    if (!c || !d_state) return DIPSB_ERR_INVALID;
+    *d_state = c->state[c->state_cur];
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_mark_state_valid(dipsb_ctx* c, int32_t valid) {
+    if (!c) return DIPSB_ERR_INVALID;
+    c->state_valid = valid != 0;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_get_state_plane(dipsb_ctx* c, uint16_t* out) {
+    if (!c || !out) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(out, c->state[c->state_cur], c->g.npx * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return DIPSB_OK;
+}
+
+// ---- scalars storage -----------------------------------------------------------------------------------------------
+static int32_t ensure_scalars(dipsb_ctx* c, uint64_t upto) {
+    if (upto <= c->scal_cap) return DIPSB_OK;
+    uint64_t cap = std::max<uint64_t>(1024, c->scal_cap);
+    while (cap < upto) cap *= 2;
+    uint64_t *ns = nullptr, *nc = nullptr;
+    CK(c, cudaMalloc(&ns, cap * sizeof(uint64_t)));
+    CK(c, cudaMalloc(&nc, cap * sizeof(uint64_t)));
+    CK(c, cudaMemsetAsync(ns, 0, cap * sizeof(uint64_t), c->stream));
+    CK(c, cudaMemsetAsync(nc, 0, cap * sizeof(uint64_t), c->stream));
+    if (c->scal_cap) {
+        CK(c, cudaMemcpyAsync(ns, c->d_sad, c->scal_cap * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(nc, c->d_cnt, c->scal_cap * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_sad); cudaFree(c->d_cnt);
+    }
+    c->d_sad = ns; c->d_cnt = nc; c->scal_cap = cap;
+    return DIPSB_OK;
+}
+
+// ---- batch ---------------------------------------------------------------------------------------------------------
+static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first) {
+    const Geometry& g = c->g;
+    if (n == 0) return DIPSB_OK;
+    if (n > 0x7FFFFFFFull) return fail(c, DIPSB_ERR_INVALID, "run_clip: too many frames in one call");
+    if (stride < g.npx * g.bpp) return fail(c, DIPSB_ERR_INVALID, "run_clip: stride %llu smaller than a frame", (unsigned long long)stride);
+    int32_t rc = ensure_scalars(c, first + n);
+    if (rc) return rc;
+    if (!c->state_valid) {   // frame 0 of the call is the reference (overall) / has no predecessor (per-frame): D = 0
+        CK(c, launch_prime(g, d_frames, c->state[c->state_cur], c->stream));
+        c->state_valid = true;
+    }
+    const bool aligned = (((uintptr_t)d_frames | stride) & 15u) == 0;
+    const uint32_t tau = c->cfg.threshold;
+    if (aligned) {
+        const uint32_t segs = plan_segments(c, n);
+        const uint32_t words = g.n_tiles * (g.threads / 32);
+        const uint64_t need = n * (uint64_t)words;
+        if (need > c->partial_cap) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->partials); c->partials = nullptr; c->partial_cap = 0;
+            CK(c, cudaMalloc(&c->partials, need * sizeof(uint32_t)));
+            c->partial_cap = need;
+        }
+        ClipArgs a;
+        a.frames = d_frames; a.stride = stride; a.n_frames = (uint32_t)n; a.n_segments = segs;
+        a.state_in = c->state[c->state_cur]; a.state_out = c->state[c->state_cur ^ 1];
+        a.acc_sum = c->acc; a.acc_cnt = c->acc + g.n_elems; a.partials = c->partials;
+        a.tau = tau; a.mode = c->cfg.mode;
+        if (c->timing) {
+            if (c->tev_used + 2 > c->tev.size()) {
+                cudaEvent_t e0, e1;
+                CK(c, cudaEventCreate(&e0));
+                CK(c, cudaEventCreate(&e1));
+                c->tev.push_back(e0); c->tev.push_back(e1);
+            }
+            CK(c, cudaEventRecord(c->tev[c->tev_used], c->stream));
+        }
+        CK(c, launch_clip(g, a, c->stream));
+        if (c->timing) {
+            CK(c, cudaEventRecord(c->tev[c->tev_used + 1], c->stream));
+            c->tev_used += 2;
+        }
+        CK(c, launch_finalize_scalars(g, c->partials, (uint32_t)n, words, c->d_sad + first, c->d_cnt + first, c->stream));
+        if (c->cfg.mode == DIPSB_MODE_PERFRAME) c->state_cur ^= 1;
+        c->last_plan[1] = segs;
+        c->last_plan[7] = 1;
+    } else {   // unaligned base/stride: per-frame kernel (TMA bulk copies need 16-byte alignment)
+        CK(c, cudaMemsetAsync(c->d_sad + first, 0, n * sizeof(uint64_t), c->stream));
+        CK(c, cudaMemsetAsync(c->d_cnt + first, 0, n * sizeof(uint64_t), c->stream));
+        for (uint64_t k = 0; k < n; ++k) {
+            FrameArgs f;
+            f.frame = d_frames + k * stride; f.pitch = (uint64_t)g.width * g.bpp; f.format = g.format; f.chan_byte = g.chan_byte;
+            f.state_in = c->state[c->state_cur];
+            f.state_out = c->cfg.mode == DIPSB_MODE_PERFRAME ? c->state[c->state_cur] : nullptr;
+            f.acc_sum = c->acc; f.acc_cnt = c->acc + g.n_elems;
+            f.sad = c->d_sad + first + k; f.cnt = c->d_cnt + first + k; f.out_rgba = nullptr;
+            f.tau = tau; f.accumulate = 1; f.colorize = 0; f.filter = DIPSB_FILTER_NONE; f.sig_scalar = 5.0f;
+            CK(c, launch_frame(g, f, c->stream));
+        }
+        c->last_plan[1] = 0;
+        c->last_plan[7] = 0;
+    }
+    c->frames_processed += n;
+    c->scal_hi = std::max(c->scal_hi, first + n);
+    c->stream_index = first + n;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_run_clip_device(dipsb_ctx* c, const void* d_frames, uint64_t n_frames, uint64_t stride, uint64_t first) {
+    if (!c || (!d_frames && n_frames)) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    return run_clip_on_stream(c, (const uint8_t*)d_frames, n_frames, stride, first);
+}
+
+extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint64_t n, uint64_t stride, uint64_t first) {
+    if (!c || (!frames && n)) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const Geometry& g = c->g;
+    const uint64_t fb = g.npx * g.bpp;
+    if (n == 0) return DIPSB_OK;
+    if (stride < fb) return fail(c, DIPSB_ERR_INVALID, "run_clip_host: stride smaller than a frame");
+    // frames are re-packed on the device side at a 16-byte aligned pitch so that the TMA path is always taken
+    const uint64_t dpitch = (fb + 15) & ~15ull;
+    const uint64_t per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (256ull << 20) / dpitch));
+    const size_t cbytes = per_chunk * dpitch;
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+    if (c->chunk_bytes < cbytes) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaStreamSynchronize(c->copy_stream));
+        for (int k = 0; k < 2; ++k) {
+            if (c->h_chunk[k]) cudaFreeHost(c->h_chunk[k]);
+            if (c->d_chunk[k]) cudaFree(c->d_chunk[k]);
+            c->h_chunk[k] = nullptr; c->d_chunk[k] = nullptr;
+        }
+        c->chunk_bytes = 0;
+        for (int k = 0; k < 2; ++k) {
+            CK(c, cudaMalloc(&c->d_chunk[k], cbytes));
+            CK(c, cudaMallocHost(&c->h_chunk[k], cbytes));
+        }
+        c->chunk_bytes = cbytes;
+    }
+    bool used[2] = {false, false};
+    uint64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const uint64_t m = std::min(per_chunk, n - done);
+        const uint8_t* src = frames + done * stride;
+        if (used[slot]) CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));   // kernels finished with d_chunk[slot]
+        if (pinned) {
+            CK(c, cudaMemcpy2DAsync(c->d_chunk[slot], dpitch, src, stride, fb, m, cudaMemcpyHostToDevice, c->copy_stream));
+        } else {
+            if (used[slot]) CK(c, cudaEventSynchronize(c->ev_copy[slot]));                 // previous H2D from h_chunk[slot] done
+            for (uint64_t k = 0; k < m; ++k) memcpy(c->h_chunk[slot] + k * dpitch, src + k * stride, fb);
+            CK(c, cudaMemcpyAsync(c->d_chunk[slot], c->h_chunk[slot], m * dpitch, cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        CK(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+        CK(c, cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
+        int32_t rc = run_clip_on_stream(c, c->d_chunk[slot], m, dpitch, first + done);
+        if (rc) return rc;
+        CK(c, cudaEventRecord(c->ev_done[slot], c->stream));
+        used[slot] = true;
+        slot ^= 1;
+        done += m;
+    }
+    return DIPSB_OK;
+}
+
+// ---- streaming -----------------------------------------------------------------------------------------------------
+extern "C" int32_t dipsb_snapshot(dipsb_ctx* c) {
+    if (!c) return DIPSB_ERR_INVALID;
+    c->snapshot_pending = true;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t width, uint32_t height, uint32_t stride,
+                                    int32_t format, uint8_t* out_rgba, dipsb_frame_stats* stats) {
+    if (!c || !px) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const Geometry& g = c->g;
+    if (width != g.width || height != g.height) return fail(c, DIPSB_ERR_INVALID, "push_frame: %ux%u does not match the context's %ux%u", width, height, g.width, g.height);
+    if (format < 0 || format > 3) return fail(c, DIPSB_ERR_INVALID, "push_frame: bad format %d", format);
+    const int bpp = bpp_of(format);
+    const uint64_t row = (uint64_t)width * bpp;
+    if (stride < row) return fail(c, DIPSB_ERR_INVALID, "push_frame: stride %u smaller than a row (%llu)", stride, (unsigned long long)row);
+    const size_t fb = row * height;
+    int32_t rc = ensure_frame_staging(c, fb);
+    if (rc) return rc;
+    rc = ensure_scalars(c, c->stream_index + 1);
+    if (rc) return rc;
+    // the input slice is borrowed for the call only (frame_extractor.rs:224-226): copy it out before returning
+    if (stride == row) memcpy(c->h_pin, px, fb);
+    else for (uint32_t y = 0; y < height; ++y) memcpy(c->h_pin + (uint64_t)y * row, px + (uint64_t)y * stride, row);
+    CK(c, cudaMemcpyAsync(c->d_frame, c->h_pin, fb, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t idx = c->stream_index;
+    const bool establishes = !c->state_valid || c->snapshot_pending;
+    FrameArgs f;
+    f.frame = c->d_frame; f.pitch = row; f.format = format; f.chan_byte = chan_byte_of(format, c->cfg.chroma);
+    f.acc_sum = c->acc; f.acc_cnt = c->acc + g.n_elems;
+    f.sad = c->d_sad + idx; f.cnt = c->d_cnt + idx;
+    f.tau = c->cfg.threshold; f.colorize = c->cfg.colorize; f.filter = c->cfg.filter; f.sig_scalar = c->cfg.sigmoid_scalar;
+    CK(c, cudaMemsetAsync(c->d_sad + idx, 0, sizeof(uint64_t), c->stream));
+    CK(c, cudaMemsetAsync(c->d_cnt + idx, 0, sizeof(uint64_t), c->stream));
+    if (establishes) {
+        // this frame becomes the reference: D = 0 for it, output is the input passed through (dips/src/lib.rs:241-245)
+        f.state_in = c->state[c->state_cur]; f.state_out = c->state[c->state_cur]; f.out_rgba = nullptr; f.accumulate = 0;
+        CK(c, launch_frame(g, f, c->stream));
+        if (out_rgba) CK(c, launch_passthrough_rgba(g, c->d_frame, row, format, c->d_rgba, c->stream));
+        c->state_valid = true;
+        c->snapshot_pending = false;
+    } else {
+        f.state_in = c->state[c->state_cur];
+        f.state_out = c->cfg.mode == DIPSB_MODE_PERFRAME ? c->state[c->state_cur] : nullptr;
+        f.out_rgba = out_rgba ? c->d_rgba : nullptr; f.accumulate = 1;
+        CK(c, launch_frame(g, f, c->stream));
+    }
+    if (out_rgba) CK(c, cudaMemcpyAsync(c->h_pin, c->d_rgba, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&c->h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&c->h_stat[1], c->d_cnt + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (out_rgba) memcpy(out_rgba, c->h_pin, g.npx * 4);
+    if (stats) { stats->frame_index = idx; stats->sad = c->h_stat[0]; stats->count = c->h_stat[1]; }
+    c->stream_index = idx + 1;
+    c->frames_processed += 1;
+    c->scal_hi = std::max(c->scal_hi, idx + 1);
+    return establishes ? DIPSB_NOT_READY : DIPSB_OK;
+}
+
+// ---- results -------------------------------------------------------------------------------------------------------
+extern "C" uint64_t dipsb_frames_processed(const dipsb_ctx* c) { return c ? c->frames_processed : 0; }
+
+extern "C" int32_t dipsb_get_accumulators(dipsb_ctx* c, uint32_t* acc_sum, uint32_t* acc_cnt) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const Geometry& g = c->g;
+    if (acc_sum) {
+        CK(c, launch_unpermute(g, c->acc, c->planar, c->stream));
+        CK(c, cudaMemcpyAsync(acc_sum, c->planar, g.npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (acc_cnt) {
+        CK(c, launch_unpermute(g, c->acc + g.n_elems, c->planar + g.npx, c->stream));
+        CK(c, cudaMemcpyAsync(acc_cnt, c->planar + g.npx, g.npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_set_accumulators(dipsb_ctx* c, const uint32_t* acc_sum, const uint32_t* acc_cnt) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const Geometry& g = c->g;
+    if (acc_sum) {
+        CK(c, cudaMemcpyAsync(c->planar, acc_sum, g.npx * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(c, launch_permute(g, c->planar, c->acc, c->stream));
+    }
+    if (acc_cnt) {
+        CK(c, cudaMemcpyAsync(c->planar + g.npx, acc_cnt, g.npx * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(c, launch_permute(g, c->planar + g.npx, c->acc + g.n_elems, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_accumulators_device(dipsb_ctx* c, void** d_acc, uint64_t* n_elems) {
+    if (!c || !d_acc || !n_elems) return DIPSB_ERR_INVALID;
+    *d_acc = c->acc;
+    *n_elems = c->g.n_elems;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_get_scalars(dipsb_ctx* c, uint64_t first, uint64_t n, uint64_t* sad, uint64_t* cnt) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return DIPSB_OK;
+    if (first + n > c->scal_hi) return fail(c, DIPSB_ERR_INVALID, "get_scalars: frames [%llu,%llu) not processed (have %llu)", (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)c->scal_hi);
+    if (sad) CK(c, cudaMemcpyAsync(sad, c->d_sad + first, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (cnt) CK(c, cudaMemcpyAsync(cnt, c->d_cnt + first, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_get_intensity_map(dipsb_ctx* c, uint64_t n_eff, float* out) {
+    if (!c || !out) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    float* d = reinterpret_cast<float*>(c->planar);
+    CK(c, launch_intensity_map(c->g, c->acc, n_eff, d, c->stream));
+    CK(c, cudaMemcpyAsync(out, d, c->g.npx * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_get_frame_means(dipsb_ctx* c, uint64_t first, uint64_t n, float* out) {
+    if (!c || (!out && n)) return DIPSB_ERR_INVALID;
+    if (n == 0) return DIPSB_OK;
+    uint64_t* tmp = new (std::nothrow) uint64_t[n];
+    if (!tmp) return fail(c, DIPSB_ERR_NOMEM, "get_frame_means: out of host memory");
+    int32_t rc = dipsb_get_scalars(c, first, n, tmp, nullptr);
+    if (rc == DIPSB_OK) {
+        const double den = 510.0 * (double)c->g.npx;   // one division of the exact integer, as the oracle does
+        for (uint64_t i = 0; i < n; ++i) out[i] = (float)((double)tmp[i] / den);
+    }
+    delete[] tmp;
+    return rc;
+}
+
+// ---- utilities -----------------------------------------------------------------------------------------------------
+extern "C" int32_t dipsb_synth_fill_device(int32_t device, void* d_dst, uint64_t first_frame, uint64_t n_frames, uint32_t width,
+                                           uint32_t height, int32_t format, uint64_t seed, int32_t profile, void* stream) {
+    if (!d_dst || format < 0 || format > 3) return DIPSB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return DIPSB_ERR_CUDA;
+    cudaError_t e = launch_synth((uint8_t*)d_dst, first_frame, n_frames, width, height, bpp_of(format), seed, profile, (cudaStream_t)stream);
+    return e == cudaSuccess ? DIPSB_OK : fail(nullptr, DIPSB_ERR_CUDA, "synth_fill: %s", cudaGetErrorString(e));
+}
+
+extern "C" int32_t dipsb_enable_timing(dipsb_ctx* c, int32_t on) {
+    if (!c) return DIPSB_ERR_INVALID;
+    c->timing = on != 0;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_clip_kernel_time(dipsb_ctx* c, double* total_ms, uint64_t* launches) {
+    if (!c || !total_ms || !launches) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < c->tev_used; i += 2) {
+        float ms = 0.f;
+        CK(c, cudaEventElapsedTime(&ms, c->tev[i], c->tev[i + 1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = c->tev_used / 2;
+    c->tev_used = 0;
+    return DIPSB_OK;
+}
+
+extern "C" uint64_t dipsb_launch_count(void) { return launch_count_value(); }

@@ -1,0 +1,297 @@
+// aux_kernels.cu -- everything around the clip kernel: reference-plane builders (K1), the per-frame streaming kernel with
+// the reference's visual colour mapping (K4), scalar finalisation, accumulator re-ordering and the synthetic clip generator.
+// All of these are once-per-clip or PCIe-bound, so they are written for clarity; the roofline kernel is clip_kernel.cu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "dipsb_internal.h"
+
+namespace dipsb {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+uint64_t launch_count_value() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void chan_offsets(int format, int& r, int& g, int& b) {
+    if (format == 2 || format == 3) { r = 2; g = 1; b = 0; }
+    else { r = 0; g = 1; b = 2; }
+}
+
+// get_intensity (dips_shader.wgsl:64-82) as the integer 510*luminance; chan_byte >= 0 selects one byte (x2)
+__device__ __forceinline__ uint32_t intensity2(const uint8_t* px, int chan_byte) {
+    if (chan_byte >= 0) return 2u * px[chan_byte];
+    const uint32_t a = px[0], b = px[1], c = px[2];
+    return max(max(a, b), c) + min(min(a, b), c);
+}
+
+// K1: state[p] = I2(frame[p])          (pre_compute_main analogue with a single start frame)
+__global__ void prime_kernel(const uint8_t* __restrict__ frame, uint64_t npx, int bpp, int chan_byte,
+                             uint16_t* __restrict__ state) {
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
+        state[p] = (uint16_t)intensity2(frame + p * bpp, chan_byte);
+}
+
+// K1': upper median of 4 start frames, pre_compute_shader.wgsl:103-131 (element [2] of the ascending sort)
+__global__ void prime_median4_kernel(const uint8_t* __restrict__ frames, uint64_t stride, uint64_t npx, int bpp,
+                                     int chan_byte, uint16_t* __restrict__ state) {
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = intensity2(frames + k * stride + p * bpp, chan_byte);
+        // third smallest of four = min of the two pair-maxima and ... written as a 5-comparator network
+        uint32_t lo01 = min(v[0], v[1]), hi01 = max(v[0], v[1]), lo23 = min(v[2], v[3]), hi23 = max(v[2], v[3]);
+        uint32_t mid_hi = max(lo01, lo23);          // second or third smallest candidates
+        uint32_t mid_lo = min(hi01, hi23);
+        state[p] = (uint16_t)max(mid_hi, mid_lo);   // sorted[2]
+    }
+}
+
+// per-frame scalars: sum the per-warp words (sad | cnt<<20) of one frame; one block per frame
+__global__ void finalize_scalars_kernel(const uint32_t* __restrict__ partials, uint32_t words_per_frame,
+                                        uint64_t* __restrict__ sad, uint64_t* __restrict__ cnt) {
+    const uint32_t t = blockIdx.x;
+    const uint32_t* row = partials + (uint64_t)t * words_per_frame;
+    unsigned long long s = 0, c = 0;
+    for (uint32_t i = threadIdx.x; i < words_per_frame; i += blockDim.x) {
+        const uint32_t w = __ldg(row + i);
+        s += w & 0xFFFFFu;
+        c += w >> 20;
+    }
+    __shared__ unsigned long long sh_s[kThreads / 32], sh_c[kThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+        c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_c[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kThreads / 32; ++k) { s += sh_s[k]; c += sh_c[k]; }
+        sad[t] = s;
+        cnt[t] = c;
+    }
+}
+
+__global__ void unpermute_kernel(const uint32_t* __restrict__ internal, uint32_t* __restrict__ planar, uint64_t npx,
+                                 uint32_t tile_px, uint32_t threads, int bpp) {
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
+        planar[p] = internal[tile_order_index(p, tile_px, threads, bpp)];
+}
+__global__ void permute_kernel(const uint32_t* __restrict__ planar, uint32_t* __restrict__ internal, uint64_t npx,
+                               uint32_t tile_px, uint32_t threads, int bpp) {
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
+        internal[tile_order_index(p, tile_px, threads, bpp)] = planar[p];
+}
+__global__ void intensity_map_kernel(const uint32_t* __restrict__ internal, float* __restrict__ out, uint64_t npx,
+                                     uint32_t tile_px, uint32_t threads, int bpp, double inv_den) {
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
+        out[p] = (float)((double)internal[tile_order_index(p, tile_px, threads, bpp)] * inv_den);
+}
+
+// ---- visual chain: compute_main colour mapping, dips_shader.wgsl:30-62, :97-118, :213-239 -----------------------------
+__device__ __forceinline__ uint8_t unorm8(float v) {
+    if (!(v > 0.0f)) return 0;
+    if (v >= 1.0f) return 255;
+    return (uint8_t)floorf(v * 255.0f + 0.5f);
+}
+__device__ void hsl_to_rgb(float h, float s, float l, float& r, float& g, float& b) {
+    const float chroma = s * (1.0f - fabsf(2.0f * l - 1.0f));
+    const float hp = h / 60.0f;
+    const float x = chroma * (1.0f - fabsf(fmodf(hp, 2.0f) - 1.0f));
+    const float m = l - chroma / 2.0f;
+    r = g = b = 0.0f;
+    if (hp >= 0 && hp < 1) { r = chroma; g = x; }
+    else if (hp >= 1 && hp < 2) { r = x; g = chroma; }
+    else if (hp >= 2 && hp < 3) { g = chroma; b = x; }
+    else if (hp >= 3 && hp < 4) { g = x; b = chroma; }
+    else if (hp >= 4 && hp < 5) { r = x; b = chroma; }
+    else if (hp >= 5 && hp <= 6) { r = chroma; b = x; }
+    r += m; g += m; b += m;
+}
+__device__ __forceinline__ uchar4 visual_pixel(int s_i2, int colorize, int filter, float sig) {
+    float diff = (float)s_i2 / 510.0f;                                  // start.r - median, :213-214
+    diff = diff * 0.5f;                                                 // map(-1,1 -> -0.5,0.5), :217
+    if (filter == 0) diff = 1.0f / (1.0f + expf(-sig * diff)) - 0.5f;   // sigmoid, :108-112
+    else if (filter == 1) diff = (-logf((1.0f / (diff + 0.5f)) - 1.0f)) / sig;  // inv_sigmoid, :114-118
+    diff *= 5.0f;                                                       // SENSITIVITY, :229
+    float r, g, b;
+    if (colorize) {
+        if (diff < 0) hsl_to_rgb(0.0f, fabsf(diff), 0.5f, r, g, b);
+        else hsl_to_rgb(120.0f, diff, 0.5f, r, g, b);
+    } else {
+        r = g = b = 0.5f - diff;
+    }
+    return make_uchar4(unorm8(r), unorm8(g), unorm8(b), 255);
+}
+
+// Streaming kernel: one frame against the state plane.  Used by dipsb_push_frame (PCIe-bound path) and as the fallback
+// of run_clip for frames whose base/stride are not 16-byte aligned (the TMA bulk copy needs that).
+struct FrameK {
+    const uint8_t* frame; uint64_t pitch; uint32_t width, height; int bpp, chan_byte;
+    const uint16_t* state_in; uint16_t* state_out; uint32_t* acc_sum; uint32_t* acc_cnt;
+    unsigned long long* sad; unsigned long long* cnt; uint8_t* out_rgba;
+    uint32_t tau, tile_px, threads; int geo_bpp; int accumulate, colorize, filter; float sig;
+};
+__global__ void frame_kernel(const FrameK K) {
+    const uint64_t npx = (uint64_t)K.width * K.height;
+    unsigned long long s = 0, c = 0;
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(p / K.width), x = (uint32_t)(p - (uint64_t)y * K.width);
+        const uint32_t cur = intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
+        const uint32_t ref = K.state_in[p];
+        const int sdiff = (int)ref - (int)cur;                          // sign convention start - current
+        const uint32_t d = (uint32_t)(sdiff < 0 ? -sdiff : sdiff);
+        const uint32_t m = d > K.tau ? 1u : 0u;
+        if (K.accumulate) {
+            const uint64_t q = tile_order_index(p, K.tile_px, K.threads, K.geo_bpp);
+            K.acc_sum[q] += d;                                          // each pixel is owned by exactly one thread
+            K.acc_cnt[q] += m;
+            s += d; c += m;
+        }
+        if (K.state_out) K.state_out[p] = (uint16_t)cur;
+        if (K.out_rgba) reinterpret_cast<uchar4*>(K.out_rgba)[p] = visual_pixel(sdiff, K.colorize, K.filter, K.sig);
+    }
+    if (K.accumulate) {
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+            c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+        }
+        __shared__ unsigned long long sh_s[kThreads / 32], sh_c[kThreads / 32];
+        if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_c[threadIdx.x >> 5] = c; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < kThreads / 32; ++k) { s += sh_s[k]; c += sh_c[k]; }
+            atomicAdd(K.sad, s);
+            atomicAdd(K.cnt, c);
+        }
+    }
+}
+
+// warm-up passthrough of frame_callback (dips/src/lib.rs:241-245): input converted to RGBA8, alpha 255
+__global__ void passthrough_kernel(const uint8_t* __restrict__ frame, uint64_t pitch, uint32_t width, uint32_t height,
+                                   int format, uint8_t* __restrict__ out) {
+    const uint64_t npx = (uint64_t)width * height;
+    const int bpp = (format == 0 || format == 2) ? 3 : 4;
+    int ro, go, bo;
+    chan_offsets(format, ro, go, bo);
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(p / width), x = (uint32_t)(p - (uint64_t)y * width);
+        const uint8_t* px = frame + (uint64_t)y * pitch + (uint64_t)x * bpp;
+        reinterpret_cast<uchar4*>(out)[p] = make_uchar4(px[ro], px[go], px[bo], bpp == 4 ? px[3] : 255);
+    }
+}
+
+// ---- synthetic clips (same bytes as oracle/dips_oracle.c: dipso_synth_fill) ------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+__device__ __forceinline__ uint32_t hash_byte(uint64_t seed, uint64_t index) {
+    const uint64_t v = mix64(seed + ((index >> 3) + 1) * 0x9E3779B97F4A7C15ull);
+    return (uint32_t)(v >> (8 * (index & 7))) & 0xFFu;
+}
+__global__ void synth_kernel(uint8_t* __restrict__ dst, uint64_t first_frame, uint64_t n_frames, uint32_t W, uint32_t H,
+                             int bpp, uint64_t seed, int profile) {
+    const uint64_t fb = (uint64_t)W * H * bpp;
+    const uint64_t total = fb * n_frames;
+    for (uint64_t o = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; o < total; o += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = o / fb, i = o - k * fb, t = first_frame + k;
+        const uint64_t g = t * fb + i;
+        uint32_t v;
+        if (profile == 0) {
+            v = hash_byte(seed, g);
+        } else {
+            const int bg = (int)hash_byte(seed ^ 0xB5AD4ECEDA1CE2A9ull, i);
+            const int noise = (int)(hash_byte(seed, g) % 17u) - 8;
+            const uint64_t p = i / (uint64_t)bpp;
+            const uint32_t x = (uint32_t)(p % W), y = (uint32_t)(p / W);
+            const uint32_t bx = (uint32_t)((t * 7u) % W), by = (uint32_t)((t * 3u) % H);
+            const uint32_t bw = W * 5u / 16u, bh = H * 5u / 16u;
+            const uint32_t dx = (x + W - bx) % W, dy = (y + H - by) % H;
+            int q = bg + noise + ((dx < bw && dy < bh) ? 64 : 0);
+            q = q < 0 ? 0 : (q > 255 ? 255 : q);
+            v = (uint32_t)q;
+        }
+        dst[o] = (uint8_t)v;
+    }
+}
+
+inline int grid_for(uint64_t n, const Geometry& g) {
+    uint64_t b = (n + kThreads - 1) / kThreads;
+    const uint64_t cap = (uint64_t)(g.num_sms ? g.num_sms : 148) * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+cudaError_t launch_prime(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s) {
+    prime_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(frame, g.npx, g.bpp, g.chan_byte, state);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_prime_median4(const Geometry& g, const uint8_t* frames, uint64_t stride, uint16_t* state,
+                                 cudaStream_t s) {
+    prime_median4_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(frames, stride, g.npx, g.bpp, g.chan_byte, state);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_finalize_scalars(const Geometry&, const uint32_t* partials, uint32_t n_frames,
+                                    uint32_t words_per_frame, uint64_t* sad, uint64_t* cnt, cudaStream_t s) {
+    if (n_frames == 0) return cudaSuccess;
+    finalize_scalars_kernel<<<n_frames, kThreads, 0, s>>>(partials, words_per_frame, sad, cnt);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_unpermute(const Geometry& g, const uint32_t* internal, uint32_t* planar, cudaStream_t s) {
+    unpermute_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(internal, planar, g.npx, g.tile_px, g.threads, g.bpp);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_permute(const Geometry& g, const uint32_t* planar, uint32_t* internal, cudaStream_t s) {
+    permute_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(planar, internal, g.npx, g.tile_px, g.threads, g.bpp);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_intensity_map(const Geometry& g, const uint32_t* internal, uint64_t n_eff, float* out, cudaStream_t s) {
+    const double inv = 1.0 / (510.0 * (double)(n_eff ? n_eff : 1));
+    intensity_map_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(internal, out, g.npx, g.tile_px, g.threads, g.bpp, inv);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) {
+    FrameK K;
+    K.frame = a.frame; K.pitch = a.pitch; K.width = g.width; K.height = g.height;
+    K.bpp = (a.format == 0 || a.format == 2) ? 3 : 4; K.chan_byte = a.chan_byte;
+    K.state_in = a.state_in; K.state_out = a.state_out; K.acc_sum = a.acc_sum; K.acc_cnt = a.acc_cnt;
+    K.sad = reinterpret_cast<unsigned long long*>(a.sad); K.cnt = reinterpret_cast<unsigned long long*>(a.cnt);
+    K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp;
+    K.accumulate = a.accumulate; K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
+    frame_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(K);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uint64_t pitch, int format, uint8_t* out,
+                                    cudaStream_t s) {
+    passthrough_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(frame, pitch, g.width, g.height, format, out);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_synth(uint8_t* dst, uint64_t first_frame, uint64_t n_frames, uint32_t w, uint32_t h, int bpp,
+                         uint64_t seed, int profile, cudaStream_t s) {
+    const uint64_t total = (uint64_t)w * h * bpp * n_frames;
+    if (total == 0) return cudaSuccess;
+    uint64_t b = (total + kThreads - 1) / kThreads;
+    if (b > 148ull * 64) b = 148ull * 64;
+    synth_kernel<<<(int)b, kThreads, 0, s>>>(dst, first_frame, n_frames, w, h, bpp, seed, profile);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace dipsb

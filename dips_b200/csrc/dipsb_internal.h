@@ -1,0 +1,101 @@
+// Internal declarations shared by the translation units of libdips_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dipsb {
+
+constexpr int kPxPerThread = 16;        // pixels owned by one thread of the clip kernel (8 packed u16x2 registers)
+constexpr int kFlushFrames = 128;       // 510*128 < 65536: packed u16 accumulators are flushed to u32 every 128 frames
+constexpr int kMaxStages = 8;
+
+// Geometry of one context (fixed at create time so that the internal accumulator order never changes).
+struct Geometry {
+    uint32_t width, height;
+    uint64_t npx;            // width*height
+    int bpp;                 // 3 or 4
+    int format;              // dipsb_format
+    int chan_byte;           // -1: all channels (max+min); else byte offset of the selected channel inside a pixel
+    uint32_t threads;        // consumer threads per block (multiple of 32)
+    uint32_t tile_px;        // threads * kPxPerThread
+    uint32_t n_tiles;        // ceil(npx / tile_px)
+    uint64_t n_elems;        // n_tiles * tile_px: length of each accumulator plane in internal (tile) order
+    uint32_t blocks_per_sm;  // resident blocks per SM the plan assumes
+    uint32_t stages;         // pipeline depth
+    uint32_t num_sms;
+};
+
+struct ClipArgs {
+    const uint8_t* frames;       // frame k at frames + k*stride
+    uint64_t stride;             // bytes
+    uint32_t n_frames;           // frames in this call
+    uint32_t n_segments;         // grid.y
+    const uint16_t* state_in;    // u16[n_elems >= npx], planar pixel order
+    uint16_t* state_out;         // per-frame mode: I2 of the last frame (written by the last segment)
+    uint32_t* acc_sum;           // u32[n_elems], internal order, RED target
+    uint32_t* acc_cnt;
+    uint32_t* partials;          // u32[n_frames][n_tiles*warps]: sad | cnt<<20 per warp per frame
+    uint32_t tau;                // clamped to <= 511
+    int mode;                    // dipsb_mode
+};
+
+// Which pixel of its tile does register slot k (0..15) of thread `thread` hold?
+//   3 B/px: 16 consecutive pixels per thread (48 contiguous bytes, conflict-free 128-bit shared loads at stride 48 B).
+//   4 B/px: four groups of 4 consecutive pixels, group v at 4*(v*threads + thread) (128-bit shared loads at stride 16 B).
+// index of pixel p in the internal accumulator order: tile*tile_px + k*threads + thread.
+__host__ __device__ inline uint64_t tile_order_index(uint64_t p, uint32_t tile_px, uint32_t threads, int bpp) {
+    const uint64_t tile = p / tile_px;
+    const uint32_t q = (uint32_t)(p - tile * tile_px);
+    uint32_t thread, k;
+    if (bpp == 3) {
+        thread = q / kPxPerThread;
+        k = q % kPxPerThread;
+    } else {
+        const uint32_t v = q / (4u * threads), r = q % (4u * threads);
+        thread = r / 4u;
+        k = 4u * v + (r % 4u);
+    }
+    return tile * tile_px + (uint64_t)k * threads + thread;
+}
+
+size_t clip_smem_bytes(const Geometry& g, uint32_t stages);
+// returns resident blocks/SM for (threads, stages) or 0 when it does not fit
+int clip_occupancy(const Geometry& g, uint32_t threads, uint32_t stages);
+cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s);
+
+cudaError_t launch_prime(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s);
+cudaError_t launch_prime_median4(const Geometry& g, const uint8_t* frames, uint64_t stride, uint16_t* state,
+                                 cudaStream_t s);
+cudaError_t launch_finalize_scalars(const Geometry& g, const uint32_t* partials, uint32_t n_frames,
+                                    uint32_t words_per_frame, uint64_t* sad, uint64_t* cnt, cudaStream_t s);
+cudaError_t launch_unpermute(const Geometry& g, const uint32_t* acc_internal, uint32_t* planar, cudaStream_t s);
+cudaError_t launch_permute(const Geometry& g, const uint32_t* planar, uint32_t* acc_internal, cudaStream_t s);
+
+struct FrameArgs {
+    const uint8_t* frame;        // one frame, row pitch `pitch` bytes
+    uint64_t pitch;
+    int format;                  // format of this frame (may differ from the context's in push_frame)
+    int chan_byte;
+    const uint16_t* state_in;
+    uint16_t* state_out;         // nullptr: do not update
+    uint32_t* acc_sum;
+    uint32_t* acc_cnt;
+    uint64_t* sad;               // single slots, pre-zeroed
+    uint64_t* cnt;
+    uint8_t* out_rgba;           // nullable: visual frame
+    uint32_t tau;
+    int accumulate;              // 0: only prime/visual
+    int colorize, filter;
+    float sig_scalar;
+};
+cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s);
+cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uint64_t pitch, int format,
+                                    uint8_t* out_rgba, cudaStream_t s);
+cudaError_t launch_synth(uint8_t* dst, uint64_t first_frame, uint64_t n_frames, uint32_t w, uint32_t h, int bpp,
+                         uint64_t seed, int profile, cudaStream_t s);
+cudaError_t launch_intensity_map(const Geometry& g, const uint32_t* acc_internal, uint64_t n_eff, float* out,
+                                 cudaStream_t s);
+
+void count_launch(uint64_t n = 1);
+
+}  // namespace dipsb

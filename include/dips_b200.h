@@ -1,0 +1,173 @@
+/*
+ * dips_b200.h -- C ABI of libdips_b200.so: the B200 (sm_100a) implementation of the DiPs per-pixel
+ * frame-difference hot path.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (paths relative to the RubenMovsesyan/DiPs root):
+ *   dipsb_create / dipsb_destroy      ComputeState::new                  dips/src/gpu/mod.rs:59-165
+ *                                     DiPsCompute::new                   dips_alt/src/dips_compute/mod.rs:270-496
+ *   dipsb_push_frame                  frame_callback = add_texture+dispatch   dips/src/lib.rs:233-246,
+ *                                                                        dips/src/gpu/mod.rs:170-216, :306-397
+ *                                     DiPsCompute::send_frame            dips_alt/src/dips_compute/mod.rs:498-646
+ *   dipsb_snapshot                    send_frame(.., snapshot = Some(())) dips_alt/src/lib.rs:222-225, :636-639
+ *                                     and the refresh markers            dips_alt/src/lib.rs:668-670
+ *   dipsb_prime_device                pre_compute_main ("start" plane)   dips/src/gpu/shaders/pre_compute_shader.wgsl:92-132
+ *   dipsb_run_clip_device / _host     compute_main applied to a whole clip    dips/src/gpu/shaders/dips_shader.wgsl:172-240
+ *                                     (the per-frame dispatch loop of    dips/src/frame_extractor.rs:206-276)
+ *   dipsb_config fields               pipeline-overridable constants     dips/src/gpu/mod.rs:101-109, dips_shader.wgsl:15-21
+ *
+ * Semantics (integer contract):
+ *   I2 = max(r,g,b)+min(r,g,b) in [0,510]  (2*channel with a chroma filter)
+ *   overall:   D_t = |I2_t - I2_ref|;  per-frame: D_t = |I2_t - I2_{t-1}|, D_0 = 0
+ *   M_t = D_t > threshold;  acc_sum[p] += D_t(p);  acc_cnt[p] += M_t(p);  sad[t] = sum_p D_t;  cnt[t] = sum_p M_t
+ *
+ * The context keeps a "state plane" (u16 I2 per pixel): the reference plane in overall mode, the I2 of the
+ * last processed frame in per-frame mode.  Consecutive run/push calls therefore chain: a clip may be fed in
+ * chunks, and a frame-range shard on another GPU is primed with frame 0 (overall) or with the one-frame halo
+ * t0-1 (per-frame) through dipsb_prime_device before its first run call.
+ *
+ * Threading: one caller at a time per context; the context may migrate between threads (every entry point
+ * selects its device).  Errors: 0 = ok, 1 = DIPSB_NOT_READY (warm-up / passthrough), <0 = error with a message
+ * in dipsb_last_error().  Nothing throws or aborts across this boundary, and there is no CPU fallback: without
+ * a usable CUDA device dipsb_create fails.
+ */
+#ifndef DIPS_B200_H
+#define DIPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIPSB_ABI_VERSION 1
+
+typedef struct dipsb_ctx dipsb_ctx;
+
+enum dipsb_status {
+    DIPSB_OK = 0,
+    DIPSB_NOT_READY = 1,
+    DIPSB_ERR_INVALID = -1,
+    DIPSB_ERR_CUDA = -2,
+    DIPSB_ERR_NOMEM = -3,
+    DIPSB_ERR_STATE = -4
+};
+
+enum dipsb_format { DIPSB_FMT_RGB8 = 0, DIPSB_FMT_RGBX8 = 1, DIPSB_FMT_BGR8 = 2, DIPSB_FMT_BGRX8 = 3 };
+enum dipsb_mode { DIPSB_MODE_OVERALL = 0, DIPSB_MODE_PERFRAME = 1 };
+/* numbering of dips/src/lib.rs:52-61 */
+enum dipsb_chroma { DIPSB_CHROMA_NONE = 0, DIPSB_CHROMA_RED = 1, DIPSB_CHROMA_GREEN = 2, DIPSB_CHROMA_BLUE = 3 };
+/* numbering of dips/src/lib.rs:32-41 */
+enum dipsb_filter { DIPSB_FILTER_SIGMOID = 0, DIPSB_FILTER_INV_SIGMOID = 1, DIPSB_FILTER_NONE = 255 };
+enum dipsb_synth { DIPSB_SYNTH_UNIFORM = 0, DIPSB_SYNTH_SCENE = 1 };
+
+typedef struct dipsb_config {
+    uint32_t struct_size;      /* sizeof(dipsb_config), for ABI evolution */
+    int32_t device;            /* CUDA device ordinal */
+    uint32_t width, height;    /* pixels */
+    int32_t format;            /* dipsb_format of the frames fed to run_clip / push_frame */
+    int32_t mode;              /* dipsb_mode */
+    int32_t chroma;            /* dipsb_chroma */
+    uint32_t threshold;        /* tau in I2 units [0,510]; a float theta in [0,1] maps to floor(theta*510) */
+    /* visual output of dipsb_push_frame (reference compute_main colour mapping) */
+    int32_t colorize;          /* COLORIZE override, dips_shader.wgsl:15 */
+    int32_t filter;            /* dipsb_filter, FILTER_TYPE override */
+    float sigmoid_scalar;      /* SIGMOID_HORIZONTAL_SCALAR override (UI "sensitivity") */
+    int32_t spatial_window;    /* WINDOW_SIZE override; only 1 is implemented */
+    uint32_t reserved[4];
+} dipsb_config;
+
+typedef struct dipsb_frame_stats {
+    uint64_t frame_index;
+    uint64_t sad;              /* sum_p D_t(p) */
+    uint64_t count;            /* sum_p M_t(p) */
+} dipsb_frame_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int32_t dipsb_abi_version(void);
+void dipsb_default_config(dipsb_config *cfg);
+int32_t dipsb_create(const dipsb_config *cfg, dipsb_ctx **out);
+void dipsb_destroy(dipsb_ctx *ctx);
+const char *dipsb_last_error(const dipsb_ctx *ctx);      /* ctx may be NULL: last error of dipsb_create */
+/* zero the accumulators and scalars, forget the state plane and the frame counter */
+int32_t dipsb_reset(dipsb_ctx *ctx);
+/* change tau / mode between clips (accumulators are kept; call dipsb_reset to clear) */
+int32_t dipsb_set_threshold(dipsb_ctx *ctx, uint32_t threshold);
+/* all work of this context is issued on `stream` (a cudaStream_t; NULL = the context's own stream) */
+int32_t dipsb_set_stream(dipsb_ctx *ctx, void *stream);
+int32_t dipsb_synchronize(dipsb_ctx *ctx);
+
+/* ---- state plane (reference frame / halo) --------------------------------------------------- */
+/* state := I2(frame) for one raw frame resident on the device (K1). */
+int32_t dipsb_prime_device(dipsb_ctx *ctx, const void *d_frame);
+/* state := upper median of the I2 of 4 consecutive raw frames (reference "start" plane). */
+int32_t dipsb_prime_median4_device(dipsb_ctx *ctx, const void *d_frames, uint64_t frame_stride_bytes);
+int32_t dipsb_prime_host(dipsb_ctx *ctx, const uint8_t *frame);
+/* device pointer to the u16[width*height] state plane (for an NCCL broadcast / send-recv) and a setter
+ * that marks it valid after a peer wrote it. */
+int32_t dipsb_state_plane_device(dipsb_ctx *ctx, void **d_state);
+int32_t dipsb_mark_state_valid(dipsb_ctx *ctx, int32_t valid);
+int32_t dipsb_get_state_plane(dipsb_ctx *ctx, uint16_t *out);
+
+/* ---- batch: a clip (or a frame-range shard of one) ------------------------------------------ */
+/*
+ * Frames k = 0..n_frames-1 live at d_frames + k*frame_stride_bytes, tightly packed rows.  They are frames
+ * first_frame_index .. first_frame_index+n_frames-1 of the logical clip; per-frame scalars are stored under
+ * that index.  If the state plane is not valid it is primed from frame 0 of this call (so D of that frame is 0).
+ * Asynchronous with respect to the host; ordered on the context's stream.
+ */
+int32_t dipsb_run_clip_device(dipsb_ctx *ctx, const void *d_frames, uint64_t n_frames,
+                              uint64_t frame_stride_bytes, uint64_t first_frame_index);
+/* Same from pageable or pinned HOST memory: chunks are staged through pinned buffers and uploaded on a copy
+ * stream overlapped with the kernels of the previous chunk.  Returns after the last kernel was issued. */
+int32_t dipsb_run_clip_host(dipsb_ctx *ctx, const uint8_t *frames, uint64_t n_frames,
+                            uint64_t frame_stride_bytes, uint64_t first_frame_index);
+
+/* ---- streaming: one frame per call (the reference's per-frame boundary) --------------------- */
+/*
+ * px: host frame, `stride` bytes per row.  out_rgba (nullable): width*height*4 bytes, receives the reference's
+ * visual frame for this input (RGBA8, alpha 255).  stats (nullable).  Returns DIPSB_NOT_READY and copies the
+ * input through (converted to RGBA8) while there is no reference yet, as frame_callback does during warm-up.
+ */
+int32_t dipsb_push_frame(dipsb_ctx *ctx, const uint8_t *px, uint32_t width, uint32_t height, uint32_t stride,
+                         int32_t format, uint8_t *out_rgba, dipsb_frame_stats *stats);
+/* the next pushed frame becomes the reference (dips_alt snapshot / refresh marker) */
+int32_t dipsb_snapshot(dipsb_ctx *ctx);
+
+/* ---- results -------------------------------------------------------------------------------- */
+uint64_t dipsb_frames_processed(const dipsb_ctx *ctx);
+/* planar row-major u32[width*height]; either pointer may be NULL.  Synchronises the stream. */
+int32_t dipsb_get_accumulators(dipsb_ctx *ctx, uint32_t *acc_sum, uint32_t *acc_cnt);
+int32_t dipsb_set_accumulators(dipsb_ctx *ctx, const uint32_t *acc_sum, const uint32_t *acc_cnt);
+/*
+ * Device view of the accumulators for collectives: one contiguous u32[2*n_elems] buffer (sum plane then count
+ * plane, in the library's internal tile order -- identical on every context of the same geometry, so an
+ * element-wise NCCL sum across ranks is exact).  Finalises pending work first.
+ */
+int32_t dipsb_accumulators_device(dipsb_ctx *ctx, void **d_acc, uint64_t *n_elems);
+/* per-frame scalars of logical frames first..first+n-1; either pointer may be NULL. */
+int32_t dipsb_get_scalars(dipsb_ctx *ctx, uint64_t first, uint64_t n, uint64_t *sad, uint64_t *cnt);
+/* X6 float outputs: acc_sum/(510*n_eff) per pixel, sad[t]/(510*W*H) per frame */
+int32_t dipsb_get_intensity_map(dipsb_ctx *ctx, uint64_t n_eff, float *out);
+int32_t dipsb_get_frame_means(dipsb_ctx *ctx, uint64_t first, uint64_t n, float *out);
+
+/* ---- utilities ------------------------------------------------------------------------------ */
+/* deterministic synthetic clip generated on the device (same bytes as the oracle's generator) */
+int32_t dipsb_synth_fill_device(int32_t device, void *d_dst, uint64_t first_frame, uint64_t n_frames,
+                                uint32_t width, uint32_t height, int32_t format, uint64_t seed, int32_t profile,
+                                void *stream);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t dipsb_launch_count(void);
+/* last clip kernel geometry, for reports: tiles, frame segments, threads per block, stages, blocks per SM */
+int32_t dipsb_last_plan(const dipsb_ctx *ctx, uint32_t out[8]);
+/* optional device-side timing of the clip kernel alone (cudaEvent pairs on the context's stream around each launch).
+ * dipsb_clip_kernel_time synchronises, returns the summed milliseconds and launch count since the last call, and resets. */
+int32_t dipsb_enable_timing(dipsb_ctx *ctx, int32_t on);
+int32_t dipsb_clip_kernel_time(dipsb_ctx *ctx, double *total_ms, uint64_t *launches);
+/* tuning knobs (0 = automatic): force pipeline stages / pixels per tile / frame segments */
+int32_t dipsb_set_tuning(dipsb_ctx *ctx, uint32_t stages, uint32_t tile_px, uint32_t segments);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,76 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, exports every symbol include/dips_b200.h declares,
+and fails loudly (no fallback) without a GPU.  No compute is called here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dips_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dipsb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from dips_b200 import _build, _lib
+    so = _build.build()
+    assert os.path.exists(so)
+    lib = ctypes.CDLL(so)
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dips_b200.h but not exported"
+    assert set(names) == set(_lib.SYMBOLS), set(names) ^ set(_lib.SYMBOLS)
+    assert _lib.load().dipsb_abi_version() == 1
+
+
+def test_config_struct_layout():
+    from dips_b200 import _lib
+    cfg = _lib.Config()
+    _lib.load().dipsb_default_config(ctypes.byref(cfg))
+    assert cfg.struct_size == ctypes.sizeof(_lib.Config) == 64
+    assert cfg.filter == 255 and cfg.spatial_window == 1 and abs(cfg.sigmoid_scalar - 5.0) < 1e-9
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import dips_b200
+    with pytest.raises(dips_b200.DipsError) as e:
+        dips_b200.Context(64, 48)
+    assert "no CUDA device" in str(e.value) and "no CPU fallback" in str(e.value)
+
+
+def test_invalid_arguments_are_rejected_before_touching_the_device():
+    from dips_b200 import _lib
+    L = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = _lib.Config()
+    L.dipsb_default_config(ctypes.byref(cfg))
+    cfg.width, cfg.height = 0, 10
+    assert L.dipsb_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"empty frame" in L.dipsb_last_error(None)
+    cfg.width, cfg.height, cfg.format = 8, 8, 9
+    assert L.dipsb_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    cfg.format, cfg.spatial_window = 0, 3
+    assert L.dipsb_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"spatial_window" in L.dipsb_last_error(None)
+    cfg.spatial_window, cfg.struct_size = 1, 12
+    assert L.dipsb_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert L.dipsb_reset(None) == -1 and L.dipsb_frames_processed(None) == 0
+
+
+def test_product_does_not_import_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "dips_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("the oracle's generator", "").replace("as the oracle does", "").replace("oracle/dips_oracle.c", ""), f

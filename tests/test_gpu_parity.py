@@ -1,0 +1,340 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test drives the CUDA path through the C ABI
+(dips_b200.Context -> libdips_b200.so) and checks it bit-exactly against the CPU oracle / the committed fixtures."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SYNTH = json.load(open(os.path.join(GOLD, "synth_golden.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.init()
+    return torch
+
+
+def to_device(torch, clip: np.ndarray):
+    return torch.from_numpy(np.ascontiguousarray(clip)).cuda()
+
+
+def run_gpu(torch, clip, w, h, fmt, mode, tau, chroma=0, chunks=None, tuning=None, stride_pad=0, offset=0):
+    """Run `clip` ([n, frame_bytes] uint8) through the library; returns (acc_sum, acc_cnt, sad, cnt, state, plan)."""
+    import dips_b200
+    n, fb = clip.shape
+    stride = fb + stride_pad
+    if stride_pad or offset:
+        host = np.zeros(offset + n * stride + 64, np.uint8)
+        for t in range(n):
+            host[offset + t * stride: offset + t * stride + fb] = clip[t]
+        dev = torch.from_numpy(host).cuda()
+        base = dev.data_ptr() + offset
+    else:
+        dev = to_device(torch, clip)
+        base = dev.data_ptr()
+    with dips_b200.Context(w, h, fmt, mode, tau, chroma) as ctx:
+        if tuning:
+            ctx.set_tuning(**tuning)
+        bounds = [0, n] if not chunks else chunks
+        for a, b in zip(bounds, bounds[1:]):
+            ctx.run_clip_device(base + a * stride, b - a, stride, a)
+        ctx.synchronize()
+        acc_sum, acc_cnt = ctx.get_accumulators()
+        sad, cnt = ctx.get_scalars(0, n)
+        state = ctx.get_state_plane()
+        plan = ctx.last_plan()
+        assert ctx.frames_processed == n
+    return acc_sum, acc_cnt, sad, cnt, state, plan
+
+
+def check(oracle, got, clip, fmt, mode, tau, chroma=0):
+    want = oracle.run_clip(clip, fmt, mode, tau, chroma)
+    acc_sum, acc_cnt, sad, cnt, state, _ = got
+    assert np.array_equal(sad, want.sad), "per-frame sad"
+    assert np.array_equal(cnt, want.cnt), "per-frame count"
+    assert np.array_equal(acc_sum, want.acc_sum), "acc_sum"
+    assert np.array_equal(acc_cnt, want.acc_cnt), "acc_cnt"
+    assert np.array_equal(state, want.state), "state plane"
+
+
+def test_synth_generator_matches_oracle(torch_cuda, oracle):
+    import dips_b200
+    torch = torch_cuda
+    for fmt, profile, w, h, n, first in ((0, 1, 96, 64, 5, 0), (1, 0, 33, 17, 4, 3), (2, 1, 61, 37, 3, 1000), (3, 1, 80, 60, 2, 7)):
+        fb = w * h * dips_b200.bytes_per_pixel(fmt)
+        dev = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
+        dips_b200.synth_fill_device(0, dev.data_ptr(), first, n, w, h, fmt, 0x44695073, profile,
+                                    torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want = oracle.synth_clip(n, w, h, fmt, profile=profile, first_frame=first)
+        assert np.array_equal(dev.cpu().numpy().reshape(n, fb), want)
+
+
+@pytest.mark.parametrize("case", SYNTH["cases"], ids=lambda c: c["name"])
+def test_committed_golden_fixtures(torch_cuda, oracle, case):
+    clip = oracle.synth_clip(case["n_frames"], case["width"], case["height"], case["fmt"], profile=case["profile"])
+    assert sha(clip) == case["clip_sha256"]
+    acc_sum, acc_cnt, sad, cnt, state, plan = run_gpu(torch_cuda, clip, case["width"], case["height"], case["fmt"],
+                                                      case["mode"], case["tau"], case["chroma"])
+    assert plan["tma_path"]
+    assert [int(v) for v in sad] == case["sad"] and [int(v) for v in cnt] == case["cnt"]
+    assert sha(acc_sum) == case["acc_sum_sha256"] and sha(acc_cnt) == case["acc_cnt_sha256"]
+    assert sha(state) == case["state_sha256"]
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("chroma", [0, 1, 2, 3])
+def test_all_variants_small(torch_cuda, oracle, fmt, mode, chroma):
+    w, h, n = 200, 75, 9     # 15000 px: several tiles with a ragged last one
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE, seed=11 + fmt)
+    check(oracle, run_gpu(torch_cuda, clip, w, h, fmt, mode, 24, chroma), clip, fmt, mode, 24, chroma)
+
+
+@pytest.mark.parametrize("tau", [0, 1, 32, 128, 509, 510, 511, 70000])
+def test_thresholds(torch_cuda, oracle, tau):
+    w, h, n = 128, 64, 6
+    clip = oracle.synth_clip(n, w, h, 0, profile=oracle.SYNTH_UNIFORM)
+    check(oracle, run_gpu(torch_cuda, clip, w, h, 0, 0, tau), clip, 0, 0, tau)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (5, 3), (16, 1), (17, 3), (511, 2), (513, 7), (640, 480), (1000, 9)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_ragged_sizes(torch_cuda, oracle, w, h, fmt):
+    n = 5
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_UNIFORM, seed=w * 131 + h)
+    for mode in (0, 1):
+        got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 100)
+        check(oracle, got, clip, fmt, mode, 100)
+
+
+def test_extremes_saturate_correctly(torch_cuda, oracle):
+    """all-black reference vs all-white frames: D = 510 everywhere; 300 frames cross the 128-frame flush twice."""
+    w, h, n = 64, 32, 300
+    clip = np.full((n, w * h * 3), 255, np.uint8)
+    clip[0] = 0
+    got = run_gpu(torch_cuda, clip, w, h, 0, 0, 509)
+    check(oracle, got, clip, 0, 0, 509)
+    assert int(got[0][0]) == 510 * (n - 1) and int(got[1][0]) == n - 1
+    alt = np.zeros((n, w * h * 3), np.uint8)
+    alt[1::2] = 255
+    got = run_gpu(torch_cuda, alt, w, h, 0, 1, 0)
+    check(oracle, got, alt, 0, 1, 0)
+
+
+def test_single_frame_and_empty_call(torch_cuda, oracle):
+    import dips_b200
+    w, h = 40, 20
+    clip = oracle.synth_clip(1, w, h, 1)
+    check(oracle, run_gpu(torch_cuda, clip, w, h, 1, 1, 0), clip, 1, 1, 0)
+    with dips_b200.Context(w, h, 1) as ctx:
+        ctx.run_clip_device(0, 0)           # empty clip: no-op, no error
+        assert ctx.frames_processed == 0
+        s, c = ctx.get_accumulators()
+        assert not s.any() and not c.any()
+        with pytest.raises(dips_b200.DipsError):
+            ctx.get_scalars(0, 1)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_chunked_calls_chain(torch_cuda, oracle, mode, fmt):
+    w, h, n = 320, 100, 40
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 16, chunks=[0, 1, 2, 17, 33, 40])
+    check(oracle, got, clip, fmt, mode, 16)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("segments", [2, 3, 7])
+def test_forced_frame_segments(torch_cuda, oracle, mode, segments):
+    w, h, n = 256, 64, 45
+    clip = oracle.synth_clip(n, w, h, 0, profile=oracle.SYNTH_SCENE)
+    got = run_gpu(torch_cuda, clip, w, h, 0, mode, 8, tuning=dict(segments=segments))
+    assert got[5]["segments"] == segments
+    check(oracle, got, clip, 0, mode, 8)
+
+
+@pytest.mark.parametrize("tile_px,stages", [(512, 2), (1024, 3), (2048, 8), (8192, 4), (16384, 2)])
+def test_forced_tile_geometry(torch_cuda, oracle, tile_px, stages):
+    w, h, n = 300, 77, 12
+    for fmt in (0, 1):
+        clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, tuning=dict(stages=stages, tile_px=tile_px))
+        assert got[5]["tile_px"] == tile_px and got[5]["stages"] == stages
+        check(oracle, got, clip, fmt, 1, 8)
+
+
+def test_padded_stride_and_unaligned_fallback(torch_cuda, oracle):
+    w, h, n = 100, 30, 7
+    for fmt in (0, 1):
+        clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, stride_pad=48)       # 16-byte aligned pitch: TMA path
+        assert got[5]["tma_path"]
+        check(oracle, got, clip, fmt, 1, 8)
+        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, stride_pad=5)        # unaligned pitch: per-frame kernel
+        assert not got[5]["tma_path"]
+        check(oracle, got, clip, fmt, 1, 8)
+        got = run_gpu(torch_cuda, clip, w, h, fmt, 0, 8, offset=3)            # unaligned base
+        assert not got[5]["tma_path"]
+        check(oracle, got, clip, fmt, 0, 8)
+    # frame size not a multiple of 16 bytes but aligned pitch: bulk part + tail bytes
+    w, h = 37, 5
+    clip = oracle.synth_clip(n, w, h, 0, profile=oracle.SYNTH_UNIFORM)
+    pad = (-clip.shape[1]) % 16
+    got = run_gpu(torch_cuda, clip, w, h, 0, 0, 8, stride_pad=pad)
+    assert got[5]["tma_path"]
+    check(oracle, got, clip, 0, 0, 8)
+
+
+def test_config1_full_640x480x300(torch_cuda, oracle):
+    """BASELINE.json configs[0]: 640x480 RGB8, 300 frames, overall difference vs first frame."""
+    w, h, n = 640, 480, 300
+    clip = oracle.synth_clip(n, w, h, 0, profile=oracle.SYNTH_SCENE)
+    for mode in (0, 1):
+        got = run_gpu(torch_cuda, clip, w, h, 0, mode, 32)
+        check(oracle, got, clip, 0, mode, 32)
+
+
+def test_reset_prime_and_accumulator_roundtrip(torch_cuda, oracle):
+    import dips_b200
+    torch = torch_cuda
+    w, h, n = 160, 90, 10
+    clip = oracle.synth_clip(n, w, h, 0, profile=oracle.SYNTH_SCENE)
+    dev = to_device(torch, clip)
+    with dips_b200.Context(w, h, 0, 0, 16) as ctx:
+        # explicit reference = frame 3 (not the first frame of the call)
+        ctx.prime_device(dev[3].data_ptr())
+        ctx.run_clip_device(dev.data_ptr(), n)
+        want = oracle.run_clip(clip, 0, 0, 16, state=oracle.i2_plane(clip[3], 0))
+        s, c = ctx.get_accumulators()
+        assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+        # float outputs (tolerance 1e-5 relative, north star)
+        im = ctx.get_intensity_map(n)
+        assert np.allclose(im, oracle.intensity_map(want.acc_sum, n), rtol=1e-5, atol=0)
+        fm = ctx.get_frame_means(0, n)
+        assert np.allclose(fm, oracle.frame_means(want.sad, w * h), rtol=1e-5, atol=0)
+        # median-of-4 start plane (reference pre_compute_main)
+        ctx.reset()
+        ctx.prime_median4_device(dev.data_ptr(), clip.shape[1])
+        assert np.array_equal(ctx.get_state_plane(), oracle.median4_plane(clip[:4], 0))
+        # set/get accumulators round trip (checkpoint/resume) then continue accumulating
+        ctx.reset()
+        ctx.set_accumulators(want.acc_sum, want.acc_cnt)
+        s, c = ctx.get_accumulators()
+        assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+        ctx.prime_device(dev[3].data_ptr())
+        ctx.run_clip_device(dev.data_ptr(), n)
+        s, c = ctx.get_accumulators()
+        assert np.array_equal(s, 2 * want.acc_sum) and np.array_equal(c, 2 * want.acc_cnt)
+        # reset really clears
+        ctx.reset()
+        s, c = ctx.get_accumulators()
+        assert not s.any() and not c.any() and ctx.frames_processed == 0
+
+
+def test_run_clip_host_pageable_and_pinned(torch_cuda, oracle):
+    import dips_b200
+    torch = torch_cuda
+    w, h, n = 320, 180, 25
+    for fmt, mode in ((0, 0), (1, 1), (0, 1)):
+        clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+        want = oracle.run_clip(clip, fmt, mode, 20)
+        for pinned in (False, True):
+            with dips_b200.Context(w, h, fmt, mode, 20) as ctx:
+                if pinned:
+                    t = torch.from_numpy(clip).pin_memory()
+                    ctx.run_clip_host(t.data_ptr(), n, clip.shape[1])
+                else:
+                    ctx.run_clip_host(clip)
+                ctx.synchronize()
+                s, c = ctx.get_accumulators()
+                sad, cnt = ctx.get_scalars(0, n)
+            assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+            assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_logical_shards_merge_exactly(torch_cuda, oracle, mode):
+    """R logical shards run one after another on one GPU through the same sharding code; the all-reduce is replaced by
+    an in-process integer sum.  Result must equal the single-shard run for every R."""
+    import dips_b200
+    from dips_b200 import sharding
+    torch = torch_cuda
+    w, h, n, fmt, tau = 256, 120, 37, 0, 12
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    want = oracle.run_clip(clip, fmt, mode, tau)
+    dev = to_device(torch, clip)
+    for R in (1, 2, 4, 8):
+        total = None
+        sad = np.zeros(n, np.uint64)
+        cnt = np.zeros(n, np.uint64)
+        for r in range(R):
+            t0, t1 = sharding.shard_range(r, R, n)
+            with dips_b200.Context(w, h, fmt, mode, tau) as ctx:
+                eng = sharding.GpuShardEngine(ctx, dev[t0:t1], torch)
+                if r > 0 or mode == 0:
+                    eng.prime(dev[0] if mode == 0 else dev[t0 - 1])      # what broadcast / halo exchange deliver
+                sharding.run_sharded(eng, mode, t0)
+                ctx.synchronize()
+                acc = eng.acc_tensor().clone()
+                total = acc if total is None else total + acc
+                s, c = ctx.get_scalars(t0, t1 - t0)
+                sad[t0:t1], cnt[t0:t1] = s, c
+        with dips_b200.Context(w, h, fmt, mode, tau) as ctx:      # un-permute the merged accumulators
+            ptr, ne = ctx.accumulators_device()
+            view = torch.as_tensor(sharding._DeviceBuffer(ptr, 2 * ne, "<i4"), device="cuda")
+            view.copy_(total)
+            torch.cuda.synchronize()
+            s, c = ctx.get_accumulators()
+        assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt), f"R={R}"
+        assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt), f"R={R}"
+
+
+def test_full_size_1080p_properties(torch_cuda, oracle):
+    """BASELINE configs[1]/[2] geometry (1920x1080 RGB8) on a device-generated clip: size-independent properties on
+    all frames, bit-exact oracle comparison on a bounded prefix."""
+    import dips_b200
+    torch = torch_cuda
+    w, h, n, fmt, tau = 1920, 1080, 200, 0, 32
+    fb = w * h * 3
+    dev = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
+    dips_b200.synth_fill_device(0, dev.data_ptr(), 0, n, w, h, fmt, 0x44695073, dips_b200.SYNTH_SCENE,
+                                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    prefix = 12
+    host = dev[: prefix * fb].cpu().numpy().reshape(prefix, fb)
+    res = {}
+    for mode in (0, 1):
+        with dips_b200.Context(w, h, fmt, mode, tau) as ctx:
+            ctx.run_clip_device(dev.data_ptr(), n)
+            ctx.synchronize()
+            s, c = ctx.get_accumulators()
+            sad, cnt = ctx.get_scalars(0, n)
+            res[mode] = (s, c, sad, cnt)
+            # checksum of checksums
+            assert int(s.astype(np.uint64).sum()) == int(sad.sum())
+            assert int(c.astype(np.uint64).sum()) == int(cnt.sum())
+            assert int(sad[0]) == 0 and int(cnt[0]) == 0
+            # prefix against the oracle (scalars are per frame, so they compare directly)
+            want = oracle.run_clip(host, fmt, mode, tau)
+            assert np.array_equal(sad[:prefix], want.sad) and np.array_equal(cnt[:prefix], want.cnt)
+            # idempotence: a second identical pass doubles the accumulators and repeats the scalars
+            ctx.mark_state_valid(False)
+            ctx.run_clip_device(dev.data_ptr(), n)
+            s2, c2 = ctx.get_accumulators()
+            sad2, _ = ctx.get_scalars(0, n)
+            assert np.array_equal(s2, 2 * s) and np.array_equal(c2, 2 * c) and np.array_equal(sad2, sad)
+    # telescoping bound between the two modes
+    assert np.all(res[0][2] <= np.cumsum(res[1][2]))

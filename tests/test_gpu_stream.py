@@ -1,0 +1,90 @@
+"""GPU tests of the streaming boundary (dipsb_push_frame): the reference's per-frame callback contract
+(dips/src/lib.rs:233-246): same-frame RGBA8 output, passthrough while there is no reference, alpha 255."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rgba_of(frame, fmt, npx):
+    bpp = 3 if fmt in (0, 2) else 4
+    px = frame.reshape(npx, bpp)
+    order = [2, 1, 0] if fmt in (2, 3) else [0, 1, 2]
+    out = np.full((npx, 4), 255, np.uint8)
+    out[:, :3] = px[:, order]
+    if bpp == 4:
+        out[:, 3] = px[:, 3]
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("fmt", [1, 0, 3])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("filt,colorize", [(255, False), (0, False), (1, False), (255, True), (0, True)])
+def test_push_frame_matches_oracle(oracle, fmt, mode, filt, colorize):
+    import dips_b200
+    w, h, n, tau = 96, 54, 7, 10
+    npx = w * h
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    want = oracle.run_clip(clip, fmt, mode, tau)
+    i2 = [oracle.i2_plane(clip[t], fmt) for t in range(n)]
+    with dips_b200.Context(w, h, fmt, mode, tau, colorize=colorize, filt=filt, sigmoid_scalar=5.0) as ctx:
+        for t in range(n):
+            rc, rgba, (idx, sad, cnt) = ctx.push_frame(clip[t])
+            assert idx == t and sad == int(want.sad[t]) and cnt == int(want.cnt[t])
+            if t == 0:
+                assert rc == dips_b200.NOT_READY
+                assert np.array_equal(rgba, rgba_of(clip[0], fmt, npx))          # passthrough
+            else:
+                assert rc == 0
+                ref = i2[0] if mode == 0 else i2[t - 1]
+                vis = oracle.visual_frame(ref, i2[t], colorize, filt, 5.0)
+                diff = np.abs(vis.astype(int) - rgba.astype(int))
+                assert diff.max() <= 1, f"visual frame differs by {diff.max()} LSB"      # X7: +-1 LSB
+                assert np.all(rgba.reshape(-1, 4)[:, 3] == 255)
+        s, c = ctx.get_accumulators()
+        assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+        sad, cnt = ctx.get_scalars(0, n)
+        assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)
+
+
+def test_snapshot_and_row_stride(oracle):
+    import dips_b200
+    w, h, fmt = 50, 20, 1
+    clip = oracle.synth_clip(6, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    with dips_b200.Context(w, h, fmt, 0, 0) as ctx:
+        ctx.push_frame(clip[0], want_rgba=False)
+        _, _, (_, sad1, _) = ctx.push_frame(clip[1], want_rgba=False)
+        assert sad1 == int(np.abs(oracle.i2_plane(clip[1], fmt).astype(int) - oracle.i2_plane(clip[0], fmt).astype(int)).sum())
+        ctx.snapshot()                                   # dips_alt refresh marker: next frame becomes the reference
+        rc, _, (_, sad2, _) = ctx.push_frame(clip[2], want_rgba=False)
+        assert rc == dips_b200.NOT_READY and sad2 == 0
+        _, _, (_, sad3, _) = ctx.push_frame(clip[3], want_rgba=False)
+        assert sad3 == int(np.abs(oracle.i2_plane(clip[3], fmt).astype(int) - oracle.i2_plane(clip[2], fmt).astype(int)).sum())
+        # padded rows
+        stride = w * 4 + 12
+        padded = np.zeros((h, stride), np.uint8)
+        padded[:, : w * 4] = clip[4].reshape(h, w * 4)
+        _, _, (_, sad4, _) = ctx.push_frame(padded, stride=stride, want_rgba=False)
+        assert sad4 == int(np.abs(oracle.i2_plane(clip[4], fmt).astype(int) - oracle.i2_plane(clip[2], fmt).astype(int)).sum())
+        # wrong geometry is an error, not a crash
+        with pytest.raises(dips_b200.DipsError):
+            ctx._ck(ctx._lib.dipsb_push_frame(ctx._h, clip[0].ctypes.data, w + 1, h, (w + 1) * 4, fmt, None, None))
+
+
+def test_push_then_batch_interop(oracle):
+    """frames pushed one by one and a following device batch continue the same accumulators and indices"""
+    import torch
+    import dips_b200
+    w, h, fmt, mode, tau = 64, 40, 0, 1, 5
+    clip = oracle.synth_clip(20, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    want = oracle.run_clip(clip, fmt, mode, tau)
+    dev = torch.from_numpy(clip).cuda()
+    with dips_b200.Context(w, h, fmt, mode, tau) as ctx:
+        for t in range(6):
+            ctx.push_frame(clip[t], want_rgba=False)
+        ctx.run_clip_device(dev[6].data_ptr(), 14, clip.shape[1], 6)
+        ctx.synchronize()
+        s, c = ctx.get_accumulators()
+        sad, cnt = ctx.get_scalars(0, 20)
+    assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+    assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)

@@ -1,0 +1,104 @@
+"""CPU tests (gloo, world_size 2) of the frame-range sharding host logic in dips_b200/sharding.py.  The per-shard engine
+is a numpy/oracle stand-in -- what is under test is the orchestration: ranges, frame-0 broadcast, halo send/recv and the
+accumulator all-reduce must reproduce the single-rank result bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dips_b200 import sharding
+
+
+def test_shard_ranges_cover_and_are_disjoint():
+    for n in (1, 7, 300, 1800, 3601):
+        for world in (1, 2, 3, 4, 8):
+            edges = [sharding.shard_range(r, world, n) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for a, b in zip(edges, edges[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(2, 2, 10)
+
+
+class OracleEngine:
+    """ShardEngine over numpy arrays; the math is the oracle's (this test is about the exchange, not the kernel)."""
+
+    def __init__(self, O, frames, fmt, mode, tau):
+        self.O, self.frames, self.fmt, self.mode, self.tau = O, frames, fmt, mode, tau
+        npx = frames.shape[1] // O.bpp(fmt)
+        self.acc = np.zeros(2 * npx, np.int32)
+        self.state = None
+        self.sad = self.cnt = None
+
+    def first_frame(self):
+        return torch.from_numpy(self.frames[0])
+
+    def last_frame(self):
+        return torch.from_numpy(self.frames[-1])
+
+    def frame_buffer(self):
+        return torch.empty(self.frames.shape[1], dtype=torch.uint8)
+
+    def prime(self, frame):
+        self.state = self.O.i2_plane(frame.numpy(), self.fmt)
+
+    def run(self, first_frame_index):
+        r = self.O.run_clip(self.frames, self.fmt, self.mode, self.tau, state=self.state)
+        npx = r.acc_sum.size
+        self.acc[:npx] = r.acc_sum.view(np.int32)
+        self.acc[npx:] = r.acc_cnt.view(np.int32)
+        self.sad, self.cnt, self.first = r.sad, r.cnt, first_frame_index
+
+    def acc_tensor(self):
+        return torch.from_numpy(self.acc)
+
+
+def _worker(rank, world, port, mode, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        fmt, tau, n, w, h = O.FMT_RGB8, 12, 11, 24, 10
+        clip = O.synth_clip(n, w, h, fmt, profile=O.SYNTH_SCENE)
+        t0, t1 = sharding.shard_range(rank, world, n)
+        eng = OracleEngine(O, clip[t0:t1], fmt, mode, tau)
+        sharding.run_sharded(eng, mode, t0, rank, world, dist)
+        whole = O.run_clip(clip, fmt, mode, tau)
+        npx = w * h
+        assert np.array_equal(eng.acc[:npx].view(np.uint32), whole.acc_sum), "acc_sum differs after all-reduce"
+        assert np.array_equal(eng.acc[npx:].view(np.uint32), whole.acc_cnt), "acc_cnt differs after all-reduce"
+        assert np.array_equal(eng.sad, whole.sad[t0:t1]) and np.array_equal(eng.cnt, whole.cnt[t0:t1])
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("mode", [sharding.MODE_OVERALL, sharding.MODE_PERFRAME])
+def test_two_rank_sharding_matches_single_rank(mode, tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), mode, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_single_rank_needs_no_dist():
+    from oracle import oracle as O
+    clip = O.synth_clip(5, 12, 6, O.FMT_RGBX8)
+    eng = OracleEngine(O, clip, O.FMT_RGBX8, 1, 3)
+    sharding.run_sharded(eng, 1, 0)
+    whole = O.run_clip(clip, O.FMT_RGBX8, 1, 3)
+    assert np.array_equal(eng.acc[: 12 * 6].view(np.uint32), whole.acc_sum)
