@@ -99,6 +99,9 @@ class Context:
     def set_stream(self, stream: int) -> None:
         self._ck(self._lib.dipsb_set_stream(self._h, stream))
 
+    def use_private_stream(self) -> None:
+        self._ck(self._lib.dipsb_use_private_stream(self._h))
+
     def synchronize(self) -> None:
         self._ck(self._lib.dipsb_synchronize(self._h))
 

@@ -148,7 +148,7 @@ extern "C" void dipsb_default_config(dipsb_config* cfg) {
 
 static void free_all(dipsb_ctx* c) {
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 2; ++k) {
         if (c->state[k]) cudaFree(c->state[k]);
         if (c->ev_copy[k]) cudaEventDestroy(c->ev_copy[k]);
@@ -268,7 +268,15 @@ extern "C" int32_t dipsb_set_stream(dipsb_ctx* c, void* stream) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));   // keep ordering of already issued work
-    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    c->stream = (cudaStream_t)stream;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_use_private_stream(dipsb_ctx* c) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stream = c->own_stream;
     return DIPSB_OK;
 }
 

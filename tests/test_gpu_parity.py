@@ -87,7 +87,7 @@ def test_committed_golden_fixtures(torch_cuda, oracle, case):
     assert sha(clip) == case["clip_sha256"]
     acc_sum, acc_cnt, sad, cnt, state, plan = run_gpu(torch_cuda, clip, case["width"], case["height"], case["fmt"],
                                                       case["mode"], case["tau"], case["chroma"])
-    assert plan["tma_path"]
+    assert plan["tma_path"] == (clip.shape[1] % 16 == 0)     # unaligned frame pitch -> per-frame fallback kernel
     assert [int(v) for v in sad] == case["sad"] and [int(v) for v in cnt] == case["cnt"]
     assert sha(acc_sum) == case["acc_sum_sha256"] and sha(acc_cnt) == case["acc_cnt_sha256"]
     assert sha(state) == case["state_sha256"]
@@ -180,7 +180,8 @@ def test_padded_stride_and_unaligned_fallback(torch_cuda, oracle):
     w, h, n = 100, 30, 7
     for fmt in (0, 1):
         clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
-        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, stride_pad=48)       # 16-byte aligned pitch: TMA path
+        pad = 48 + (-clip.shape[1]) % 16
+        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, stride_pad=pad)      # 16-byte aligned pitch: TMA path
         assert got[5]["tma_path"]
         check(oracle, got, clip, fmt, 1, 8)
         got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, stride_pad=5)        # unaligned pitch: per-frame kernel
