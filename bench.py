@@ -51,6 +51,7 @@ def parse_args():
     p.add_argument("--stages", type=int, default=0)
     p.add_argument("--tile-px", type=int, default=0)
     p.add_argument("--segments", type=int, default=0)
+    p.add_argument("--regs", type=int, default=0)
     return p.parse_args()
 
 
@@ -238,8 +239,8 @@ def main():
     torch.cuda.synchronize()
 
     ctx = dips_b200.Context(w, h, fmt, mode, tau, device=local_rank)
-    if args.stages or args.tile_px or args.segments:
-        ctx.set_tuning(args.stages, args.tile_px, args.segments)
+    if args.stages or args.tile_px or args.segments or args.regs:
+        ctx.set_tuning(args.stages, args.tile_px, args.segments, args.regs)
     ctx.set_stream(stream.cuda_stream)
     engine = sharding.GpuShardEngine(ctx, clip, torch)
 

@@ -105,8 +105,8 @@ class Context:
     def synchronize(self) -> None:
         self._ck(self._lib.dipsb_synchronize(self._h))
 
-    def set_tuning(self, stages: int = 0, tile_px: int = 0, segments: int = 0) -> None:
-        self._ck(self._lib.dipsb_set_tuning(self._h, stages, tile_px, segments))
+    def set_tuning(self, stages: int = 0, tile_px: int = 0, segments: int = 0, regs: int = 0) -> None:
+        self._ck(self._lib.dipsb_set_tuning(self._h, stages, tile_px, segments, regs))
 
     def enable_timing(self, on: bool = True) -> None:
         self._ck(self._lib.dipsb_enable_timing(self._h, int(on)))
@@ -121,7 +121,7 @@ class Context:
         out = (C.c_uint32 * 8)()
         self._ck(self._lib.dipsb_last_plan(self._h, C.byref(out)))
         return dict(tiles=out[0], segments=out[1], threads=out[2], stages=out[3], blocks_per_sm=out[4],
-                    tile_px=out[5], smem_bytes=out[6], tma_path=bool(out[7]))
+                    tile_px=out[5], smem_bytes=out[6] & 0xFFFFFF, regs=out[6] >> 24, tma_path=bool(out[7]))
 
     # -- state plane ------------------------------------------------------------------------------------------
     def prime_device(self, d_frame: int) -> None:

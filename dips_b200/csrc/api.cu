@@ -47,7 +47,7 @@ struct dipsb_ctx {
     uint8_t* h_chunk[2] = {nullptr, nullptr};
     uint8_t* d_chunk[2] = {nullptr, nullptr};
     size_t chunk_bytes = 0;
-    uint32_t tune_stages = 0, tune_tile_px = 0, tune_segments = 0;
+    uint32_t tune_stages = 0, tune_tile_px = 0, tune_segments = 0, tune_regs = 0;
     uint32_t last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool timing = false;
     std::vector<cudaEvent_t> tev;              // start/stop pairs around clip kernel launches
@@ -84,41 +84,48 @@ static int chan_byte_of(int format, int chroma) {
 }
 
 // ---- planning ------------------------------------------------------------------------------------------------------
-// Pick block size (=> tile), pipeline depth and residency so that (a) the tiles fill the resident slots of the 148 SMs
-// in whole waves, (b) at least ~64 KB of frame bytes are in flight per SM, (c) as many threads as possible are resident.
-static void plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_tile_px) {
-    double best_score = -1.0;
-    uint32_t best_thr = 256, best_stages = 4, best_occ = 1;
-    const uint32_t thr_lo = force_tile_px ? 32 : 128, thr_hi = force_tile_px ? 1024 : 512;
-    for (uint32_t thr = thr_lo; thr <= thr_hi; thr += 32) {
-        if (force_tile_px && thr * kPxPerThread != force_tile_px) continue;
-        uint32_t stages = force_stages ? force_stages : 3;
-        int occ = clip_occupancy(g, thr, stages);
+// Measured on B200 (profiles/r01_sweeps.md): the clip kernel runs fastest with ONE large block per SM -- every SM streams
+// one contiguous 40-56 KB slice of each frame through a 3-4 deep TMA ring, all SMs advance frame by frame together -- and
+// is co-limited by HBM and the integer ALU pipe, so every SM must get the same number of pixels.  Plan: tile_px =
+// npx / (num_sms * waves) rounded up to 16 pixels with the fewest waves that fit a block (<= 896 threads at 72 registers,
+// <= 1024 at 64); deepest pipeline (<= 4 stages) that fits in shared memory.  Frames too small to give every SM a
+// 2048-pixel tile keep 2048-pixel tiles, run several blocks per SM and are split into frame segments instead.
+static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_tile_px, uint32_t force_regs = 0) {
+    const uint64_t min_tile = std::min<uint64_t>(2048, (g.npx + 15) / 16 * 16);
+    for (int regs : {72, 64, 80, 96}) {
+        if (force_regs ? (uint32_t)regs != force_regs : regs > 72) continue;   // 80/96 only on request (tuning)
+        const uint32_t max_thr = (uint32_t)clip_max_threads_per_sm(regs);
+        const uint64_t max_slots = (uint64_t)max_thr * kPxPerThread;
+        uint64_t tile_px;
+        if (force_tile_px) tile_px = force_tile_px;
+        else {
+            const uint64_t waves = (g.npx + g.num_sms * max_slots - 1) / (g.num_sms * max_slots);
+            tile_px = (g.npx + g.num_sms * waves - 1) / (g.num_sms * waves);
+            tile_px = std::max<uint64_t>((tile_px + 15) / 16 * 16, min_tile);
+            // 72 registers (896 threads) unless only the 64-register variant (1024 threads) saves a whole wave
+            if (!force_regs && regs == 72) {
+                const uint64_t slots64 = 1024ull * kPxPerThread;
+                const uint64_t waves64 = (g.npx + g.num_sms * slots64 - 1) / (g.num_sms * slots64);
+                if (waves64 < waves) continue;
+            }
+        }
+        if (tile_px > max_slots) continue;
+        const uint32_t thr = (uint32_t)((tile_px + kPxPerThread * 32 - 1) / (kPxPerThread * 32)) * 32;
+        uint32_t stages = force_stages ? force_stages : 4;
+        int occ = clip_occupancy(thr, g.bpp, stages, regs);
+        while (!force_stages && occ <= 0 && stages > 2) occ = clip_occupancy(thr, g.bpp, --stages, regs);
         if (occ <= 0) continue;
-        if (!force_stages) {
-            const uint64_t tile_bytes = (uint64_t)thr * kPxPerThread * g.bpp;
-            while (stages < (uint32_t)kMaxStages && (uint64_t)occ * (stages - 1) * tile_bytes < 64 * 1024 &&
-                   clip_occupancy(g, thr, stages + 1) == occ)
-                ++stages;
-        }
-        const uint64_t slots = (uint64_t)occ * g.num_sms;
-        const uint64_t tiles = (g.npx + (uint64_t)thr * kPxPerThread - 1) / ((uint64_t)thr * kPxPerThread);
-        double util = 1.0;
-        if (tiles >= slots) {
-            const uint64_t waves = (tiles + slots - 1) / slots;
-            util = (double)tiles / (double)(waves * slots);
-        }
-        const double resident = std::min(1.0, (double)(occ * thr) / 1024.0);
-        // utilisation dominates (2 % buckets), then resident threads, then a mild preference for larger tiles
-        const double score = (double)(int)(util * 50.0) * 100.0 + resident * 10.0 + (double)thr / 1024.0;
-        if (score > best_score) { best_score = score; best_thr = thr; best_stages = stages; best_occ = (uint32_t)occ; }
+        g.threads = thr;
+        g.tile_px = (uint32_t)tile_px;
+        g.n_tiles = (uint32_t)((g.npx + tile_px - 1) / tile_px);
+        g.n_elems = (uint64_t)g.n_tiles * thr * kPxPerThread;
+        g.state_elems = g.npx + (uint64_t)thr * kPxPerThread;
+        g.stages = stages;
+        g.blocks_per_sm = (uint32_t)occ;
+        g.regs = regs;
+        return true;
     }
-    g.threads = best_thr;
-    g.tile_px = best_thr * kPxPerThread;
-    g.n_tiles = (uint32_t)((g.npx + g.tile_px - 1) / g.tile_px);
-    g.n_elems = (uint64_t)g.n_tiles * g.tile_px;
-    g.stages = best_stages;
-    g.blocks_per_sm = best_occ;
+    return false;
 }
 
 static uint32_t plan_segments(const dipsb_ctx* c, uint64_t n_frames) {
@@ -168,8 +175,8 @@ static void free_all(dipsb_ctx* c) {
 static int32_t alloc_planes(dipsb_ctx* c) {
     const Geometry& g = c->g;
     for (int k = 0; k < 2; ++k) {
-        CK(c, cudaMalloc(&c->state[k], g.n_elems * sizeof(uint16_t)));
-        CK(c, cudaMemsetAsync(c->state[k], 0, g.n_elems * sizeof(uint16_t), c->stream));
+        CK(c, cudaMalloc(&c->state[k], g.state_elems * sizeof(uint16_t)));
+        CK(c, cudaMemsetAsync(c->state[k], 0, g.state_elems * sizeof(uint16_t), c->stream));
     }
     CK(c, cudaMalloc(&c->acc, 2 * g.n_elems * sizeof(uint32_t)));
     CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
@@ -212,7 +219,10 @@ extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
     g.width = cfg->width; g.height = cfg->height; g.npx = (uint64_t)cfg->width * cfg->height;
     g.format = cfg->format; g.bpp = bpp_of(cfg->format); g.chan_byte = chan_byte_of(cfg->format, cfg->chroma);
     g.num_sms = (uint32_t)prop.multiProcessorCount;
-    plan_geometry(g, 0, 0);
+    if (!plan_geometry(g, 0, 0)) {
+        delete c;
+        return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: no kernel geometry fits %ux%u", cfg->width, cfg->height);
+    }
     int32_t rc = DIPSB_OK;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -248,7 +258,7 @@ extern "C" int32_t dipsb_reset(dipsb_ctx* c) {
     CK(c, cudaSetDevice(c->device));
     const Geometry& g = c->g;
     CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
-    for (int k = 0; k < 2; ++k) CK(c, cudaMemsetAsync(c->state[k], 0, g.n_elems * sizeof(uint16_t), c->stream));
+    for (int k = 0; k < 2; ++k) CK(c, cudaMemsetAsync(c->state[k], 0, g.state_elems * sizeof(uint16_t), c->stream));
     if (c->scal_cap) {
         CK(c, cudaMemsetAsync(c->d_sad, 0, c->scal_cap * sizeof(uint64_t), c->stream));
         CK(c, cudaMemsetAsync(c->d_cnt, 0, c->scal_cap * sizeof(uint64_t), c->stream));
@@ -287,38 +297,46 @@ extern "C" int32_t dipsb_synchronize(dipsb_ctx* c) {
     return DIPSB_OK;
 }
 
-extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile_px, uint32_t segments) {
+extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile_px, uint32_t segments, uint32_t regs) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     if (stages > (uint32_t)kMaxStages || (stages && stages < 2)) return fail(c, DIPSB_ERR_INVALID, "set_tuning: stages %u outside [2,%d]", stages, kMaxStages);
-    if (tile_px && (tile_px % (32 * kPxPerThread) || tile_px < 32u * kPxPerThread || tile_px > 1024u * kPxPerThread))
-        return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u must be a multiple of %d in [%d, %d]", tile_px, 32 * kPxPerThread, 32 * kPxPerThread, 1024 * kPxPerThread);
-    const bool regeo = (stages != c->tune_stages) || (tile_px != c->tune_tile_px);
+    if (tile_px && (tile_px % 16 || tile_px > 1024u * kPxPerThread))
+        return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u must be a multiple of 16 and <= %d", tile_px, 1024 * kPxPerThread);
+    if (regs && regs != 64 && regs != 72 && regs != 80 && regs != 96) return fail(c, DIPSB_ERR_INVALID, "set_tuning: regs %u not one of 64/72/80/96", regs);
+    const bool regeo = (stages != c->tune_stages) || (tile_px != c->tune_tile_px) || (regs != c->tune_regs);
     c->tune_segments = segments;
     if (!regeo) return DIPSB_OK;
     if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_tuning: geometry can only change on a fresh or reset context");
     CK(c, cudaStreamSynchronize(c->stream));
     Geometry g = c->g;
-    if (tile_px) {
-        g.threads = tile_px / kPxPerThread;
-        if (clip_occupancy(g, g.threads, stages ? stages : 3) <= 0) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u do not fit", tile_px, stages);
-    }
-    plan_geometry(g, stages, tile_px);
-    if (clip_occupancy(g, g.threads, g.stages) <= 0) return fail(c, DIPSB_ERR_INVALID, "set_tuning: configuration does not fit in shared memory");
+    if (!plan_geometry(g, stages, tile_px, regs)) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u / regs %u do not fit", tile_px, stages, regs);
     for (int k = 0; k < 2; ++k) { cudaFree(c->state[k]); c->state[k] = nullptr; }
     cudaFree(c->acc); c->acc = nullptr;
     cudaFree(c->planar); c->planar = nullptr;
     c->g = g;
-    c->tune_stages = stages; c->tune_tile_px = tile_px;
+    c->tune_stages = stages; c->tune_tile_px = tile_px; c->tune_regs = regs;
     c->state_valid = false;
     return alloc_planes(c);
+}
+
+// host-only: the plan the library would use for a geometry on a device with num_sms SMs (no device is touched)
+extern "C" int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t format, uint32_t num_sms, uint32_t out[8]) {
+    if (!out || !width || !height || format < 0 || format > 3 || !num_sms) return DIPSB_ERR_INVALID;
+    Geometry g{};
+    g.width = width; g.height = height; g.npx = (uint64_t)width * height;
+    g.format = format; g.bpp = bpp_of(format); g.chan_byte = -1; g.num_sms = num_sms;
+    if (!plan_geometry(g, 0, 0)) return DIPSB_ERR_INVALID;
+    out[0] = g.n_tiles; out[1] = 0; out[2] = g.threads; out[3] = g.stages; out[4] = g.blocks_per_sm; out[5] = g.tile_px;
+    out[6] = (uint32_t)clip_smem_bytes(g.threads, g.bpp, g.stages) | ((uint32_t)g.regs << 24); out[7] = clip_active_warps(g);
+    return DIPSB_OK;
 }
 
 extern "C" int32_t dipsb_last_plan(const dipsb_ctx* c, uint32_t out[8]) {
     if (!c || !out) return DIPSB_ERR_INVALID;
     memcpy(out, c->last_plan, sizeof c->last_plan);
     out[0] = c->g.n_tiles; out[2] = c->g.threads; out[3] = c->g.stages; out[4] = c->g.blocks_per_sm; out[5] = c->g.tile_px;
-    out[6] = (uint32_t)clip_smem_bytes(c->g, c->g.stages);
+    out[6] = (uint32_t)clip_smem_bytes(c->g.threads, c->g.bpp, c->g.stages) | ((uint32_t)c->g.regs << 24);
     return DIPSB_OK;
 }
 
@@ -426,12 +444,14 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         CK(c, launch_prime(g, d_frames, c->state[c->state_cur], c->stream));
         c->state_valid = true;
     }
-    const bool aligned = (((uintptr_t)d_frames | stride) & 15u) == 0;
+    // the TMA bulk copies of the clip kernel need 16-byte aligned addresses and sizes
+    const bool aligned = (((uintptr_t)d_frames | stride | (g.npx * g.bpp)) & 15u) == 0;
     const uint32_t tau = c->cfg.threshold;
     if (aligned) {
         const uint32_t segs = plan_segments(c, n);
-        const uint32_t words = g.n_tiles * (g.threads / 32);
+        const uint32_t words = g.n_tiles * clip_active_warps(g);
         const uint64_t need = n * (uint64_t)words;
+        if (need >= (1ull << 32)) return fail(c, DIPSB_ERR_INVALID, "run_clip: %llu frames x %u warps exceed the per-call scalar scratch; split the call", (unsigned long long)n, words);
         if (need > c->partial_cap) {
             CK(c, cudaStreamSynchronize(c->stream));
             cudaFree(c->partials); c->partials = nullptr; c->partial_cap = 0;

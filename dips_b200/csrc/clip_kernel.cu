@@ -21,6 +21,7 @@
 //     coalesced RED.ADD (the planes are kept in a tile order that makes thread-adjacent = address-adjacent).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "dipsb_internal.h"
 
@@ -46,6 +47,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// same, but ordered after the computation of `token` (a fake data dependency): keeps the compiler from overlapping the
+// register-hungry tail of one frame with the loads of the next, which would cost ~16 more live registers per thread
+__device__ __forceinline__ void mbar_wait_after(uint32_t bar, uint32_t parity, uint32_t token) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        ".reg .b32 T;\n"
+        "and.b32 T, %2, 0;\n"
+        "add.u32 T, T, %0;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [T], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity), "r"(token)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -58,6 +77,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
         "l"(src), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_nohint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
@@ -142,21 +166,55 @@ struct KParams {
     uint32_t* partials;
     uint32_t n_frames;
     uint32_t n_segments;
-    uint32_t tile_px;
+    uint32_t tile_px;        // pixels per tile (multiple of 16, <= 16*blockDim.x)
     uint32_t stages;
-    uint32_t stage_bytes;   // bytes reserved per stage (tile_px*bpp rounded up to 128)
+    uint32_t stage_bytes;    // bytes reserved per stage: 16*blockDim.x*bpp rounded up to 128
     uint32_t words_per_frame;
+    uint32_t active_warps;   // warps per block that own pixels; the others leave after the setup
     uint32_t tau;
+    uint32_t l2_evict_first; // 1: frames are fetched with an L2 evict-first policy (they are read exactly once)
+    uint32_t one;            // the constant 1 (an IMAD multiplier the compiler cannot fold away, see add_fma)
 };
 
-template <int BPP, int CH, int MODE>
-__global__ void __maxnreg__(64) clip_kernel(const KParams P) {
+// a + b on the FMA pipe (IMAD with a multiplier the compiler cannot fold): the integer ALU pipe is the busier one here
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+
+// One frame for my 16 pixels: D = |cur-ref| per packed half, threshold, accumulate; returns sad | count<<20 of the thread.
+//   hi = max(cur, ref)           VIMNMX.U16x2            (ALU pipe)
+//   d  = 2*hi - cur - ref        2 x IMAD                (FMA pipe; every partial result is >= 0 per half: no borrow)
+//   m  = min(max(d - tau, 0), 1) VIADDMNMX.S16x2.RELU    (ALU pipe)
+//   per-frame sums with IDP.2A (adds both halves into a scalar in one FMA-pipe instruction)
+__device__ __forceinline__ uint32_t diff16(const uint32_t* cur, const uint32_t* ref, uint32_t* accD, uint32_t* accM,
+                                           uint32_t negtau2, uint32_t one) {
+    uint32_t sD = 0u, sM = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t hi = __vmaxu2(cur[j], ref[j]);
+        const uint32_t t = hi * 2u - cur[j];
+        const uint32_t d = add_fma(t, 0u - ref[j], one);
+        const uint32_t m = __viaddmin_s16x2_relu(d, negtau2, 0x00010001u);
+        accD[j] = add_fma(accD[j], d, one);
+        accM[j] = add_fma(accM[j], m, one);
+        sD = __dp2a_lo(d, 0x0101u, sD);
+        sM = __dp2a_lo(m, 0x0101u, sM);
+    }
+    return sD + (sM << 20);   // sad <= 16*510 and cnt <= 16 per thread; x32 lanes still fits the 20/12-bit fields
+}
+
+template <int BPP, int CH, int MODE, int MAXREG>
+__global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int kWords = BPP * 4;  // 32-bit words of raw pixels per thread per frame
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t nthr = blockDim.x, nwarps = nthr >> 5;
+    const uint32_t nthr = blockDim.x;
     const uint32_t tile = blockIdx.x, seg = blockIdx.y;
     const uint32_t S = P.stages;
+    const uint32_t stage_bytes = P.stage_bytes;
+    const uint32_t slots = nthr * kPxPerThread;   // accumulator slots per tile (>= tile_px)
 
     // frame range of this segment, and the extra leading "prime" frame of per-frame mode
     const uint32_t t0 = (uint32_t)(((uint64_t)P.n_frames * seg) / P.n_segments);
@@ -169,60 +227,60 @@ __global__ void __maxnreg__(64) clip_kernel(const KParams P) {
     const uint64_t remain_px = P.npx - tile_first_px;
     const uint32_t valid_px = remain_px < P.tile_px ? (uint32_t)remain_px : P.tile_px;
     const uint32_t valid_bytes = valid_px * BPP;
-    const uint32_t bulk_bytes = valid_bytes & ~15u, tail_bytes = valid_bytes & 15u;
-    const uint32_t tile_bytes = P.tile_px * BPP;
 
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_base = smem_base + S * P.stage_bytes;  // full[S] then empty[S], 8 bytes each
-    auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (S + s); };
+    const uint32_t full_bar = smem_base + S * stage_bytes;   // full[S] then empty[S], 8 bytes each
+    const uint32_t empty_bar = full_bar + 8u * S;
 
-    if (valid_px < P.tile_px) {  // partial last tile: bytes past the valid range must read as zero
-        for (uint32_t o = tid * 16u; o < S * P.stage_bytes; o += nthr * 16u)
+    // Bytes past the tile's valid range must read as zero in every stage (TMA never writes them): the pixels they stand
+    // for then have I2 = 0 against a zero reference and contribute nothing.
+    if (valid_px < slots) {
+        for (uint32_t o = tid * 16u; o < S * stage_bytes; o += nthr * 16u)
             *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), nwarps);
+            mbar_init(full_bar + 8u * s, 1);
+            mbar_init(empty_bar + 8u * s, P.active_warps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (warp >= P.active_warps) return;   // warps without pixels (tile_px < 16*blockDim.x); they never touch a barrier
 
-    const uint8_t* src0 = P.frames + (uint64_t)first * P.stride + tile_first_px * BPP;
-    uint64_t policy = 0;
-    if (tid == 0) policy = policy_evict_first();
-
-    auto issue = [&](uint32_t iter, uint32_t stage) {  // thread 0 only
-        const uint8_t* src = src0 + (uint64_t)iter * P.stride;
-        const uint32_t dst = smem_base + stage * P.stage_bytes;
-        if (tail_bytes) {
-            for (uint32_t k = 0; k < tail_bytes; ++k) smem[stage * P.stage_bytes + bulk_bytes + k] = src[bulk_bytes + k];
-        }
-        mbar_arrive_expect_tx(full_bar(stage), bulk_bytes);
-        if (bulk_bytes) bulk_g2s(dst, src, bulk_bytes, full_bar(stage), policy);
+    // ---- producer (thread 0): one TMA bulk copy per frame, re-arming the buffer freed one iteration ago ----------------
+    // (the host only takes this kernel when frame bytes, base and stride are multiples of 16, so valid_bytes is too)
+    const uint64_t tile_byte0 = tile_first_px * BPP;
+    auto issue = [&](uint32_t it, uint32_t stage) {   // frame `first + it` of the call into buffer `stage`
+        const uint8_t* src = P.frames + (uint64_t)(first + it) * P.stride + tile_byte0;
+        mbar_arrive_expect_tx(full_bar + 8u * stage, valid_bytes);
+        if (P.l2_evict_first) bulk_g2s(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage, policy_evict_first());
+        else bulk_g2s_nohint(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage);
     };
-
     if (tid == 0) {
         const uint32_t pre = (S - 1 < count) ? S - 1 : count;
         for (uint32_t j = 0; j < pre; ++j) issue(j, j);
     }
 
-    // reference / previous-frame I2 of my 16 pixels (state planes are padded with zeros up to n_tiles*tile_px).
+    // ---- my 16 pixels: reference / previous-frame I2 (zero for slots beyond the tile's pixels) ---------------------------
     // 3 B/px: pixels tid*16 .. +15 of the tile; 4 B/px: groups of 4 pixels at 4*(v*nthr + tid), v = 0..3.
-    uint32_t ref[8];
+    uint32_t ra[8], rb[8];
     if constexpr (BPP == 3) {
-        const uint4* sp = reinterpret_cast<const uint4*>(P.state_in + tile_first_px + (uint64_t)tid * kPxPerThread);
-        const uint4 r0 = __ldg(sp), r1 = __ldg(sp + 1);
-        ref[0] = r0.x; ref[1] = r0.y; ref[2] = r0.z; ref[3] = r0.w;
-        ref[4] = r1.x; ref[5] = r1.y; ref[6] = r1.z; ref[7] = r1.w;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        if (tid * kPxPerThread < valid_px) {
+            const uint4* sp = reinterpret_cast<const uint4*>(P.state_in + tile_first_px + (uint64_t)tid * kPxPerThread);
+            r0 = __ldg(sp); r1 = __ldg(sp + 1);
+        }
+        ra[0] = r0.x; ra[1] = r0.y; ra[2] = r0.z; ra[3] = r0.w;
+        ra[4] = r1.x; ra[5] = r1.y; ra[6] = r1.z; ra[7] = r1.w;
     } else {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            const uint2 r = __ldg(reinterpret_cast<const uint2*>(P.state_in + tile_first_px + 4u * (v * nthr + tid)));
-            ref[2 * v] = r.x; ref[2 * v + 1] = r.y;
+            uint2 r = make_uint2(0, 0);
+            const uint32_t off = 4u * (v * nthr + tid);
+            if (off < valid_px) r = __ldg(reinterpret_cast<const uint2*>(P.state_in + tile_first_px + off));
+            ra[2 * v] = r.x; ra[2 * v + 1] = r.y;
         }
     }
     uint32_t accD[8], accM[8];
@@ -231,15 +289,14 @@ __global__ void __maxnreg__(64) clip_kernel(const KParams P) {
 
     const uint32_t tau = P.tau > 511u ? 511u : P.tau;
     const uint32_t negtau2 = ((0u - tau) & 0xFFFFu) * 0x00010001u;  // (-tau, -tau) as s16x2
-    const uint32_t one2 = 0x00010001u;
-    uint32_t* const acc_sum = P.acc_sum + tile_first_px + tid;
-    uint32_t* const acc_cnt = P.acc_cnt + tile_first_px + tid;
-    uint32_t* part = P.partials + (uint64_t)first * P.words_per_frame + tile * nwarps + warp;
+    uint32_t part = first * P.words_per_frame + tile * P.active_warps + warp;   // index into P.partials (host checks < 2^32)
     // 3 B/px: 48 contiguous bytes per thread; 4 B/px: four 16-byte groups strided by the block (both conflict-free)
     const uint32_t my_smem = smem_base + (BPP == 3 ? tid * 48u : tid * 16u);
     const uint32_t my_step = (BPP == 3) ? 16u : nthr * 16u;
 
     auto flush = [&]() {
+        uint32_t* const acc_sum = P.acc_sum + (uint64_t)tile * slots + tid;
+        uint32_t* const acc_cnt = P.acc_cnt + (uint64_t)tile * slots + tid;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             atomicAdd(acc_sum + (2 * j) * nthr, accD[j] & 0xFFFFu);
@@ -250,80 +307,102 @@ __global__ void __maxnreg__(64) clip_kernel(const KParams P) {
         }
     };
 
-    uint32_t stage = 0, parity = 0, prev_stage = 0, prev_parity = 0, since_flush = 0;
-#pragma unroll 1
-    for (uint32_t i = 0; i < count; ++i) {
-        // ---- consume stage: raw bytes -> registers, release the buffer
-        mbar_wait(full_bar(stage), parity);
+    uint32_t stage = 0, parity = 0, iter = 0;
+    // consume one frame: wait for its bytes, pull my pixels into registers, release the buffer, (thread 0) refill the
+    // buffer released in the previous iteration, and turn the bytes into 8 packed intensities
+    auto fetch = [&](uint32_t* cur, uint32_t token) {
+        mbar_wait_after(full_bar + 8u * stage, parity, token);
         uint32_t w[kWords];
 #pragma unroll
         for (int v = 0; v < BPP; ++v) {
-            const uint4 x = lds128(my_smem + stage * P.stage_bytes + my_step * v);
+            const uint4 x = lds128(my_smem + stage * stage_bytes + my_step * v);
             w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(stage));
-        // ---- producer duty (thread 0): refill the buffer released during the previous iteration
-        if (tid == 0) {
-            const uint32_t j = i + S - 1;
-            if (j < count) {
-                if (i > 0) mbar_wait(empty_bar(prev_stage), prev_parity);
-                issue(j, i > 0 ? prev_stage : S - 1);
-            }
+        if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
+        if (tid == 0 && iter + S - 1 < count) {
+            const uint32_t ps = stage == 0 ? S - 1 : stage - 1;   // == (iter + S - 1) % S
+            if (iter > 0) mbar_wait(empty_bar + 8u * ps, stage == 0 ? parity ^ 1u : parity);
+            issue(iter + S - 1, ps);
         }
-        prev_stage = stage; prev_parity = parity;
+        ++iter;
         if (++stage == S) { stage = 0; parity ^= 1u; }
-
-        // ---- intensity, difference, threshold, accumulate
-        uint32_t cur[8];
         intensity16<BPP, CH>(w, cur);
-        if (prime_first && i == 0) {  // halo frame t0-1: only establishes the previous-frame plane
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ref[j] = cur[j];
-            part += P.words_per_frame;
-            continue;
-        }
-        uint32_t sD = 0u, sM = 0u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t d = __vmaxu2(cur[j], ref[j]) - __vminu2(cur[j], ref[j]);  // |cur-ref| per half, no borrow
-            const uint32_t m = __viaddmin_s16x2_relu(d, negtau2, one2);              // (d - tau > 0) ? 1 : 0 per half
-            accD[j] += d; accM[j] += m;
-            sD += d; sM += m;
-            if (MODE == 1) ref[j] = cur[j];
-        }
-        // per-frame scalars: fold halves (IDP.2A), pack sad | cnt<<20, warp-reduce, one store per warp
-        const uint32_t packed = __dp2a_lo(sD, 0x0101u, __dp2a_lo(sM, 0x0101u, 0u) << 20);
+    };
+    auto emit = [&](uint32_t packed) {   // per-frame scalars: warp-reduce, one 4-byte store per warp per frame
         const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, packed);
-        if (lane == 0) *part = wsum;
+        if (lane == 0) P.partials[part] = wsum;
         part += P.words_per_frame;
-        if (++since_flush == (uint32_t)kFlushFrames) { flush(); since_flush = 0; }
+        return wsum;
+    };
+    const uint32_t one = P.one;
+
+    uint32_t token = 0;
+    if (prime_first) {   // halo frame t0-1: only establishes the previous-frame plane
+        fetch(ra, token);
+        part += P.words_per_frame;
+    }
+    const uint32_t iter0 = iter;   // 1 after a halo frame, else 0
+    // two frames per trip so that per-frame mode ping-pongs ra/rb without register moves
+    while (iter + 2 <= count) {
+        fetch(rb, token);
+        token = emit(diff16(rb, ra, accD, accM, negtau2, one));
+        if constexpr (MODE == 0) {
+            fetch(rb, token);
+            token = emit(diff16(rb, ra, accD, accM, negtau2, one));
+        } else {
+            fetch(ra, token);
+            token = emit(diff16(ra, rb, accD, accM, negtau2, one));
+        }
+        if (((iter - iter0) & (uint32_t)(kFlushFrames - 1)) == 0u) flush();   // every 128 accumulated frames
+    }
+    if (iter < count) {
+        fetch(rb, token);
+        emit(diff16(rb, ra, accD, accM, negtau2, one));
+        if constexpr (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ra[j] = rb[j];
+        }
     }
     flush();
 
     if (MODE == 1 && seg == P.n_segments - 1) {  // chain: I2 of the last frame becomes the next call's previous frame
         if constexpr (BPP == 3) {
-            uint4* sp = reinterpret_cast<uint4*>(P.state_out + tile_first_px + (uint64_t)tid * kPxPerThread);
-            sp[0] = make_uint4(ref[0], ref[1], ref[2], ref[3]);
-            sp[1] = make_uint4(ref[4], ref[5], ref[6], ref[7]);
+            if (tid * kPxPerThread < valid_px) {
+                uint4* sp = reinterpret_cast<uint4*>(P.state_out + tile_first_px + (uint64_t)tid * kPxPerThread);
+                sp[0] = make_uint4(ra[0], ra[1], ra[2], ra[3]);
+                sp[1] = make_uint4(ra[4], ra[5], ra[6], ra[7]);
+            }
         } else {
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-                *reinterpret_cast<uint2*>(P.state_out + tile_first_px + 4u * (v * nthr + tid)) =
-                    make_uint2(ref[2 * v], ref[2 * v + 1]);
+            for (int v = 0; v < 4; ++v) {
+                const uint32_t off = 4u * (v * nthr + tid);
+                if (off < valid_px)
+                    *reinterpret_cast<uint2*>(P.state_out + tile_first_px + off) = make_uint2(ra[2 * v], ra[2 * v + 1]);
+            }
         }
     }
 }
 
-template <int BPP, int CH, int MODE>
-cudaError_t launch_t(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
-    auto kfn = clip_kernel<BPP, CH, MODE>;
+template <int BPP, int CH, int MODE, int MAXREG>
+cudaError_t launch_r(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
+    auto kfn = clip_kernel<BPP, CH, MODE, MAXREG>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(g.n_tiles, a.n_segments, 1), block(g.threads, 1, 1);
     kfn<<<grid, block, smem, s>>>(kp);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int BPP, int CH, int MODE>
+cudaError_t launch_t(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
+    switch (g.regs) {   // register variant chosen by the planner: more registers <-> fewer resident warps
+        case 96: return launch_r<BPP, CH, MODE, 96>(g, a, kp, smem, s);
+        case 80: return launch_r<BPP, CH, MODE, 80>(g, a, kp, smem, s);
+        case 72: return launch_r<BPP, CH, MODE, 72>(g, a, kp, smem, s);
+        default: return launch_r<BPP, CH, MODE, 64>(g, a, kp, smem, s);
+    }
 }
 
 template <int BPP, int CH>
@@ -341,27 +420,29 @@ cudaError_t launch_c(const Geometry& g, const ClipArgs& a, const KParams& kp, si
     }
 }
 
-inline uint32_t stage_bytes_of(const Geometry& g) { return (g.tile_px * (uint32_t)g.bpp + 127u) & ~127u; }
+inline uint32_t stage_bytes_of(uint32_t threads, int bpp) { return (threads * kPxPerThread * (uint32_t)bpp + 127u) & ~127u; }
 
 }  // namespace
 
-size_t clip_smem_bytes(const Geometry& g, uint32_t stages) {
-    return (size_t)stages * stage_bytes_of(g) + 16u * stages;  // buffers + full/empty mbarriers
+size_t clip_smem_bytes(uint32_t threads, int bpp, uint32_t stages) {
+    return (size_t)stages * stage_bytes_of(threads, bpp) + 16u * stages;  // buffers + full/empty mbarriers
 }
 
-int clip_occupancy(const Geometry& g, uint32_t threads, uint32_t stages) {
-    Geometry t = g;
-    t.threads = threads;
-    t.tile_px = threads * kPxPerThread;
-    const size_t smem = clip_smem_bytes(t, stages) + 1024;  // + per-block reservation
+// registers are allocated per warp in units of 256: warps/SM = floor(65536 / (regs*32)), e.g. 72 -> 28, 80 -> 25, 96 -> 21
+int clip_max_threads_per_sm(int regs) { return (65536 / (regs * 32)) * 32; }
+
+int clip_occupancy(uint32_t threads, int bpp, uint32_t stages, int regs) {
+    const size_t smem = clip_smem_bytes(threads, bpp, stages) + 1024;  // + per-block reservation
     const size_t smem_sm = 227 * 1024;
     if (smem > smem_sm) return 0;
-    int by_smem = (int)(smem_sm / smem);
-    int by_regs = (int)(65536 / (64 * threads));
-    int by_thr = (int)(2048 / threads);
-    int occ = by_smem < by_regs ? by_smem : by_regs;
-    occ = occ < by_thr ? occ : by_thr;
+    const int by_smem = (int)(smem_sm / smem);
+    const int by_thr = clip_max_threads_per_sm(regs) / (int)threads;
+    int occ = by_smem < by_thr ? by_smem : by_thr;
     return occ > 32 ? 32 : occ;
+}
+
+uint32_t clip_active_warps(const Geometry& g) {
+    return g.bpp == 3 ? (g.tile_px + 511u) / 512u : g.threads / 32u;
 }
 
 cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
@@ -370,10 +451,14 @@ cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
     kp.state_in = a.state_in; kp.state_out = a.state_out;
     kp.acc_sum = a.acc_sum; kp.acc_cnt = a.acc_cnt; kp.partials = a.partials;
     kp.n_frames = a.n_frames; kp.n_segments = a.n_segments;
-    kp.tile_px = g.tile_px; kp.stages = g.stages; kp.stage_bytes = stage_bytes_of(g);
-    kp.words_per_frame = g.n_tiles * (g.threads / 32);
+    kp.tile_px = g.tile_px; kp.stages = g.stages; kp.stage_bytes = stage_bytes_of(g.threads, g.bpp);
+    kp.active_warps = clip_active_warps(g);
+    kp.words_per_frame = g.n_tiles * kp.active_warps;
     kp.tau = a.tau;
-    const size_t smem = clip_smem_bytes(g, g.stages);
+    static const int l2_hint = [] { const char* e = getenv("DIPSB_L2_EVICT_FIRST"); return e ? atoi(e) : 1; }();
+    kp.l2_evict_first = (uint32_t)l2_hint;
+    kp.one = 1u;
+    const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages);
     return g.bpp == 3 ? launch_c<3>(g, a, kp, smem, s) : launch_c<4>(g, a, kp, smem, s);
 }
 

@@ -16,12 +16,14 @@ struct Geometry {
     int bpp;                 // 3 or 4
     int format;              // dipsb_format
     int chan_byte;           // -1: all channels (max+min); else byte offset of the selected channel inside a pixel
-    uint32_t threads;        // consumer threads per block (multiple of 32)
-    uint32_t tile_px;        // threads * kPxPerThread
+    uint32_t threads;        // threads per block (multiple of 32); a block has 16*threads accumulator slots
+    uint32_t tile_px;        // pixels per tile: multiple of 16, <= 16*threads (chosen so the tiles fill the SMs evenly)
     uint32_t n_tiles;        // ceil(npx / tile_px)
-    uint64_t n_elems;        // n_tiles * tile_px: length of each accumulator plane in internal (tile) order
+    uint64_t n_elems;        // n_tiles * 16*threads: length of each accumulator plane in internal (tile) order
+    uint64_t state_elems;    // npx + 16*threads: length of a state plane (zero padded past npx)
     uint32_t blocks_per_sm;  // resident blocks per SM the plan assumes
     uint32_t stages;         // pipeline depth
+    int regs;                // register variant of the clip kernel (64, 72, 80 or 96 registers per thread)
     uint32_t num_sms;
 };
 
@@ -42,7 +44,7 @@ struct ClipArgs {
 // Which pixel of its tile does register slot k (0..15) of thread `thread` hold?
 //   3 B/px: 16 consecutive pixels per thread (48 contiguous bytes, conflict-free 128-bit shared loads at stride 48 B).
 //   4 B/px: four groups of 4 consecutive pixels, group v at 4*(v*threads + thread) (128-bit shared loads at stride 16 B).
-// index of pixel p in the internal accumulator order: tile*tile_px + k*threads + thread.
+// index of pixel p in the internal accumulator order: tile*(16*threads) + k*threads + thread.
 __host__ __device__ inline uint64_t tile_order_index(uint64_t p, uint32_t tile_px, uint32_t threads, int bpp) {
     const uint64_t tile = p / tile_px;
     const uint32_t q = (uint32_t)(p - tile * tile_px);
@@ -55,12 +57,15 @@ __host__ __device__ inline uint64_t tile_order_index(uint64_t p, uint32_t tile_p
         thread = r / 4u;
         k = 4u * v + (r % 4u);
     }
-    return tile * tile_px + (uint64_t)k * threads + thread;
+    return tile * ((uint64_t)threads * kPxPerThread) + (uint64_t)k * threads + thread;
 }
 
-size_t clip_smem_bytes(const Geometry& g, uint32_t stages);
-// returns resident blocks/SM for (threads, stages) or 0 when it does not fit
-int clip_occupancy(const Geometry& g, uint32_t threads, uint32_t stages);
+size_t clip_smem_bytes(uint32_t threads, int bpp, uint32_t stages);
+// resident threads per SM allowed by a register variant of the clip kernel (64 -> 1024, 72 -> 896, 80 -> 800, 96 -> 672)
+int clip_max_threads_per_sm(int regs);
+// resident blocks/SM for (threads, stages, register variant), or 0 when it does not fit
+int clip_occupancy(uint32_t threads, int bpp, uint32_t stages, int regs);
+uint32_t clip_active_warps(const Geometry& g);
 cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s);
 
 cudaError_t launch_prime(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s);

@@ -160,14 +160,19 @@ int32_t dipsb_synth_fill_device(int32_t device, void *d_dst, uint64_t first_fram
                                 void *stream);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t dipsb_launch_count(void);
-/* last clip kernel geometry, for reports: tiles, frame segments, threads per block, stages, blocks per SM */
+/* last clip kernel geometry, for reports: [0] tiles, [1] frame segments, [2] threads per block, [3] stages, [4] blocks per
+ * SM, [5] pixels per tile, [6] dynamic shared memory bytes | registers << 24, [7] 1 = TMA clip kernel / 0 = fallback */
 int32_t dipsb_last_plan(const dipsb_ctx *ctx, uint32_t out[8]);
 /* optional device-side timing of the clip kernel alone (cudaEvent pairs on the context's stream around each launch).
  * dipsb_clip_kernel_time synchronises, returns the summed milliseconds and launch count since the last call, and resets. */
 int32_t dipsb_enable_timing(dipsb_ctx *ctx, int32_t on);
 int32_t dipsb_clip_kernel_time(dipsb_ctx *ctx, double *total_ms, uint64_t *launches);
-/* tuning knobs (0 = automatic): force pipeline stages / pixels per tile / frame segments */
-int32_t dipsb_set_tuning(dipsb_ctx *ctx, uint32_t stages, uint32_t tile_px, uint32_t segments);
+/* host-only: the plan (same layout as dipsb_last_plan, [7] = active warps per block) the library would choose for a
+ * geometry on a device with num_sms SMs; touches no device. */
+int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t format, uint32_t num_sms, uint32_t out[8]);
+/* tuning knobs (0 = automatic): pipeline stages, pixels per tile (multiple of 16), frame segments, register variant of
+ * the clip kernel (64/72/80/96).  Geometry knobs can only change on a fresh or reset context. */
+int32_t dipsb_set_tuning(dipsb_ctx *ctx, uint32_t stages, uint32_t tile_px, uint32_t segments, uint32_t regs);
 
 #ifdef __cplusplus
 }

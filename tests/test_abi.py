@@ -74,3 +74,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp", ".hpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.replace("the oracle's generator", "").replace("as the oracle does", "").replace("oracle/dips_oracle.c", ""), f
+
+
+def test_planner_fills_the_sms_evenly():
+    """dipsb_plan_query is host-only: for the BASELINE geometries the tiles must fill 148 SMs in (nearly) whole waves."""
+    from dips_b200 import _lib
+    L = _lib.load()
+    for (w, h, fmt) in [(1920, 1080, 0), (3840, 2160, 1), (7680, 4320, 0), (640, 480, 0), (1, 1, 0), (37, 5, 0), (8192, 8192, 1)]:
+        out = (ctypes.c_uint32 * 8)()
+        assert L.dipsb_plan_query(w, h, fmt, 148, ctypes.byref(out)) == 0
+        tiles, threads, stages, occ, tile_px = out[0], out[2], out[3], out[4], out[5]
+        smem, regs = out[6] & 0xFFFFFF, out[6] >> 24
+        npx = w * h
+        assert threads % 32 == 0 and 32 <= threads <= 1024 and tile_px % 16 == 0 and tile_px <= 16 * threads
+        assert tiles == -(-npx // tile_px) and 2 <= stages <= 8 and occ >= 1 and regs in (64, 72, 80, 96)
+        assert occ * threads * regs <= 65536 and occ * (smem + 1024) <= 227 * 1024
+        resident = occ * 148
+        if tiles >= resident:                      # large frames: whole waves, < 3 % of the last wave idle
+            waves = -(-tiles // resident)
+            assert tiles / (waves * resident) > 0.97, (w, h, tiles, resident)
+    out = (ctypes.c_uint32 * 8)()
+    assert L.dipsb_plan_query(0, 10, 0, 148, ctypes.byref(out)) == -1

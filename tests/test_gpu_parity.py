@@ -166,18 +166,29 @@ def test_forced_frame_segments(torch_cuda, oracle, mode, segments):
     check(oracle, got, clip, 0, mode, 8)
 
 
-@pytest.mark.parametrize("tile_px,stages", [(512, 2), (1024, 3), (2048, 8), (8192, 4), (16384, 2)])
-def test_forced_tile_geometry(torch_cuda, oracle, tile_px, stages):
+@pytest.mark.parametrize("tile_px,stages,regs", [(512, 2, 0), (1040, 3, 72), (2048, 8, 64), (7008, 4, 80), (3504, 3, 96),
+                                                  (14336, 2, 72), (16384, 2, 64), (16, 3, 0)])
+def test_forced_tile_geometry(torch_cuda, oracle, tile_px, stages, regs):
     w, h, n = 300, 77, 12
     for fmt in (0, 1):
         clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
-        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, tuning=dict(stages=stages, tile_px=tile_px))
-        assert got[5]["tile_px"] == tile_px and got[5]["stages"] == stages
+        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, tuning=dict(stages=stages, tile_px=tile_px, regs=regs))
+        assert got[5]["tile_px"] == tile_px and got[5]["stages"] == stages and (not regs or got[5]["regs"] == regs)
         check(oracle, got, clip, fmt, 1, 8)
 
 
+@pytest.mark.parametrize("regs", [64, 72, 80, 96])
+@pytest.mark.parametrize("fmt,mode", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_register_variants(torch_cuda, oracle, regs, fmt, mode):
+    w, h, n = 640, 360, 140          # > 128 frames: crosses the packed-accumulator flush
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 20, tuning=dict(regs=regs))
+    assert got[5]["regs"] == regs
+    check(oracle, got, clip, fmt, mode, 20)
+
+
 def test_padded_stride_and_unaligned_fallback(torch_cuda, oracle):
-    w, h, n = 100, 30, 7
+    w, h, n = 112, 30, 7       # frame bytes are a multiple of 16 for both formats
     for fmt in (0, 1):
         clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
         pad = 48 + (-clip.shape[1]) % 16
@@ -190,12 +201,12 @@ def test_padded_stride_and_unaligned_fallback(torch_cuda, oracle):
         got = run_gpu(torch_cuda, clip, w, h, fmt, 0, 8, offset=3)            # unaligned base
         assert not got[5]["tma_path"]
         check(oracle, got, clip, fmt, 0, 8)
-    # frame size not a multiple of 16 bytes but aligned pitch: bulk part + tail bytes
+    # frame size not a multiple of 16 bytes (even with an aligned pitch): per-frame kernel
     w, h = 37, 5
     clip = oracle.synth_clip(n, w, h, 0, profile=oracle.SYNTH_UNIFORM)
     pad = (-clip.shape[1]) % 16
     got = run_gpu(torch_cuda, clip, w, h, 0, 0, 8, stride_pad=pad)
-    assert got[5]["tma_path"]
+    assert not got[5]["tma_path"]
     check(oracle, got, clip, 0, 0, 8)
 
 
