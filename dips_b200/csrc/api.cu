@@ -112,6 +112,9 @@ static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_til
         if (tile_px > max_slots) continue;
         const uint32_t thr = (uint32_t)((tile_px + kPxPerThread * 32 - 1) / (kPxPerThread * 32)) * 32;
         uint32_t stages = force_stages ? force_stages : 4;
+        // measured (profiles/r01_sweeps.md): 4 stages beat 3 for 42-49 KB slices, but a 4 x 56 KB ring (4K RGBx, 224 KB: all
+        // of the SM's shared memory) is slower than 3 x 56 KB -- keep the ring <= 200 KB
+        if (!force_stages && clip_smem_bytes(thr, g.bpp, stages) > 200 * 1024) stages = 3;
         int occ = clip_occupancy(thr, g.bpp, stages, regs);
         while (!force_stages && occ <= 0 && stages > 2) occ = clip_occupancy(thr, g.bpp, --stages, regs);
         if (occ <= 0) continue;
@@ -258,7 +261,7 @@ extern "C" int32_t dipsb_reset(dipsb_ctx* c) {
     CK(c, cudaSetDevice(c->device));
     const Geometry& g = c->g;
     CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
-    for (int k = 0; k < 2; ++k) CK(c, cudaMemsetAsync(c->state[k], 0, g.state_elems * sizeof(uint16_t), c->stream));
+    // the state planes need no clearing: the next run primes [0, npx) and the zero padding past npx is never written
     if (c->scal_cap) {
         CK(c, cudaMemsetAsync(c->d_sad, 0, c->scal_cap * sizeof(uint64_t), c->stream));
         CK(c, cudaMemsetAsync(c->d_cnt, 0, c->scal_cap * sizeof(uint64_t), c->stream));

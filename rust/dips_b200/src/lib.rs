@@ -1,0 +1,251 @@
+//! Safe wrappers that keep the reference's per-frame API so the callers compile unchanged:
+//!   * `ComputeState::{new, add_texture, dispatch}`  == dips/src/gpu/mod.rs:59, :170, :306
+//!   * `frame_callback`                              == dips/src/lib.rs:233-246
+//!   * `DiPsCompute::{new, send_frame}`              == dips_alt/src/dips_compute/mod.rs:270, :498
+//! The wgpu device/queue/bind-group machinery is gone: the state lives in a `dipsb_ctx` (CUDA, sm_100a).
+//! Shipped as source only (no Rust toolchain in the build image); see INTEGRATION.md for how a maintainer wires it in.
+use std::ffi::CStr;
+use std::ptr;
+
+use dips_b200_sys as sys;
+
+/// dips/src/lib.rs:26-41 (numbering of `Into<f64>`)
+#[derive(Copy, Clone, Debug)]
+pub enum DiPsFilter {
+    Unfiltered,
+    Sigmoid,
+    InverseSigmoid,
+}
+
+impl DiPsFilter {
+    fn as_ffi(self) -> i32 {
+        match self {
+            DiPsFilter::Unfiltered => sys::DIPSB_FILTER_NONE,
+            DiPsFilter::Sigmoid => sys::DIPSB_FILTER_SIGMOID,
+            DiPsFilter::InverseSigmoid => sys::DIPSB_FILTER_INV_SIGMOID,
+        }
+    }
+}
+
+/// dips/src/lib.rs:44-61
+#[derive(Copy, Clone, Debug)]
+pub enum ChromaFilter {
+    None,
+    Red,
+    Green,
+    Blue,
+}
+
+impl ChromaFilter {
+    fn as_ffi(self) -> i32 {
+        match self {
+            ChromaFilter::None => 0,
+            ChromaFilter::Red => 1,
+            ChromaFilter::Green => 2,
+            ChromaFilter::Blue => 3,
+        }
+    }
+}
+
+fn last_error(ctx: *const sys::dipsb_ctx) -> String {
+    unsafe { CStr::from_ptr(sys::dipsb_last_error(ctx)).to_string_lossy().into_owned() }
+}
+
+/// Same constructor arguments as the reference's `ComputeState::new` (dips/src/gpu/mod.rs:59-65).  The CUDA context is
+/// created lazily on the first `add_texture`, because the reference only learns the frame size there (:170).
+pub struct ComputeState {
+    colorize: bool,
+    spatial_window_size: i32,
+    sensitivity: f32,
+    filter_type: DiPsFilter,
+    chroma_filter: ChromaFilter,
+    ctx: *mut sys::dipsb_ctx,
+    width: u32,
+    height: u32,
+    pending: Vec<u8>,
+    have_frame: bool,
+}
+
+// One caller at a time, but the owner thread may change (GStreamer streaming thread vs. the smol executor thread,
+// dips/src/frame_extractor.rs:76, :232-234): Send, not Sync.  Every entry point of the library selects its device.
+unsafe impl Send for ComputeState {}
+
+impl ComputeState {
+    pub fn new(
+        colorize: bool,
+        spatial_window_size: i32,
+        sensitivity: f32,
+        filter_type: DiPsFilter,
+        chroma_filter: ChromaFilter,
+    ) -> anyhow::Result<Self> {
+        if spatial_window_size != 1 {
+            // windows > 1 are effectively broken in the reference shader; not reproduced
+            anyhow::bail!("spatial_window_size {} is not supported by the B200 path (only 1)", spatial_window_size);
+        }
+        Ok(Self {
+            colorize,
+            spatial_window_size,
+            sensitivity,
+            filter_type,
+            chroma_filter,
+            ctx: ptr::null_mut(),
+            width: 0,
+            height: 0,
+            pending: Vec::new(),
+            have_frame: false,
+        })
+    }
+
+    fn ensure_ctx(&mut self, width: u32, height: u32) -> anyhow::Result<()> {
+        if !self.ctx.is_null() && (width, height) == (self.width, self.height) {
+            return Ok(());
+        }
+        if !self.ctx.is_null() {
+            unsafe { sys::dipsb_destroy(self.ctx) };
+            self.ctx = ptr::null_mut();
+        }
+        let mut cfg: sys::dipsb_config = unsafe { std::mem::zeroed() };
+        unsafe { sys::dipsb_default_config(&mut cfg) };
+        cfg.width = width;
+        cfg.height = height;
+        cfg.format = sys::DIPSB_FMT_RGBX8; // the decoder hands over tightly packed RGBA (frame_extractor.rs:141-148)
+        cfg.mode = sys::DIPSB_MODE_OVERALL;
+        cfg.chroma = self.chroma_filter.as_ffi();
+        cfg.colorize = self.colorize as i32;
+        cfg.filter = self.filter_type.as_ffi();
+        cfg.sigmoid_scalar = self.sensitivity;
+        cfg.spatial_window = self.spatial_window_size;
+        let mut ctx = ptr::null_mut();
+        let rc = unsafe { sys::dipsb_create(&cfg, &mut ctx) };
+        if rc != sys::DIPSB_OK {
+            anyhow::bail!("dipsb_create failed ({}): {}", rc, last_error(ptr::null()));
+        }
+        self.ctx = ctx;
+        self.width = width;
+        self.height = height;
+        Ok(())
+    }
+
+    /// dips/src/gpu/mod.rs:170 -- the slice is borrowed for the call only, so it is copied here.
+    pub fn add_texture(&mut self, width: u32, height: u32, frame_data: &[u8]) {
+        if self.ensure_ctx(width, height).is_err() {
+            self.have_frame = false;
+            return;
+        }
+        self.pending.clear();
+        self.pending.extend_from_slice(frame_data);
+        self.have_frame = true;
+    }
+
+    /// dips/src/gpu/mod.rs:306 -- `None` while there is no reference yet (the caller passes the input through).
+    pub fn dispatch(&mut self) -> Option<Vec<u8>> {
+        if !self.have_frame || self.ctx.is_null() {
+            return None;
+        }
+        self.have_frame = false;
+        let mut out = vec![0u8; (self.width * self.height * 4) as usize];
+        let rc = unsafe {
+            sys::dipsb_push_frame(
+                self.ctx,
+                self.pending.as_ptr(),
+                self.width,
+                self.height,
+                self.width * 4,
+                sys::DIPSB_FMT_RGBX8,
+                out.as_mut_ptr(),
+                ptr::null_mut(),
+            )
+        };
+        match rc {
+            sys::DIPSB_OK => Some(out),
+            _ => None, // DIPSB_NOT_READY (reference frame) or an error: passthrough, like the reference's warm-up
+        }
+    }
+}
+
+impl Drop for ComputeState {
+    fn drop(&mut self) {
+        if !self.ctx.is_null() {
+            unsafe { sys::dipsb_destroy(self.ctx) };
+        }
+    }
+}
+
+/// dips/src/lib.rs:233-246, unchanged.
+pub fn frame_callback(width: u32, height: u32, frame_data: &[u8], compute: &mut ComputeState) -> Vec<u8> {
+    compute.add_texture(width, height, frame_data);
+    if let Some(new_frame) = compute.dispatch() {
+        new_frame
+    } else {
+        frame_data.to_vec()
+    }
+}
+
+/// dips_alt/src/dips_compute/mod.rs:151-234
+#[derive(Debug, Default, Copy, Clone, PartialEq)]
+pub enum Filter {
+    #[default]
+    Sigmoid = 0,
+    InverseSigmoid = 1,
+}
+
+#[derive(Debug, Copy, Clone)]
+pub struct DiPsProperties {
+    pub colorize: bool,
+    pub window_size: u8,
+    pub sigmoid_horizontal_scalar: f32,
+    pub filter_type: Filter,
+    pub chroma_filter: ChromaFilter,
+}
+
+/// `DiPsCompute::new(num_textures, w, h, window, device, queue, properties)` minus the wgpu handles, which have no
+/// meaning on the CUDA path (dips_alt/src/dips_compute/mod.rs:270-278); `send_frame` keeps its shape (:498-503) minus the
+/// swap-chain texture of the live-render path.
+pub struct DiPsCompute {
+    ctx: *mut sys::dipsb_ctx,
+    width: u32,
+    height: u32,
+}
+
+impl DiPsCompute {
+    pub fn new(_num_textures: usize, textures_width: u32, textures_height: u32, props: DiPsProperties) -> anyhow::Result<Self> {
+        let mut cfg: sys::dipsb_config = unsafe { std::mem::zeroed() };
+        unsafe { sys::dipsb_default_config(&mut cfg) };
+        cfg.width = textures_width;
+        cfg.height = textures_height;
+        cfg.format = sys::DIPSB_FMT_RGBX8;
+        cfg.mode = sys::DIPSB_MODE_OVERALL;
+        cfg.chroma = props.chroma_filter.as_ffi();
+        cfg.colorize = props.colorize as i32;
+        cfg.filter = props.filter_type as i32;
+        cfg.sigmoid_scalar = props.sigmoid_horizontal_scalar;
+        cfg.spatial_window = props.window_size as i32;
+        let mut ctx = ptr::null_mut();
+        let rc = unsafe { sys::dipsb_create(&cfg, &mut ctx) };
+        if rc != sys::DIPSB_OK {
+            anyhow::bail!("dipsb_create failed ({}): {}", rc, last_error(ptr::null()));
+        }
+        Ok(Self { ctx, width: textures_width, height: textures_height })
+    }
+
+    /// `snapshot: Some(())` makes this frame the new reference (dips_alt/src/lib.rs:222-225, refresh markers :668-670).
+    pub fn send_frame(&mut self, frame: &[u8], snapshot: Option<()>) -> Vec<u8> {
+        if snapshot.is_some() {
+            unsafe { sys::dipsb_snapshot(self.ctx) };
+        }
+        let mut out = vec![0u8; (self.width * self.height * 4) as usize];
+        let rc = unsafe {
+            sys::dipsb_push_frame(self.ctx, frame.as_ptr(), self.width, self.height, self.width * 4, sys::DIPSB_FMT_RGBX8, out.as_mut_ptr(), ptr::null_mut())
+        };
+        if rc < 0 {
+            panic!("dipsb_push_frame failed ({}): {}", rc, last_error(self.ctx)); // the reference panics on device loss too
+        }
+        out
+    }
+}
+
+impl Drop for DiPsCompute {
+    fn drop(&mut self) {
+        unsafe { sys::dipsb_destroy(self.ctx) };
+    }
+}

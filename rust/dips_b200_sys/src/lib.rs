@@ -1,0 +1,91 @@
+//! Raw bindings to `libdips_b200.so`.  One declaration per entry point of `include/dips_b200.h`, same order.
+//! NOTE: this crate is shipped as source only -- the build image has no Rust toolchain;
+//! it is kept in lock-step with the header by `tests/test_abi.py::test_rust_sys_crate_declares_every_symbol`.
+#![allow(non_camel_case_types)]
+
+use std::os::raw::{c_char, c_void};
+
+#[repr(C)]
+pub struct dipsb_ctx {
+    _private: [u8; 0],
+}
+
+pub const DIPSB_OK: i32 = 0;
+pub const DIPSB_NOT_READY: i32 = 1;
+pub const DIPSB_ERR_INVALID: i32 = -1;
+pub const DIPSB_ERR_CUDA: i32 = -2;
+pub const DIPSB_ERR_NOMEM: i32 = -3;
+pub const DIPSB_ERR_STATE: i32 = -4;
+
+pub const DIPSB_FMT_RGB8: i32 = 0;
+pub const DIPSB_FMT_RGBX8: i32 = 1;
+pub const DIPSB_FMT_BGR8: i32 = 2;
+pub const DIPSB_FMT_BGRX8: i32 = 3;
+pub const DIPSB_MODE_OVERALL: i32 = 0;
+pub const DIPSB_MODE_PERFRAME: i32 = 1;
+pub const DIPSB_FILTER_SIGMOID: i32 = 0;
+pub const DIPSB_FILTER_INV_SIGMOID: i32 = 1;
+pub const DIPSB_FILTER_NONE: i32 = 255;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct dipsb_config {
+    pub struct_size: u32,
+    pub device: i32,
+    pub width: u32,
+    pub height: u32,
+    pub format: i32,
+    pub mode: i32,
+    pub chroma: i32,
+    pub threshold: u32,
+    pub colorize: i32,
+    pub filter: i32,
+    pub sigmoid_scalar: f32,
+    pub spatial_window: i32,
+    pub reserved: [u32; 4],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct dipsb_frame_stats {
+    pub frame_index: u64,
+    pub sad: u64,
+    pub count: u64,
+}
+
+extern "C" {
+    pub fn dipsb_abi_version() -> i32;
+    pub fn dipsb_default_config(cfg: *mut dipsb_config);
+    pub fn dipsb_create(cfg: *const dipsb_config, out: *mut *mut dipsb_ctx) -> i32;
+    pub fn dipsb_destroy(ctx: *mut dipsb_ctx);
+    pub fn dipsb_last_error(ctx: *const dipsb_ctx) -> *const c_char;
+    pub fn dipsb_reset(ctx: *mut dipsb_ctx) -> i32;
+    pub fn dipsb_set_threshold(ctx: *mut dipsb_ctx, threshold: u32) -> i32;
+    pub fn dipsb_set_stream(ctx: *mut dipsb_ctx, stream: *mut c_void) -> i32;
+    pub fn dipsb_use_private_stream(ctx: *mut dipsb_ctx) -> i32;
+    pub fn dipsb_synchronize(ctx: *mut dipsb_ctx) -> i32;
+    pub fn dipsb_prime_device(ctx: *mut dipsb_ctx, d_frame: *const c_void) -> i32;
+    pub fn dipsb_prime_median4_device(ctx: *mut dipsb_ctx, d_frames: *const c_void, frame_stride_bytes: u64) -> i32;
+    pub fn dipsb_prime_host(ctx: *mut dipsb_ctx, frame: *const u8) -> i32;
+    pub fn dipsb_state_plane_device(ctx: *mut dipsb_ctx, d_state: *mut *mut c_void) -> i32;
+    pub fn dipsb_mark_state_valid(ctx: *mut dipsb_ctx, valid: i32) -> i32;
+    pub fn dipsb_get_state_plane(ctx: *mut dipsb_ctx, out: *mut u16) -> i32;
+    pub fn dipsb_run_clip_device(ctx: *mut dipsb_ctx, d_frames: *const c_void, n_frames: u64, frame_stride_bytes: u64, first_frame_index: u64) -> i32;
+    pub fn dipsb_run_clip_host(ctx: *mut dipsb_ctx, frames: *const u8, n_frames: u64, frame_stride_bytes: u64, first_frame_index: u64) -> i32;
+    pub fn dipsb_push_frame(ctx: *mut dipsb_ctx, px: *const u8, width: u32, height: u32, stride: u32, format: i32, out_rgba: *mut u8, stats: *mut dipsb_frame_stats) -> i32;
+    pub fn dipsb_snapshot(ctx: *mut dipsb_ctx) -> i32;
+    pub fn dipsb_frames_processed(ctx: *const dipsb_ctx) -> u64;
+    pub fn dipsb_get_accumulators(ctx: *mut dipsb_ctx, acc_sum: *mut u32, acc_cnt: *mut u32) -> i32;
+    pub fn dipsb_set_accumulators(ctx: *mut dipsb_ctx, acc_sum: *const u32, acc_cnt: *const u32) -> i32;
+    pub fn dipsb_accumulators_device(ctx: *mut dipsb_ctx, d_acc: *mut *mut c_void, n_elems: *mut u64) -> i32;
+    pub fn dipsb_get_scalars(ctx: *mut dipsb_ctx, first: u64, n: u64, sad: *mut u64, cnt: *mut u64) -> i32;
+    pub fn dipsb_get_intensity_map(ctx: *mut dipsb_ctx, n_eff: u64, out: *mut f32) -> i32;
+    pub fn dipsb_get_frame_means(ctx: *mut dipsb_ctx, first: u64, n: u64, out: *mut f32) -> i32;
+    pub fn dipsb_synth_fill_device(device: i32, d_dst: *mut c_void, first_frame: u64, n_frames: u64, width: u32, height: u32, format: i32, seed: u64, profile: i32, stream: *mut c_void) -> i32;
+    pub fn dipsb_launch_count() -> u64;
+    pub fn dipsb_last_plan(ctx: *const dipsb_ctx, out: *mut u32) -> i32;
+    pub fn dipsb_enable_timing(ctx: *mut dipsb_ctx, on: i32) -> i32;
+    pub fn dipsb_clip_kernel_time(ctx: *mut dipsb_ctx, total_ms: *mut f64, launches: *mut u64) -> i32;
+    pub fn dipsb_plan_query(width: u32, height: u32, format: i32, num_sms: u32, out: *mut u32) -> i32;
+    pub fn dipsb_set_tuning(ctx: *mut dipsb_ctx, stages: u32, tile_px: u32, segments: u32, regs: u32) -> i32;
+}

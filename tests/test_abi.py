@@ -95,3 +95,10 @@ def test_planner_fills_the_sms_evenly():
             assert tiles / (waves * resident) > 0.97, (w, h, tiles, resident)
     out = (ctypes.c_uint32 * 8)()
     assert L.dipsb_plan_query(0, 10, 0, 148, ctypes.byref(out)) == -1
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/dips_b200_sys (shipped as source: no Rust toolchain here) must stay 1:1 with include/dips_b200.h."""
+    text = open(os.path.join(ROOT, "rust", "dips_b200_sys", "src", "lib.rs")).read()
+    rust = set(re.findall(r"pub fn (dipsb_[a-z0-9_]+)\s*\(", text))
+    assert rust == set(declared_symbols()), rust ^ set(declared_symbols())
