@@ -14,7 +14,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32),
         ("format", C.c_int32), ("mode", C.c_int32), ("chroma", C.c_int32), ("threshold", C.c_uint32),
         ("colorize", C.c_int32), ("filter", C.c_int32), ("sigmoid_scalar", C.c_float), ("spatial_window", C.c_int32),
-        ("reserved", C.c_uint32 * 4),
+        ("flavor", C.c_int32), ("reserved", C.c_uint32 * 3),
     ]
 
 

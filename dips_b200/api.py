@@ -16,6 +16,7 @@ MODE_OVERALL, MODE_PERFRAME = 0, 1
 CHROMA_NONE, CHROMA_RED, CHROMA_GREEN, CHROMA_BLUE = 0, 1, 2, 3
 FILTER_SIGMOID, FILTER_INV_SIGMOID, FILTER_NONE = 0, 1, 255
 SYNTH_UNIFORM, SYNTH_SCENE = 0, 1
+FLAVOR_FRAME0, FLAVOR_DIPS_RING4, FLAVOR_ALT_RING2, FLAVOR_ALT_RING2_MEDIAN = 0, 1, 2, 3
 OK, NOT_READY = 0, 1
 
 
@@ -53,13 +54,13 @@ class Context:
 
     def __init__(self, width: int, height: int, fmt: int = FMT_RGBX8, mode: int = MODE_OVERALL, threshold: int = 0,
                  chroma: int = CHROMA_NONE, device: int = 0, colorize: bool = False, filt: int = FILTER_NONE,
-                 sigmoid_scalar: float = 5.0, spatial_window: int = 1):
+                 sigmoid_scalar: float = 5.0, spatial_window: int = 1, flavor: int = FLAVOR_FRAME0):
         self._lib = _lib.load()
         cfg = _lib.Config()
         self._lib.dipsb_default_config(C.byref(cfg))
         cfg.device, cfg.width, cfg.height, cfg.format, cfg.mode = device, width, height, fmt, mode
         cfg.chroma, cfg.threshold, cfg.colorize, cfg.filter = chroma, threshold, int(colorize), filt
-        cfg.sigmoid_scalar, cfg.spatial_window = sigmoid_scalar, spatial_window
+        cfg.sigmoid_scalar, cfg.spatial_window, cfg.flavor = sigmoid_scalar, spatial_window, flavor
         h = C.c_void_p()
         rc = self._lib.dipsb_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -38,6 +38,8 @@ struct dipsb_ctx {
     uint64_t partial_cap = 0;                  // in u32 words
     uint64_t frames_processed = 0;
     uint64_t stream_index = 0;                 // logical index of the next pushed frame
+    uint16_t* ring = nullptr;                  // ring flavours: 4 (dips) or 2 (dips_alt) u16 I2 planes of npx
+    uint32_t ring_seen = 0, ring_index = 0;    // frames pushed since the last (re)start, next slot to overwrite
     // streaming staging
     uint8_t* d_frame = nullptr; size_t d_frame_bytes = 0;
     uint8_t* d_rgba = nullptr;
@@ -167,7 +169,7 @@ static void free_all(dipsb_ctx* c) {
         if (c->d_chunk[k]) cudaFree(c->d_chunk[k]);
     }
     cudaFree(c->acc); cudaFree(c->planar); cudaFree(c->d_sad); cudaFree(c->d_cnt); cudaFree(c->partials);
-    cudaFree(c->d_frame); cudaFree(c->d_rgba);
+    cudaFree(c->d_frame); cudaFree(c->d_rgba); cudaFree(c->ring);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_stat) cudaFreeHost(c->h_stat);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -184,6 +186,10 @@ static int32_t alloc_planes(dipsb_ctx* c) {
     CK(c, cudaMalloc(&c->acc, 2 * g.n_elems * sizeof(uint32_t)));
     CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
     CK(c, cudaMalloc(&c->planar, 2 * g.npx * sizeof(uint32_t)));
+    if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0 && !c->ring) {
+        CK(c, cudaMalloc(&c->ring, 4 * g.npx * sizeof(uint16_t)));
+        CK(c, cudaMemsetAsync(c->ring, 0, 4 * g.npx * sizeof(uint16_t), c->stream));   // wgpu textures start zeroed
+    }
     return DIPSB_OK;
 }
 
@@ -197,6 +203,9 @@ extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
     if (cfg->mode != DIPSB_MODE_OVERALL && cfg->mode != DIPSB_MODE_PERFRAME)
         return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: bad mode %d", cfg->mode);
     if (cfg->chroma < 0 || cfg->chroma > 3) return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: bad chroma %d", cfg->chroma);
+    if (cfg->flavor < 0 || cfg->flavor > 3) return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: bad flavor %d", cfg->flavor);
+    if (cfg->flavor != DIPSB_FLAVOR_FRAME0 && cfg->mode != DIPSB_MODE_OVERALL)
+        return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: the ring flavours are overall-mode only");
     if (cfg->spatial_window != 1 && cfg->spatial_window != 0)
         return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: spatial_window %d not implemented (only 1)", cfg->spatial_window);
     int ndev = 0;
@@ -261,6 +270,11 @@ extern "C" int32_t dipsb_reset(dipsb_ctx* c) {
     CK(c, cudaSetDevice(c->device));
     const Geometry& g = c->g;
     CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
+    if (c->ring) {
+        CK(c, cudaMemsetAsync(c->ring, 0, 4 * g.npx * sizeof(uint16_t), c->stream));
+        for (int k = 0; k < 2; ++k) CK(c, cudaMemsetAsync(c->state[k], 0, g.state_elems * sizeof(uint16_t), c->stream));
+    }
+    c->ring_seen = 0; c->ring_index = 0;
     // the state planes need no clearing: the next run primes [0, npx) and the zero padding past npx is never written
     if (c->scal_cap) {
         CK(c, cudaMemsetAsync(c->d_sad, 0, c->scal_cap * sizeof(uint64_t), c->stream));
@@ -439,6 +453,7 @@ static int32_t ensure_scalars(dipsb_ctx* c, uint64_t upto) {
 static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first) {
     const Geometry& g = c->g;
     if (n == 0) return DIPSB_OK;
+    if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0) return fail(c, DIPSB_ERR_STATE, "run_clip: the ring flavours are streaming-only (dipsb_push_frame)");
     if (n > 0x7FFFFFFFull) return fail(c, DIPSB_ERR_INVALID, "run_clip: too many frames in one call");
     if (stride < g.npx * g.bpp) return fail(c, DIPSB_ERR_INVALID, "run_clip: stride %llu smaller than a frame", (unsigned long long)stride);
     int32_t rc = ensure_scalars(c, first + n);
@@ -595,26 +610,63 @@ extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t wi
     else for (uint32_t y = 0; y < height; ++y) memcpy(c->h_pin + (uint64_t)y * row, px + (uint64_t)y * stride, row);
     CK(c, cudaMemcpyAsync(c->d_frame, c->h_pin, fb, cudaMemcpyHostToDevice, c->stream));
     const uint64_t idx = c->stream_index;
-    const bool establishes = !c->state_valid || c->snapshot_pending;
-    FrameArgs f;
-    f.frame = c->d_frame; f.pitch = row; f.format = format; f.chan_byte = chan_byte_of(format, c->cfg.chroma);
-    f.acc_sum = c->acc; f.acc_cnt = c->acc + g.n_elems;
-    f.sad = c->d_sad + idx; f.cnt = c->d_cnt + idx;
-    f.tau = c->cfg.threshold; f.colorize = c->cfg.colorize; f.filter = c->cfg.filter; f.sig_scalar = c->cfg.sigmoid_scalar;
     CK(c, cudaMemsetAsync(c->d_sad + idx, 0, sizeof(uint64_t), c->stream));
     CK(c, cudaMemsetAsync(c->d_cnt + idx, 0, sizeof(uint64_t), c->stream));
-    if (establishes) {
-        // this frame becomes the reference: D = 0 for it, output is the input passed through (dips/src/lib.rs:241-245)
-        f.state_in = c->state[c->state_cur]; f.state_out = c->state[c->state_cur]; f.out_rgba = nullptr; f.accumulate = 0;
-        CK(c, launch_frame(g, f, c->stream));
-        if (out_rgba) CK(c, launch_passthrough_rgba(g, c->d_frame, row, format, c->d_rgba, c->stream));
-        c->state_valid = true;
-        c->snapshot_pending = false;
+    bool establishes;
+    if (c->cfg.flavor == DIPSB_FLAVOR_FRAME0) {
+        establishes = !c->state_valid || c->snapshot_pending;
+        FrameArgs f;
+        f.frame = c->d_frame; f.pitch = row; f.format = format; f.chan_byte = chan_byte_of(format, c->cfg.chroma);
+        f.acc_sum = c->acc; f.acc_cnt = c->acc + g.n_elems;
+        f.sad = c->d_sad + idx; f.cnt = c->d_cnt + idx;
+        f.tau = c->cfg.threshold; f.colorize = c->cfg.colorize; f.filter = c->cfg.filter; f.sig_scalar = c->cfg.sigmoid_scalar;
+        if (establishes) {
+            // this frame becomes the reference: D = 0 for it, output is the input passed through (dips/src/lib.rs:241-245)
+            f.state_in = c->state[c->state_cur]; f.state_out = c->state[c->state_cur]; f.out_rgba = nullptr; f.accumulate = 0;
+            CK(c, launch_frame(g, f, c->stream));
+            if (out_rgba) CK(c, launch_passthrough_rgba(g, c->d_frame, row, format, c->d_rgba, c->stream));
+            c->state_valid = true;
+            c->snapshot_pending = false;
+        } else {
+            f.state_in = c->state[c->state_cur];
+            f.state_out = c->cfg.mode == DIPSB_MODE_PERFRAME ? c->state[c->state_cur] : nullptr;
+            f.out_rgba = out_rgba ? c->d_rgba : nullptr; f.accumulate = 1;
+            CK(c, launch_frame(g, f, c->stream));
+        }
     } else {
-        f.state_in = c->state[c->state_cur];
-        f.state_out = c->cfg.mode == DIPSB_MODE_PERFRAME ? c->state[c->state_cur] : nullptr;
-        f.out_rgba = out_rgba ? c->d_rgba : nullptr; f.accumulate = 1;
-        CK(c, launch_frame(g, f, c->stream));
+        RingArgs r;
+        r.frame = c->d_frame; r.pitch = row; r.format = format; r.chan_byte = chan_byte_of(format, c->cfg.chroma);
+        r.ring = c->ring; r.start = c->state[c->state_cur];
+        r.acc_sum = c->acc; r.acc_cnt = c->acc + g.n_elems; r.sad = c->d_sad + idx; r.cnt = c->d_cnt + idx;
+        r.out_rgba = out_rgba ? c->d_rgba : nullptr;
+        r.tau = c->cfg.threshold; r.colorize = c->cfg.colorize; r.filter = c->cfg.filter; r.sig_scalar = c->cfg.sigmoid_scalar;
+        r.grey_slot = -1; r.compute_start = 0; r.snapshot = 0; r.median_is_max = 0; r.do_diff = 1;
+        if (c->cfg.flavor == DIPSB_FLAVOR_DIPS_RING4) {
+            if (c->snapshot_pending) { c->ring_seen = 0; c->ring_index = 0; c->snapshot_pending = false; }   // restart the warm-up
+            r.n_slots = 4;
+            const uint32_t seen = ++c->ring_seen;                     // frames including this one
+            if (seen < 4) {                                            // dispatch() == None: passthrough (mod.rs:394-396)
+                r.write_slot = (int)seen - 1; r.do_diff = 0;
+            } else if (seen == 4) {                                    // pre-compute + first dispatch on slot 0 (mod.rs:177-214)
+                r.write_slot = 3; r.compute_start = 1; r.grey_slot = 0;
+            } else {                                                   // update_temporal_texture (bind_groups.rs:407-427)
+                r.write_slot = r.grey_slot = (int)c->ring_index;
+                c->ring_index = (c->ring_index + 1) % 4;
+            }
+            if (seen > 4) c->ring_seen = 5;                            // saturate
+            establishes = seen < 4;
+        } else {
+            r.n_slots = 2;
+            r.median_is_max = c->cfg.flavor == DIPSB_FLAVOR_ALT_RING2_MEDIAN;
+            r.write_slot = (int)c->ring_index;                        // texture_index, mod.rs:507-521
+            c->ring_index = (c->ring_index + 1) % 2;
+            r.snapshot = c->snapshot_pending ? 1 : 0;
+            c->snapshot_pending = false;
+            establishes = false;                                       // dips_alt always returns a computed frame
+        }
+        CK(c, launch_ring(g, r, c->stream));
+        if (establishes && out_rgba) CK(c, launch_passthrough_rgba(g, c->d_frame, row, format, c->d_rgba, c->stream));
+        c->state_valid = true;
     }
     if (out_rgba) CK(c, cudaMemcpyAsync(c->h_pin, c->d_rgba, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaMemcpyAsync(&c->h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));

@@ -172,6 +172,79 @@ __global__ void frame_kernel(const FrameK K) {
     }
 }
 
+// Reference-flavour rings (N1).  Everything is kept in I2 units (x510): a raw slot holds max+min, a grey slot holds
+// 2*q with q = unorm8 store of the intensity = floor(I2/2 + 0.5) = (I2+1)>>1 (dips_shader.wgsl:187 writes the filtered
+// newest frame back as rgba8unorm grey), so the float expressions of the shader become exact integers until the colour map.
+struct RingK {
+    const uint8_t* frame; uint64_t pitch; uint32_t width, height; int bpp, chan_byte;
+    uint16_t* ring; int n_slots, write_slot, grey_slot, compute_start, snapshot, median_is_max, do_diff;
+    uint16_t* start; uint32_t* acc_sum; uint32_t* acc_cnt; unsigned long long* sad; unsigned long long* cnt; uint8_t* out_rgba;
+    uint32_t tau, tile_px, threads; int geo_bpp, colorize, filter; float sig;
+};
+__device__ __forceinline__ uint32_t upper_median4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {   // sorted[2]
+    const uint32_t lo01 = min(a, b), hi01 = max(a, b), lo23 = min(c, d), hi23 = max(c, d);
+    return max(max(lo01, lo23), min(hi01, hi23));
+}
+__global__ void ring_kernel(const RingK K) {
+    const uint64_t npx = (uint64_t)K.width * K.height;
+    unsigned long long s = 0, c = 0;
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(p / K.width), x = (uint32_t)(p - (uint64_t)y * K.width);
+        const uint32_t raw = intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
+        uint32_t v[4] = {0, 0, 0, 0};
+        for (int k = 0; k < K.n_slots; ++k) v[k] = K.ring[(uint64_t)k * npx + p];
+        v[K.write_slot] = raw;
+        uint32_t start = K.start[p], med;
+        bool grey_out = false;
+        if (K.n_slots == 4) {                                       // `dips`
+            if (K.compute_start) {                                   // pre_compute_shader.wgsl:103-131, stored rgba8unorm
+                start = 2u * ((upper_median4(v[0], v[1], v[2], v[3]) + 1u) >> 1);
+                K.start[p] = (uint16_t)start;
+            }
+            if (K.grey_slot >= 0) {                                  // dips_shader.wgsl:187
+                v[K.grey_slot] = 2u * ((v[K.grey_slot] + 1u) >> 1);
+                K.ring[(uint64_t)K.grey_slot * npx + p] = (uint16_t)v[K.grey_slot];
+            }
+            if (K.grey_slot != K.write_slot) K.ring[(uint64_t)K.write_slot * npx + p] = (uint16_t)v[K.write_slot];
+            med = upper_median4(v[0], v[1], v[2], v[3]);             // :191-214
+        } else {                                                     // `dips_alt`, NUM_TEXTURES = 2
+            K.ring[(uint64_t)K.write_slot * npx + p] = (uint16_t)raw;
+            med = K.median_is_max ? max(v[0], v[1]) : min(v[0], v[1]);
+            if (K.snapshot) {                                        // pre_compute_shader.wgsl:231-235
+                start = 2u * ((med + 1u) >> 1);
+                K.start[p] = (uint16_t)start;
+                grey_out = true;
+            }
+        }
+        if (!K.do_diff) continue;
+        if (grey_out) {
+            const uint8_t q = (uint8_t)(start >> 1);
+            if (K.out_rgba) reinterpret_cast<uchar4*>(K.out_rgba)[p] = make_uchar4(q, q, q, 255);
+            continue;
+        }
+        const int sdiff = (int)start - (int)med;
+        const uint32_t d = (uint32_t)(sdiff < 0 ? -sdiff : sdiff);
+        const uint32_t m = d > K.tau ? 1u : 0u;
+        const uint64_t q = tile_order_index(p, K.tile_px, K.threads, K.geo_bpp);
+        K.acc_sum[q] += d;
+        K.acc_cnt[q] += m;
+        s += d; c += m;
+        if (K.out_rgba) reinterpret_cast<uchar4*>(K.out_rgba)[p] = visual_pixel(sdiff, K.colorize, K.filter, K.sig);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+        c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+    }
+    __shared__ unsigned long long sh_s[kThreads / 32], sh_c[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_c[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kThreads / 32; ++k) { s += sh_s[k]; c += sh_c[k]; }
+        if (s) atomicAdd(K.sad, s);
+        if (c) atomicAdd(K.cnt, c);
+    }
+}
+
 // warm-up passthrough of frame_callback (dips/src/lib.rs:241-245): input converted to RGBA8, alpha 255
 __global__ void passthrough_kernel(const uint8_t* __restrict__ frame, uint64_t pitch, uint32_t width, uint32_t height,
                                    int format, uint8_t* __restrict__ out) {
@@ -274,6 +347,20 @@ cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) 
     K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp;
     K.accumulate = a.accumulate; K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
     frame_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(K);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s) {
+    RingK K;
+    K.frame = a.frame; K.pitch = a.pitch; K.width = g.width; K.height = g.height;
+    K.bpp = (a.format == 0 || a.format == 2) ? 3 : 4; K.chan_byte = a.chan_byte;
+    K.ring = a.ring; K.n_slots = a.n_slots; K.write_slot = a.write_slot; K.grey_slot = a.grey_slot;
+    K.compute_start = a.compute_start; K.snapshot = a.snapshot; K.median_is_max = a.median_is_max; K.do_diff = a.do_diff;
+    K.start = a.start; K.acc_sum = a.acc_sum; K.acc_cnt = a.acc_cnt;
+    K.sad = reinterpret_cast<unsigned long long*>(a.sad); K.cnt = reinterpret_cast<unsigned long long*>(a.cnt);
+    K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp;
+    K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
+    ring_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(K);
     count_launch();
     return cudaGetLastError();
 }

@@ -94,6 +94,22 @@ struct FrameArgs {
     float sig_scalar;
 };
 cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s);
+// reference-flavour temporal rings (N1): one frame against a ring of u16 I2 planes
+struct RingArgs {
+    const uint8_t* frame; uint64_t pitch; int format; int chan_byte;
+    uint16_t* ring;              // n_slots planes of npx u16
+    int n_slots;                 // 4 (dips) or 2 (dips_alt)
+    int write_slot;              // slot that receives the raw I2 of this frame
+    int grey_slot;               // slot quantised to grey in place (dips), -1: none
+    int compute_start;           // dips: start plane := grey(upper median of the 4 raw slots)
+    int snapshot;                // dips_alt: snapshot plane := grey(median), output = that grey
+    int median_is_max;           // dips_alt: 0 = as shipped (min of two), 1 = in-bounds median (max of two)
+    int do_diff;                 // produce output / accumulate (0 during warm-up)
+    uint16_t* start;             // start / snapshot plane (u16, I2 units, even values)
+    uint32_t* acc_sum; uint32_t* acc_cnt; uint64_t* sad; uint64_t* cnt; uint8_t* out_rgba;
+    uint32_t tau; int colorize, filter; float sig_scalar;
+};
+cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s);
 cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uint64_t pitch, int format,
                                     uint8_t* out_rgba, cudaStream_t s);
 cudaError_t launch_synth(uint8_t* dst, uint64_t first_frame, uint64_t n_frames, uint32_t w, uint32_t h, int bpp,

@@ -60,6 +60,19 @@ enum dipsb_chroma { DIPSB_CHROMA_NONE = 0, DIPSB_CHROMA_RED = 1, DIPSB_CHROMA_GR
 /* numbering of dips/src/lib.rs:32-41 */
 enum dipsb_filter { DIPSB_FILTER_SIGMOID = 0, DIPSB_FILTER_INV_SIGMOID = 1, DIPSB_FILTER_NONE = 255 };
 enum dipsb_synth { DIPSB_SYNTH_UNIFORM = 0, DIPSB_SYNTH_SCENE = 1 };
+/*
+ * Temporal semantics of dipsb_push_frame:
+ *   FRAME0        north star: the reference is the first frame pushed (or a prime / snapshot), temporal window 1.
+ *   DIPS_RING4    the `dips` crate as shipped: the first 3 frames pass through; start plane = grey(upper median of the
+ *                 first 4 frames); every output = start - median(ring of 4), the newest ring slot quantised to grey in
+ *                 place (dips/src/gpu/mod.rs:170-216, bind_groups.rs:407-427, dips_shader.wgsl:187-214).
+ *   ALT_RING2     `dips_alt` as shipped: ring of 2 frames, "median" = min of the two (zero-sentinel sort,
+ *                 pre_compute_shader.wgsl:212-227); dipsb_snapshot() makes the next frame store and return the grey
+ *                 snapshot (dips_alt/src/lib.rs:222-225); until then the snapshot plane is zero.
+ *   ALT_RING2_MEDIAN  the same with the in-bounds median (max of the two).
+ * The ring flavours exist for drop-in visual parity; they are streaming-only (dipsb_run_clip_* needs FRAME0).
+ */
+enum dipsb_flavor { DIPSB_FLAVOR_FRAME0 = 0, DIPSB_FLAVOR_DIPS_RING4 = 1, DIPSB_FLAVOR_ALT_RING2 = 2, DIPSB_FLAVOR_ALT_RING2_MEDIAN = 3 };
 
 typedef struct dipsb_config {
     uint32_t struct_size;      /* sizeof(dipsb_config), for ABI evolution */
@@ -74,7 +87,8 @@ typedef struct dipsb_config {
     int32_t filter;            /* dipsb_filter, FILTER_TYPE override */
     float sigmoid_scalar;      /* SIGMOID_HORIZONTAL_SCALAR override (UI "sensitivity") */
     int32_t spatial_window;    /* WINDOW_SIZE override; only 1 is implemented */
-    uint32_t reserved[4];
+    int32_t flavor;            /* dipsb_flavor */
+    uint32_t reserved[3];
 } dipsb_config;
 
 typedef struct dipsb_frame_stats {

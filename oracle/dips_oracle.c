@@ -363,3 +363,61 @@ int dipso_cs_frame(dipso_cs *cs, const uint8_t *rgba_in, uint8_t *rgba_out) {
     }
     return 0;
 }
+
+/* ---- reference-flavour `dips_alt` DiPsCompute (N1) ----------------------------------------- */
+
+struct dipso_alt {
+    uint32_t w, h;
+    int colorize, filter, chroma, intended;
+    float sig_scalar;
+    unsigned index;       /* texture_index, UCircularIndex(0, NUM_TEXTURES), dips_alt/src/dips_compute/mod.rs:519 */
+    uint8_t *ring[2];     /* input_textures, RGBA8, zero-initialised */
+    uint8_t *snap;        /* snapshot_texture, RGBA8, zero-initialised */
+};
+
+dipso_alt *dipso_alt_new(uint32_t width, uint32_t height, int colorize, int filter, float sig_scalar, int chroma,
+                         int intended_median) {
+    dipso_alt *a = (dipso_alt *)calloc(1, sizeof(*a));
+    const size_t fb = (size_t)width * height * 4;
+    a->w = width; a->h = height; a->colorize = colorize; a->filter = filter; a->chroma = chroma;
+    a->intended = intended_median; a->sig_scalar = sig_scalar;
+    a->ring[0] = (uint8_t *)calloc(fb, 1); a->ring[1] = (uint8_t *)calloc(fb, 1); a->snap = (uint8_t *)calloc(fb, 1);
+    return a;
+}
+
+void dipso_alt_free(dipso_alt *a) {
+    if (!a) return;
+    free(a->ring[0]); free(a->ring[1]); free(a->snap); free(a);
+}
+
+void dipso_alt_frame(dipso_alt *a, const uint8_t *rgba_in, int snapshot, uint8_t *rgba_out) {
+    const size_t npx = (size_t)a->w * a->h;
+    memcpy(a->ring[a->index], rgba_in, npx * 4);             /* write_texture into slot index, then index += 1 (:507-521) */
+    a->index = (a->index + 1) % 2;
+    for (size_t p = 0; p < npx; ++p) {
+        /* median_array[i] = intensity of texture i (WINDOW_SIZE == 1), 16-slot array otherwise zero (:201-211) */
+        float v[3] = { intensity_f32(a->ring[0] + 4 * p, a->chroma), intensity_f32(a->ring[1] + 4 * p, a->chroma), 0.0f };
+        float med;
+        if (a->intended) {
+            med = v[0] > v[1] ? v[0] : v[1];                 /* sorted[N/2] of the two real values */
+        } else {
+            /* as shipped: i,j < NUM_TEXTURES compare [j],[j+1] -- the zero in slot 2 takes part (:212-227) */
+            for (int i = 0; i < 2; ++i) {
+                int swapped = 0;
+                for (int j = 0; j < 2; ++j)
+                    if (v[j] > v[j + 1]) { float t = v[j]; v[j] = v[j + 1]; v[j + 1] = t; swapped = 1; }
+                if (!swapped) break;
+            }
+            med = v[1];                                      /* median_array[NUM_TEXTURES / 2] */
+        }
+        if (snapshot) {                                      /* :231-235 */
+            const uint8_t q = unorm8(med);
+            uint8_t *s = a->snap + 4 * p, *o = rgba_out + 4 * p;
+            s[0] = s[1] = s[2] = q; s[3] = 255;
+            o[0] = o[1] = o[2] = q; o[3] = 255;
+        } else {                                             /* :236-262 */
+            const float diff = a->snap[4 * p] / 255.0f - med;
+            visual_from_diff(visual_chain(diff, a->filter, a->sig_scalar), a->colorize, rgba_out + 4 * p);
+        }
+    }
+}

@@ -94,6 +94,19 @@ dipso_cs *dipso_cs_new(uint32_t width, uint32_t height, int colorize, int filter
 void dipso_cs_free(dipso_cs *cs);
 int dipso_cs_frame(dipso_cs *cs, const uint8_t *rgba_in, uint8_t *rgba_out);
 
+/*
+ * Reference-flavour state machine of `dips_alt` (N1): DiPsCompute::send_frame, dips_alt/src/dips_compute/mod.rs:498-646,
+ * kernel dips_alt/src/dips_compute/shaders/pre_compute_shader.wgsl:188-263 with NUM_TEXTURES = FRAME_COUNT = 2
+ * (dips_alt/src/lib.rs:36).  `snapshot` != 0 == send_frame(.., Some(()), ..).  `intended_median` == 0 reproduces the
+ * as-shipped sort (a zero sentinel is sorted in, so median_array[N/2] is the MIN of the two frames);
+ * 1 gives the in-bounds reading (sorted[N/2] of the N real values).  Textures start zero-initialised (wgpu).
+ */
+typedef struct dipso_alt dipso_alt;
+dipso_alt *dipso_alt_new(uint32_t width, uint32_t height, int colorize, int filter, float sig_scalar, int chroma,
+                         int intended_median);
+void dipso_alt_free(dipso_alt *a);
+void dipso_alt_frame(dipso_alt *a, const uint8_t *rgba_in, int snapshot, uint8_t *rgba_out);
+
 int dipso_num_threads(void);
 
 #ifdef __cplusplus

@@ -71,6 +71,12 @@ def lib() -> C.CDLL:
         L.dipso_cs_free.restype = None
         L.dipso_cs_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.dipso_cs_frame.restype = C.c_int
+        L.dipso_alt_new.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+        L.dipso_alt_new.restype = C.c_void_p
+        L.dipso_alt_free.argtypes = [C.c_void_p]
+        L.dipso_alt_free.restype = None
+        L.dipso_alt_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.dipso_alt_frame.restype = None
         L.dipso_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -186,4 +192,24 @@ class ComputeStateOracle:
     def __del__(self):
         if getattr(self, "_h", None):
             lib().dipso_cs_free(self._h)
+            self._h = None
+
+
+class DiPsComputeOracle:
+    """Reference-flavour `dips_alt` DiPsCompute (dips_alt/src/dips_compute/mod.rs) on RGBA8 frames."""
+
+    def __init__(self, width, height, colorize=True, filt=FILTER_SIGMOID, sig_scalar=5.0, chroma=CHROMA_NONE,
+                 intended_median=False):
+        self.w, self.h = width, height
+        self._h = lib().dipso_alt_new(width, height, int(colorize), filt, sig_scalar, chroma, int(intended_median))
+
+    def send_frame(self, rgba: np.ndarray, snapshot: bool = False) -> np.ndarray:
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8).reshape(-1)
+        out = np.empty_like(rgba)
+        lib().dipso_alt_frame(self._h, _ptr(rgba), int(snapshot), _ptr(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dipso_alt_free(self._h)
             self._h = None

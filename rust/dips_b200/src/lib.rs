@@ -64,6 +64,8 @@ pub struct ComputeState {
     height: u32,
     pending: Vec<u8>,
     have_frame: bool,
+    /// true (default): the crate's own temporal semantics (median-of-4 ring); false: reference = first frame
+    pub reference_exact: bool,
 }
 
 // One caller at a time, but the owner thread may change (GStreamer streaming thread vs. the smol executor thread,
@@ -93,6 +95,7 @@ impl ComputeState {
             height: 0,
             pending: Vec::new(),
             have_frame: false,
+            reference_exact: true,
         })
     }
 
@@ -115,6 +118,9 @@ impl ComputeState {
         cfg.filter = self.filter_type.as_ffi();
         cfg.sigmoid_scalar = self.sensitivity;
         cfg.spatial_window = self.spatial_window_size;
+        // DIPSB_FLAVOR_DIPS_RING4 reproduces the crate's median-of-4 ring and 3 passthrough frames exactly;
+        // DIPSB_FLAVOR_FRAME0 is the north-star semantics (reference = first frame, 1 passthrough frame)
+        cfg.flavor = if self.reference_exact { sys::DIPSB_FLAVOR_DIPS_RING4 } else { sys::DIPSB_FLAVOR_FRAME0 };
         let mut ctx = ptr::null_mut();
         let rc = unsafe { sys::dipsb_create(&cfg, &mut ctx) };
         if rc != sys::DIPSB_OK {
@@ -220,6 +226,7 @@ impl DiPsCompute {
         cfg.filter = props.filter_type as i32;
         cfg.sigmoid_scalar = props.sigmoid_horizontal_scalar;
         cfg.spatial_window = props.window_size as i32;
+        cfg.flavor = sys::DIPSB_FLAVOR_ALT_RING2; // as shipped: 2-frame ring, snapshot on request
         let mut ctx = ptr::null_mut();
         let rc = unsafe { sys::dipsb_create(&cfg, &mut ctx) };
         if rc != sys::DIPSB_OK {

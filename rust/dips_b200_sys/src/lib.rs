@@ -23,6 +23,10 @@ pub const DIPSB_FMT_BGR8: i32 = 2;
 pub const DIPSB_FMT_BGRX8: i32 = 3;
 pub const DIPSB_MODE_OVERALL: i32 = 0;
 pub const DIPSB_MODE_PERFRAME: i32 = 1;
+pub const DIPSB_FLAVOR_FRAME0: i32 = 0;
+pub const DIPSB_FLAVOR_DIPS_RING4: i32 = 1;
+pub const DIPSB_FLAVOR_ALT_RING2: i32 = 2;
+pub const DIPSB_FLAVOR_ALT_RING2_MEDIAN: i32 = 3;
 pub const DIPSB_FILTER_SIGMOID: i32 = 0;
 pub const DIPSB_FILTER_INV_SIGMOID: i32 = 1;
 pub const DIPSB_FILTER_NONE: i32 = 255;
@@ -42,7 +46,8 @@ pub struct dipsb_config {
     pub filter: i32,
     pub sigmoid_scalar: f32,
     pub spatial_window: i32,
-    pub reserved: [u32; 4],
+    pub flavor: i32,
+    pub reserved: [u32; 3],
 }
 
 #[repr(C)]

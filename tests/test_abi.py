@@ -102,3 +102,17 @@ def test_rust_sys_crate_declares_every_symbol():
     text = open(os.path.join(ROOT, "rust", "dips_b200_sys", "src", "lib.rs")).read()
     rust = set(re.findall(r"pub fn (dipsb_[a-z0-9_]+)\s*\(", text))
     assert rust == set(declared_symbols()), rust ^ set(declared_symbols())
+
+
+def test_header_is_valid_c_and_links(tmp_path):
+    """include/dips_b200.h compiles as C11 and a C program can call the library (what any FFI relies on)."""
+    import subprocess
+    from dips_b200 import _build
+    so_dir = os.path.dirname(_build.build())
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", so_dir, "-ldips_b200",
+                           "-Wl,-rpath," + so_dir])
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "plan:" in res.stdout

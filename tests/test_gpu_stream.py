@@ -88,3 +88,56 @@ def test_push_then_batch_interop(oracle):
         sad, cnt = ctx.get_scalars(0, 20)
     assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
     assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)
+
+
+def _within(a, b, tol):
+    return np.abs(a.astype(int) - b.astype(int)) <= tol
+
+
+@pytest.mark.parametrize("filt,colorize", [(255, False), (0, False), (0, True)])
+@pytest.mark.parametrize("chroma", [0, 2])
+def test_dips_ring4_flavour_matches_reference_state_machine(oracle, filt, colorize, chroma):
+    """N1: `dips` crate semantics -- 3 passthrough frames, start = grey(upper median of 4), output = start - median of the
+    4-frame ring with in-place grey quantisation.  The GPU keeps everything in exact integers (ties of the rgba8unorm
+    store round half up); the oracle restates the shader in f32, where a .5 tie may land on either side (the reference
+    leaves it to the driver).  One grey level of the start/ring plane is 2.5 LSB of output (x0.5 x5), hence: every pixel
+    within 3 LSB, and at least 97 % within 1 LSB."""
+    import dips_b200
+    w, h, n = 80, 45, 11
+    clip = oracle.synth_clip(n, w, h, oracle.FMT_RGBX8, profile=oracle.SYNTH_SCENE)
+    cs = oracle.ComputeStateOracle(w, h, colorize, filt, 5.0, chroma)
+    with dips_b200.Context(w, h, dips_b200.FMT_RGBX8, 0, 0, chroma, colorize=colorize, filt=filt,
+                           flavor=dips_b200.FLAVOR_DIPS_RING4) as ctx:
+        for t in range(n):
+            want, passthrough = cs.frame(clip[t])
+            rc, got, _ = ctx.push_frame(clip[t])
+            assert (rc == dips_b200.NOT_READY) == passthrough == (t < 3)
+            if passthrough:
+                assert np.array_equal(got, clip[t])
+            else:
+                assert _within(got, want, 3).all(), f"frame {t}: max diff {np.abs(got.astype(int) - want.astype(int)).max()}"
+                assert _within(got, want, 1).mean() >= 0.97
+        with pytest.raises(dips_b200.DipsError):
+            ctx.run_clip_device(0, 1)                  # ring flavours are streaming-only
+
+
+@pytest.mark.parametrize("intended", [False, True])
+@pytest.mark.parametrize("filt,colorize", [(0, True), (255, False), (1, False)])
+def test_dips_alt_ring2_flavour_matches_reference_state_machine(oracle, intended, filt, colorize):
+    """N1: `dips_alt` semantics -- 2-frame ring, min-of-two (as shipped) or in-bounds median, snapshot on the 3rd frame and
+    at a refresh marker (dips_alt/src/lib.rs:222-225, :668-670).  Same tolerance reasoning as the ring-of-4 test."""
+    import dips_b200
+    w, h, n = 64, 36, 10
+    clip = oracle.synth_clip(n, w, h, oracle.FMT_RGBX8, profile=oracle.SYNTH_SCENE)
+    ref = oracle.DiPsComputeOracle(w, h, colorize, filt, 5.0, 0, intended)
+    flavor = dips_b200.FLAVOR_ALT_RING2_MEDIAN if intended else dips_b200.FLAVOR_ALT_RING2
+    with dips_b200.Context(w, h, dips_b200.FMT_RGBX8, 0, 0, colorize=colorize, filt=filt, flavor=flavor) as ctx:
+        for t in range(n):
+            snap = t in (2, 6)
+            want = ref.send_frame(clip[t], snap)
+            if snap:
+                ctx.snapshot()
+            rc, got, _ = ctx.push_frame(clip[t])
+            assert rc == 0
+            assert _within(got, want, 3).all(), f"frame {t}: max diff {np.abs(got.astype(int) - want.astype(int)).max()}"
+            assert _within(got, want, 1).mean() >= 0.97

@@ -189,3 +189,24 @@ def test_compute_state_flavour(oracle):
     outs = [cs2.frame(clip[0])[0] for _ in range(6)]
     grey = outs[-1].reshape(-1, 4)
     assert np.all(np.abs(grey[:, :3].astype(int) - 128) <= 1) and np.all(grey[:, 3] == 255)
+
+
+def test_dips_alt_flavour(oracle):
+    """dips_alt DiPsCompute: zero snapshot until the first snapshot, grey snapshot frame, min-of-two quirk vs intended."""
+    w, h = 12, 6
+    clip = oracle.synth_clip(5, w, h, oracle.FMT_RGBX8, profile=oracle.SYNTH_SCENE)
+    for intended in (False, True):
+        a = oracle.DiPsComputeOracle(w, h, colorize=False, filt=oracle.FILTER_NONE, intended_median=intended)
+        i2 = [oracle.i2_plane(clip[t], oracle.FMT_RGBX8).astype(int) for t in range(5)]
+        out0 = a.send_frame(clip[0]).reshape(-1, 4)
+        # ring = [frame0, zeros]; as shipped the median is min(I0, 0) = 0 -> diff 0 -> mid grey; intended: max = I0
+        if not intended:
+            assert np.all(np.abs(out0[:, 0].astype(int) - 128) <= 1)
+        else:
+            want = np.clip(np.floor((0.5 + 2.5 * i2[0] / 510.0) * 255 + 0.5), 0, 255)
+            assert np.all(np.abs(out0[:, 0].astype(int) - want) <= 1)
+        a.send_frame(clip[1])
+        snap = a.send_frame(clip[2], snapshot=True).reshape(-1, 4)
+        med = np.maximum(i2[1], i2[2]) if intended else np.minimum(i2[1], i2[2])
+        assert np.all(np.abs(snap[:, 0].astype(int) - (med + 1) // 2) <= 1) and np.all(snap[:, 3] == 255)
+        assert np.all(snap[:, 0] == snap[:, 1]) and np.all(snap[:, 1] == snap[:, 2])
