@@ -348,6 +348,30 @@ def main():
                "h2d_GBps_per_gpu": e2e_frames * fb * args.e2e_steps / dt / 1e9}
         del host
 
+    # ---- streaming boundary (the reference's per-frame callback shape): RGBA8 frame in -> RGBA8 difference frame out ----
+    stream_info = None
+    if not args.no_e2e and world == 1:
+        sw, sh, sn = 1920, 1080, 60
+        frames_rgba = np.empty((8, sw * sh * 4), np.uint8)
+        tmp = torch.empty(8 * sw * sh * 4, dtype=torch.uint8, device=dev)
+        dips_b200.synth_fill_device(local_rank, tmp.data_ptr(), 0, 8, sw, sh, dips_b200.FMT_RGBX8, SEED,
+                                    dips_b200.SYNTH_SCENE, stream.cuda_stream)
+        torch.cuda.synchronize()
+        frames_rgba[:] = tmp.cpu().numpy().reshape(8, -1)
+        del tmp
+        stream_info = {"geometry": "1920x1080 RGBx8 in, RGBA8 difference frame out, per-frame call", "frames": sn}
+        for name in ("dipsb_push_frame", "dipsb_push_frame_pipelined"):
+            with dips_b200.Context(sw, sh, dips_b200.FMT_RGBX8, 0, tau, device=local_rank) as sctx:
+                fn = sctx.push_frame if name == "dipsb_push_frame" else sctx.push_frame_pipelined
+                for k in range(4):
+                    fn(frames_rgba[k % 8])
+                t0 = time.perf_counter()
+                for k in range(sn):
+                    fn(frames_rgba[k % 8])
+                if name != "dipsb_push_frame":
+                    sctx.flush_frame()
+                stream_info[name + "_fps"] = sn / (time.perf_counter() - t0)
+
     # ---- CPU baseline (rank 0, N == 1 only) -----------------------------------------------------------------------
     cpu = None
     if not args.no_cpu and world == 1:
@@ -364,7 +388,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
             "hbm_GBps_per_gpu_whole_step": frames * fb * args.steps / (ms_total / 1e3) / 1e9,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "stream": stream_info,
+            "gpu_launches": int(launches) * world,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -180,6 +180,28 @@ class Context:
                                                  _host_ptr(out) if want_rgba else None, C.byref(st)))
         return rc, out, (int(st.frame_index), int(st.sad), int(st.count))
 
+    def push_frame_pipelined(self, frame: np.ndarray, fmt: int | None = None, stride: int | None = None):
+        """Submit `frame`, get back the previous frame's result: (status, rgba or None, stats or None).
+        status: NOT_READY (first call), 0 (difference frame of t-1), 2 (t-1 was a passed-through warm-up frame)."""
+        fmt = self.fmt if fmt is None else fmt
+        frame = np.ascontiguousarray(frame, dtype=np.uint8)
+        stride = stride or self.width * bytes_per_pixel(fmt)
+        out = np.empty(self.npx * 4, np.uint8)
+        st = _lib.FrameStats()
+        rc = self._ck(self._lib.dipsb_push_frame_pipelined(self._h, _host_ptr(frame), self.width, self.height, stride,
+                                                           fmt, _host_ptr(out), C.byref(st)))
+        if rc == NOT_READY:
+            return rc, None, None
+        return rc, out, (int(st.frame_index), int(st.sad), int(st.count))
+
+    def flush_frame(self):
+        out = np.empty(self.npx * 4, np.uint8)
+        st = _lib.FrameStats()
+        rc = self._ck(self._lib.dipsb_flush_frame(self._h, _host_ptr(out), C.byref(st)))
+        if rc == NOT_READY:
+            return rc, None, None
+        return rc, out, (int(st.frame_index), int(st.sad), int(st.count))
+
     def snapshot(self) -> None:
         self._ck(self._lib.dipsb_snapshot(self._h))
 

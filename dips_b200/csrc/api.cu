@@ -45,6 +45,14 @@ struct dipsb_ctx {
     uint8_t* d_rgba = nullptr;
     uint8_t* h_pin = nullptr; size_t h_pin_bytes = 0;   // pinned bounce buffer (frame in / rgba out)
     uint64_t* h_stat = nullptr;                          // pinned [2]
+    // frame slots of the streaming path (slot 0 only for the synchronous call, both for the pipelined one)
+    struct FrameSlot {
+        uint8_t* h_in = nullptr; uint8_t* d_in = nullptr; size_t in_bytes = 0;
+        uint8_t* d_out = nullptr; uint8_t* h_out = nullptr; uint64_t* h_stat = nullptr;
+        cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
+        bool pending = false, want_rgba = false; int32_t status = 0; uint64_t idx = 0;
+    } slot[2];
+    int next_slot = 0;
     // host clip staging
     uint8_t* h_chunk[2] = {nullptr, nullptr};
     uint8_t* d_chunk[2] = {nullptr, nullptr};
@@ -173,6 +181,14 @@ static void free_all(dipsb_ctx* c) {
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_stat) cudaFreeHost(c->h_stat);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+    for (auto& sl : c->slot) {
+        if (sl.h_in) cudaFreeHost(sl.h_in);
+        if (sl.h_out) cudaFreeHost(sl.h_out);
+        if (sl.h_stat) cudaFreeHost(sl.h_stat);
+        cudaFree(sl.d_in); cudaFree(sl.d_out);
+        if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 }
@@ -590,10 +606,28 @@ extern "C" int32_t dipsb_snapshot(dipsb_ctx* c) {
     return DIPSB_OK;
 }
 
-extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t width, uint32_t height, uint32_t stride,
-                                    int32_t format, uint8_t* out_rgba, dipsb_frame_stats* stats) {
-    if (!c || !px) return DIPSB_ERR_INVALID;
-    CK(c, cudaSetDevice(c->device));
+static int32_t ensure_slot(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, size_t in_bytes) {
+    const size_t rgba = c->g.npx * 4;
+    if (sl.in_bytes < in_bytes) {
+        if (sl.h_in) cudaFreeHost(sl.h_in);
+        cudaFree(sl.d_in);
+        sl.h_in = nullptr; sl.d_in = nullptr; sl.in_bytes = 0;
+        CK(c, cudaMallocHost(&sl.h_in, in_bytes));
+        CK(c, cudaMalloc(&sl.d_in, in_bytes));
+        sl.in_bytes = in_bytes;
+    }
+    if (!sl.d_out) CK(c, cudaMalloc(&sl.d_out, rgba));
+    if (!sl.h_out) CK(c, cudaMallocHost(&sl.h_out, rgba));
+    if (!sl.h_stat) CK(c, cudaMallocHost(&sl.h_stat, 2 * sizeof(uint64_t)));
+    if (!sl.ev_h2d) CK(c, cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+    if (!sl.ev_done) CK(c, cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    return DIPSB_OK;
+}
+
+// Stage one frame into `sl` and enqueue upload, kernel and read-back.  `overlap`: upload on the copy stream so that it runs
+// concurrently with the previous frame's kernel / read-back (pipelined mode); otherwise everything on the context's stream.
+static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_t* px, uint32_t width, uint32_t height,
+                            uint32_t stride, int32_t format, bool want_rgba, bool overlap) {
     const Geometry& g = c->g;
     if (width != g.width || height != g.height) return fail(c, DIPSB_ERR_INVALID, "push_frame: %ux%u does not match the context's %ux%u", width, height, g.width, g.height);
     if (format < 0 || format > 3) return fail(c, DIPSB_ERR_INVALID, "push_frame: bad format %d", format);
@@ -601,14 +635,20 @@ extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t wi
     const uint64_t row = (uint64_t)width * bpp;
     if (stride < row) return fail(c, DIPSB_ERR_INVALID, "push_frame: stride %u smaller than a row (%llu)", stride, (unsigned long long)row);
     const size_t fb = row * height;
-    int32_t rc = ensure_frame_staging(c, fb);
+    int32_t rc = ensure_slot(c, sl, fb);
     if (rc) return rc;
     rc = ensure_scalars(c, c->stream_index + 1);
     if (rc) return rc;
     // the input slice is borrowed for the call only (frame_extractor.rs:224-226): copy it out before returning
-    if (stride == row) memcpy(c->h_pin, px, fb);
-    else for (uint32_t y = 0; y < height; ++y) memcpy(c->h_pin + (uint64_t)y * row, px + (uint64_t)y * stride, row);
-    CK(c, cudaMemcpyAsync(c->d_frame, c->h_pin, fb, cudaMemcpyHostToDevice, c->stream));
+    if (stride == row) memcpy(sl.h_in, px, fb);
+    else for (uint32_t y = 0; y < height; ++y) memcpy(sl.h_in + (uint64_t)y * row, px + (uint64_t)y * stride, row);
+    if (overlap) {
+        CK(c, cudaMemcpyAsync(sl.d_in, sl.h_in, fb, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(c, cudaEventRecord(sl.ev_h2d, c->copy_stream));
+        CK(c, cudaStreamWaitEvent(c->stream, sl.ev_h2d, 0));
+    } else {
+        CK(c, cudaMemcpyAsync(sl.d_in, sl.h_in, fb, cudaMemcpyHostToDevice, c->stream));
+    }
     const uint64_t idx = c->stream_index;
     CK(c, cudaMemsetAsync(c->d_sad + idx, 0, sizeof(uint64_t), c->stream));
     CK(c, cudaMemsetAsync(c->d_cnt + idx, 0, sizeof(uint64_t), c->stream));
@@ -616,7 +656,7 @@ extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t wi
     if (c->cfg.flavor == DIPSB_FLAVOR_FRAME0) {
         establishes = !c->state_valid || c->snapshot_pending;
         FrameArgs f;
-        f.frame = c->d_frame; f.pitch = row; f.format = format; f.chan_byte = chan_byte_of(format, c->cfg.chroma);
+        f.frame = sl.d_in; f.pitch = row; f.format = format; f.chan_byte = chan_byte_of(format, c->cfg.chroma);
         f.acc_sum = c->acc; f.acc_cnt = c->acc + g.n_elems;
         f.sad = c->d_sad + idx; f.cnt = c->d_cnt + idx;
         f.tau = c->cfg.threshold; f.colorize = c->cfg.colorize; f.filter = c->cfg.filter; f.sig_scalar = c->cfg.sigmoid_scalar;
@@ -624,21 +664,21 @@ extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t wi
             // this frame becomes the reference: D = 0 for it, output is the input passed through (dips/src/lib.rs:241-245)
             f.state_in = c->state[c->state_cur]; f.state_out = c->state[c->state_cur]; f.out_rgba = nullptr; f.accumulate = 0;
             CK(c, launch_frame(g, f, c->stream));
-            if (out_rgba) CK(c, launch_passthrough_rgba(g, c->d_frame, row, format, c->d_rgba, c->stream));
+            if (want_rgba) CK(c, launch_passthrough_rgba(g, sl.d_in, row, format, sl.d_out, c->stream));
             c->state_valid = true;
             c->snapshot_pending = false;
         } else {
             f.state_in = c->state[c->state_cur];
             f.state_out = c->cfg.mode == DIPSB_MODE_PERFRAME ? c->state[c->state_cur] : nullptr;
-            f.out_rgba = out_rgba ? c->d_rgba : nullptr; f.accumulate = 1;
+            f.out_rgba = want_rgba ? sl.d_out : nullptr; f.accumulate = 1;
             CK(c, launch_frame(g, f, c->stream));
         }
     } else {
         RingArgs r;
-        r.frame = c->d_frame; r.pitch = row; r.format = format; r.chan_byte = chan_byte_of(format, c->cfg.chroma);
+        r.frame = sl.d_in; r.pitch = row; r.format = format; r.chan_byte = chan_byte_of(format, c->cfg.chroma);
         r.ring = c->ring; r.start = c->state[c->state_cur];
         r.acc_sum = c->acc; r.acc_cnt = c->acc + g.n_elems; r.sad = c->d_sad + idx; r.cnt = c->d_cnt + idx;
-        r.out_rgba = out_rgba ? c->d_rgba : nullptr;
+        r.out_rgba = want_rgba ? sl.d_out : nullptr;
         r.tau = c->cfg.threshold; r.colorize = c->cfg.colorize; r.filter = c->cfg.filter; r.sig_scalar = c->cfg.sigmoid_scalar;
         r.grey_slot = -1; r.compute_start = 0; r.snapshot = 0; r.median_is_max = 0; r.do_diff = 1;
         if (c->cfg.flavor == DIPSB_FLAVOR_DIPS_RING4) {
@@ -665,19 +705,63 @@ extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t wi
             establishes = false;                                       // dips_alt always returns a computed frame
         }
         CK(c, launch_ring(g, r, c->stream));
-        if (establishes && out_rgba) CK(c, launch_passthrough_rgba(g, c->d_frame, row, format, c->d_rgba, c->stream));
+        if (establishes && want_rgba) CK(c, launch_passthrough_rgba(g, sl.d_in, row, format, sl.d_out, c->stream));
         c->state_valid = true;
     }
-    if (out_rgba) CK(c, cudaMemcpyAsync(c->h_pin, c->d_rgba, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(&c->h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(&c->h_stat[1], c->d_cnt + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    if (out_rgba) memcpy(out_rgba, c->h_pin, g.npx * 4);
-    if (stats) { stats->frame_index = idx; stats->sad = c->h_stat[0]; stats->count = c->h_stat[1]; }
+    if (want_rgba) CK(c, cudaMemcpyAsync(sl.h_out, sl.d_out, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&sl.h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&sl.h_stat[1], c->d_cnt + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaEventRecord(sl.ev_done, c->stream));
+    sl.pending = true; sl.want_rgba = want_rgba; sl.idx = idx; sl.status = establishes ? DIPSB_NOT_READY : DIPSB_OK;
     c->stream_index = idx + 1;
     c->frames_processed += 1;
     c->scal_hi = std::max(c->scal_hi, idx + 1);
-    return establishes ? DIPSB_NOT_READY : DIPSB_OK;
+    return DIPSB_OK;
+}
+
+// wait for the frame in `sl` and hand its output to the caller; returns the frame's own status (OK / NOT_READY)
+static int32_t collect_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, uint8_t* out_rgba, dipsb_frame_stats* stats) {
+    if (!sl.pending) return fail(c, DIPSB_ERR_STATE, "no frame in flight");
+    CK(c, cudaEventSynchronize(sl.ev_done));
+    if (out_rgba && sl.want_rgba) memcpy(out_rgba, sl.h_out, c->g.npx * 4);
+    if (stats) { stats->frame_index = sl.idx; stats->sad = sl.h_stat[0]; stats->count = sl.h_stat[1]; }
+    sl.pending = false;
+    return sl.status;
+}
+
+extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t width, uint32_t height, uint32_t stride,
+                                    int32_t format, uint8_t* out_rgba, dipsb_frame_stats* stats) {
+    if (!c || !px) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (c->slot[0].pending || c->slot[1].pending) return fail(c, DIPSB_ERR_STATE, "push_frame: a pipelined frame is in flight; call dipsb_flush_frame first");
+    int32_t rc = submit_frame(c, c->slot[0], px, width, height, stride, format, out_rgba != nullptr, false);
+    if (rc) return rc;
+    return collect_frame(c, c->slot[0], out_rgba, stats);
+}
+
+extern "C" int32_t dipsb_push_frame_pipelined(dipsb_ctx* c, const uint8_t* px, uint32_t width, uint32_t height, uint32_t stride,
+                                              int32_t format, uint8_t* out_rgba_prev, dipsb_frame_stats* stats_prev) {
+    if (!c || !px) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    dipsb_ctx::FrameSlot& cur = c->slot[c->next_slot];
+    dipsb_ctx::FrameSlot& prev = c->slot[c->next_slot ^ 1];
+    if (cur.pending) return fail(c, DIPSB_ERR_STATE, "push_frame_pipelined: slot still in flight");
+    // output planes are requested for every frame in this mode (the caller decides at collection time)
+    int32_t rc = submit_frame(c, cur, px, width, height, stride, format, true, true);
+    if (rc) return rc;
+    c->next_slot ^= 1;
+    if (!prev.pending) return DIPSB_NOT_READY;          // first call: nothing to hand back yet
+    rc = collect_frame(c, prev, out_rgba_prev, stats_prev);
+    return rc < 0 ? rc : (rc == DIPSB_NOT_READY ? 2 : DIPSB_OK);
+}
+
+extern "C" int32_t dipsb_flush_frame(dipsb_ctx* c, uint8_t* out_rgba, dipsb_frame_stats* stats) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    dipsb_ctx::FrameSlot& last = c->slot[c->next_slot ^ 1];
+    if (!last.pending) return DIPSB_NOT_READY;
+    int32_t rc = collect_frame(c, last, out_rgba, stats);
+    return rc < 0 ? rc : (rc == DIPSB_NOT_READY ? 2 : DIPSB_OK);
 }
 
 // ---- results -------------------------------------------------------------------------------------------------------

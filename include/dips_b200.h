@@ -147,6 +147,17 @@ int32_t dipsb_run_clip_host(dipsb_ctx *ctx, const uint8_t *frames, uint64_t n_fr
  */
 int32_t dipsb_push_frame(dipsb_ctx *ctx, const uint8_t *px, uint32_t width, uint32_t height, uint32_t stride,
                          int32_t format, uint8_t *out_rgba, dipsb_frame_stats *stats);
+/*
+ * Pipelined variant (opt-in, one frame of latency): submits frame t -- staging copy, upload on a copy
+ * stream, kernel, read-back -- and hands back the output of frame t-1, so the host-side copies and the upload of frame t
+ * overlap the GPU work of frame t-1.  Returns DIPSB_NOT_READY on the first call (nothing to return yet), DIPSB_OK when
+ * out_rgba_prev/stats_prev hold the difference frame of t-1, 2 (DIPSB_PASSTHROUGH) when they hold a passed-through
+ * warm-up frame.  dipsb_flush_frame collects the last frame in flight.  Do not mix with dipsb_push_frame without flushing.
+ */
+#define DIPSB_PASSTHROUGH 2
+int32_t dipsb_push_frame_pipelined(dipsb_ctx *ctx, const uint8_t *px, uint32_t width, uint32_t height, uint32_t stride,
+                                   int32_t format, uint8_t *out_rgba_prev, dipsb_frame_stats *stats_prev);
+int32_t dipsb_flush_frame(dipsb_ctx *ctx, uint8_t *out_rgba, dipsb_frame_stats *stats);
 /* the next pushed frame becomes the reference (dips_alt snapshot / refresh marker) */
 int32_t dipsb_snapshot(dipsb_ctx *ctx);
 

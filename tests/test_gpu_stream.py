@@ -141,3 +141,36 @@ def test_dips_alt_ring2_flavour_matches_reference_state_machine(oracle, intended
             assert rc == 0
             assert _within(got, want, 3).all(), f"frame {t}: max diff {np.abs(got.astype(int) - want.astype(int)).max()}"
             assert _within(got, want, 1).mean() >= 0.97
+
+
+@pytest.mark.parametrize("flavor", [0, 1, 2])
+def test_pipelined_push_equals_synchronous(oracle, flavor):
+    """N2: the one-frame-latency pipelined call returns exactly what the synchronous call returns, one call later."""
+    import dips_b200
+    w, h, n, fmt = 96, 54, 9, 1
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    sync = []
+    with dips_b200.Context(w, h, fmt, 0, 7, flavor=flavor) as ctx:
+        for t in range(n):
+            sync.append(ctx.push_frame(clip[t]))
+        acc_sync = ctx.get_accumulators()
+    with dips_b200.Context(w, h, fmt, 0, 7, flavor=flavor) as ctx:
+        got = []
+        for t in range(n):
+            rc, rgba, st = ctx.push_frame_pipelined(clip[t])
+            if t == 0:
+                assert rc == dips_b200.NOT_READY and rgba is None
+            else:
+                got.append((rc, rgba, st))
+        with pytest.raises(dips_b200.DipsError):
+            ctx.push_frame(clip[0])                      # mixing without a flush is refused
+        got.append(ctx.flush_frame())
+        assert ctx.flush_frame()[0] == dips_b200.NOT_READY
+        acc_pipe = ctx.get_accumulators()
+    assert len(got) == n
+    for t in range(n):
+        rc_s, rgba_s, st_s = sync[t]
+        rc_p, rgba_p, st_p = got[t]
+        assert rc_p == (2 if rc_s == dips_b200.NOT_READY else 0)
+        assert st_p == st_s and np.array_equal(rgba_p, rgba_s), t
+    assert np.array_equal(acc_sync[0], acc_pipe[0]) and np.array_equal(acc_sync[1], acc_pipe[1])
