@@ -484,7 +484,7 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
     if (aligned) {
         const uint32_t segs = plan_segments(c, n);
         const uint32_t words = g.n_tiles * clip_active_warps(g);
-        const uint64_t need = n * (uint64_t)words;
+        const uint64_t need = n * (uint64_t)((words + 3u) & ~3u);   // rows pitched to 4 words (16-byte aligned)
         if (need >= (1ull << 32)) return fail(c, DIPSB_ERR_INVALID, "run_clip: %llu frames x %u warps exceed the per-call scalar scratch; split the call", (unsigned long long)n, words);
         if (need > c->partial_cap) {
             CK(c, cudaStreamSynchronize(c->stream));

@@ -52,18 +52,26 @@ __global__ void prime_median4_kernel(const uint8_t* __restrict__ frames, uint64_
     }
 }
 
-// per-frame scalars: sum the per-warp words (sad | cnt<<20) of one frame; one block per frame
-__global__ void finalize_scalars_kernel(const uint32_t* __restrict__ partials, uint32_t words_per_frame,
+// per-frame scalars: sum the per-warp words (sad | cnt<<20) of one frame; one 128-thread block per frame, 128-bit loads
+// (rows are pitched to a multiple of 4 words so that every row starts 16-byte aligned)
+__global__ void finalize_scalars_kernel(const uint32_t* __restrict__ partials, uint32_t words_per_frame, uint32_t row_pitch,
                                         uint64_t* __restrict__ sad, uint64_t* __restrict__ cnt) {
     const uint32_t t = blockIdx.x;
-    const uint32_t* row = partials + (uint64_t)t * words_per_frame;
+    const uint32_t* row = partials + (uint64_t)t * row_pitch;
     unsigned long long s = 0, c = 0;
-    for (uint32_t i = threadIdx.x; i < words_per_frame; i += blockDim.x) {
+    const uint32_t nvec = words_per_frame / 4;
+    const uint4* row4 = reinterpret_cast<const uint4*>(row);
+    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const uint4 w = __ldg(row4 + i);
+        s += (w.x & 0xFFFFFu) + (w.y & 0xFFFFFu) + (unsigned long long)(w.z & 0xFFFFFu) + (w.w & 0xFFFFFu);
+        c += (w.x >> 20) + (w.y >> 20) + (w.z >> 20) + (w.w >> 20);
+    }
+    for (uint32_t i = nvec * 4 + threadIdx.x; i < words_per_frame; i += blockDim.x) {
         const uint32_t w = __ldg(row + i);
         s += w & 0xFFFFFu;
         c += w >> 20;
     }
-    __shared__ unsigned long long sh_s[kThreads / 32], sh_c[kThreads / 32];
+    __shared__ unsigned long long sh_s[4], sh_c[4];
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_down_sync(0xFFFFFFFFu, s, o);
         c += __shfl_down_sync(0xFFFFFFFFu, c, o);
@@ -71,7 +79,7 @@ __global__ void finalize_scalars_kernel(const uint32_t* __restrict__ partials, u
     if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_c[threadIdx.x >> 5] = c; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < kThreads / 32; ++k) { s += sh_s[k]; c += sh_c[k]; }
+        for (int k = 1; k < 4; ++k) { s += sh_s[k]; c += sh_c[k]; }
         sad[t] = s;
         cnt[t] = c;
     }
@@ -318,7 +326,7 @@ cudaError_t launch_prime_median4(const Geometry& g, const uint8_t* frames, uint6
 cudaError_t launch_finalize_scalars(const Geometry&, const uint32_t* partials, uint32_t n_frames,
                                     uint32_t words_per_frame, uint64_t* sad, uint64_t* cnt, cudaStream_t s) {
     if (n_frames == 0) return cudaSuccess;
-    finalize_scalars_kernel<<<n_frames, kThreads, 0, s>>>(partials, words_per_frame, sad, cnt);
+    finalize_scalars_kernel<<<n_frames, 128, 0, s>>>(partials, words_per_frame, (words_per_frame + 3u) & ~3u, sad, cnt);
     count_launch();
     return cudaGetLastError();
 }

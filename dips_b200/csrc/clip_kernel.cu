@@ -169,7 +169,7 @@ struct KParams {
     uint32_t tile_px;        // pixels per tile (multiple of 16, <= 16*blockDim.x)
     uint32_t stages;
     uint32_t stage_bytes;    // bytes reserved per stage: 16*blockDim.x*bpp rounded up to 128
-    uint32_t words_per_frame;
+    uint32_t words_per_frame;   // row pitch of the per-frame scratch: tiles*active_warps rounded up to 4 words
     uint32_t active_warps;   // warps per block that own pixels; the others leave after the setup
     uint32_t tau;
     uint32_t l2_evict_first; // 1: frames are fetched with an L2 evict-first policy (they are read exactly once)
@@ -389,6 +389,10 @@ cudaError_t launch_r(const Geometry& g, const ClipArgs& a, const KParams& kp, si
     auto kfn = clip_kernel<BPP, CH, MODE, MAXREG>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // the kernel uses no L1-cached global loads in its loop: give the whole unified array to shared memory, so that the
+    // residency the planner assumed (blocks_per_sm) is what the hardware grants
+    e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     dim3 grid(g.n_tiles, a.n_segments, 1), block(g.threads, 1, 1);
     kfn<<<grid, block, smem, s>>>(kp);
     count_launch();
@@ -453,7 +457,7 @@ cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
     kp.n_frames = a.n_frames; kp.n_segments = a.n_segments;
     kp.tile_px = g.tile_px; kp.stages = g.stages; kp.stage_bytes = stage_bytes_of(g.threads, g.bpp);
     kp.active_warps = clip_active_warps(g);
-    kp.words_per_frame = g.n_tiles * kp.active_warps;
+    kp.words_per_frame = (g.n_tiles * kp.active_warps + 3u) & ~3u;
     kp.tau = a.tau;
     static const int l2_hint = [] { const char* e = getenv("DIPSB_L2_EVICT_FIRST"); return e ? atoi(e) : 1; }();
     kp.l2_evict_first = (uint32_t)l2_hint;
