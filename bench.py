@@ -292,10 +292,13 @@ def main():
     kern_avg_ms = kern_ms / max(kern_n, 1)
     achieved = alg_bytes / (kern_avg_ms / 1e3) / 1e9
     peak, peak_src = measured_peak()
+    probe_ms = ctx.stream_probe(clip.data_ptr(), frames, clip.stride(0), 5)      # compute-free TMA stream, same tiles
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload), "kernel": "clip_kernel", "kernel_ms": kern_avg_ms,
                 "kernel_share_of_step": kern_avg_ms / (ms_total / args.steps), "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0}
+                "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0,
+                "stream_probe_GBps": frames * fb / (probe_ms / 1e3) / 1e9,
+                "frac_of_stream_probe": (frames * fb / (kern_avg_ms / 1e3) / 1e9) / (frames * fb / (probe_ms / 1e3) / 1e9)}
 
     # ---- end to end: pinned host clip -> dipsb_run_clip_host -> results back on the host ---------------------------
     e2e = None

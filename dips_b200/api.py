@@ -118,6 +118,12 @@ class Context:
         self._ck(self._lib.dipsb_clip_kernel_time(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def stream_probe(self, d_frames: int, n_frames: int, stride: int | None = None, reps: int = 5) -> float:
+        """mean milliseconds of the compute-free TMA streaming probe over the clip (bandwidth ceiling of the pattern)"""
+        ms = C.c_float()
+        self._ck(self._lib.dipsb_stream_probe(self._h, d_frames, n_frames, stride or self.frame_bytes, reps, C.byref(ms)))
+        return float(ms.value)
+
     def last_plan(self) -> dict:
         out = (C.c_uint32 * 8)()
         self._ck(self._lib.dipsb_last_plan(self._h, C.byref(out)))

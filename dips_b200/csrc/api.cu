@@ -872,4 +872,26 @@ extern "C" int32_t dipsb_clip_kernel_time(dipsb_ctx* c, double* total_ms, uint64
     return DIPSB_OK;
 }
 
+// Roofline probe (measurement aid): stream the clip through the clip kernel's TMA ring without computing anything and
+// report the mean kernel time of `reps` launches; results of the context are not touched.
+extern "C" int32_t dipsb_stream_probe(dipsb_ctx* c, const void* d_frames, uint64_t n_frames, uint64_t stride, uint32_t reps, float* ms) {
+    if (!c || !d_frames || !ms || !reps || !n_frames) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const Geometry& g = c->g;
+    if ((((uintptr_t)d_frames | stride | (g.npx * g.bpp)) & 15u) != 0) return fail(c, DIPSB_ERR_INVALID, "stream_probe: clip not 16-byte aligned");
+    cudaEvent_t e0, e1;
+    CK(c, cudaEventCreate(&e0));
+    CK(c, cudaEventCreate(&e1));
+    CK(c, launch_stream_probe(g, (const uint8_t*)d_frames, stride, (uint32_t)n_frames, c->stream));   // warm-up
+    CK(c, cudaEventRecord(e0, c->stream));
+    for (uint32_t r = 0; r < reps; ++r) CK(c, launch_stream_probe(g, (const uint8_t*)d_frames, stride, (uint32_t)n_frames, c->stream));
+    CK(c, cudaEventRecord(e1, c->stream));
+    CK(c, cudaEventSynchronize(e1));
+    float total = 0.f;
+    CK(c, cudaEventElapsedTime(&total, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms = total / (float)reps;
+    return DIPSB_OK;
+}
+
 extern "C" uint64_t dipsb_launch_count(void) { return launch_count_value(); }

@@ -384,6 +384,42 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
     }
 }
 
+// Roofline probe: the clip kernel's memory side only -- same tiles, same TMA ring, same barriers, but the consumers just
+// release each buffer without reading it.  Its bandwidth is the ceiling of this access pattern on this GPU.
+__global__ void stream_probe_kernel(const __grid_constant__ KParams P, int bpp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t S = P.stages, stage_bytes = P.stage_bytes, nwarps = blockDim.x >> 5;
+    const uint64_t tile_first_px = (uint64_t)blockIdx.x * P.tile_px;
+    const uint64_t remain_px = P.npx - tile_first_px;
+    const uint32_t valid_bytes = (remain_px < P.tile_px ? (uint32_t)remain_px : P.tile_px) * (uint32_t)bpp;
+    const uint32_t smem_base = smem_u32(smem), full_bar = smem_base + S * stage_bytes, empty_bar = full_bar + 8u * S;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < S; ++s) { mbar_init(full_bar + 8u * s, 1); mbar_init(empty_bar + 8u * s, nwarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t count = P.n_frames;
+    auto issue = [&](uint32_t it, uint32_t stage) {
+        const uint8_t* src = P.frames + (uint64_t)it * P.stride + tile_first_px * bpp;
+        mbar_arrive_expect_tx(full_bar + 8u * stage, valid_bytes);
+        bulk_g2s(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage, policy_evict_first());
+    };
+    if (tid == 0) for (uint32_t j = 0; j < (S - 1 < count ? S - 1 : count); ++j) issue(j, j);
+    uint32_t stage = 0, parity = 0;
+    for (uint32_t iter = 0; iter < count; ++iter) {
+        mbar_wait(full_bar + 8u * stage, parity);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
+        if (tid == 0 && iter + S - 1 < count) {
+            const uint32_t ps = stage == 0 ? S - 1 : stage - 1;
+            if (iter > 0) mbar_wait(empty_bar + 8u * ps, stage == 0 ? parity ^ 1u : parity);
+            issue(iter + S - 1, ps);
+        }
+        if (++stage == S) { stage = 0; parity ^= 1u; }
+    }
+}
+
 template <int BPP, int CH, int MODE, int MAXREG>
 cudaError_t launch_r(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
     auto kfn = clip_kernel<BPP, CH, MODE, MAXREG>;
@@ -447,6 +483,18 @@ int clip_occupancy(uint32_t threads, int bpp, uint32_t stages, int regs) {
 
 uint32_t clip_active_warps(const Geometry& g) {
     return g.bpp == 3 ? (g.tile_px + 511u) / 512u : g.threads / 32u;
+}
+
+cudaError_t launch_stream_probe(const Geometry& g, const uint8_t* frames, uint64_t stride, uint32_t n_frames, cudaStream_t s) {
+    KParams kp{};
+    kp.frames = frames; kp.stride = stride; kp.npx = g.npx; kp.n_frames = n_frames;
+    kp.tile_px = g.tile_px; kp.stages = g.stages; kp.stage_bytes = stage_bytes_of(g.threads, g.bpp);
+    const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages);
+    cudaError_t e = cudaFuncSetAttribute(stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    stream_probe_kernel<<<g.n_tiles, 128, smem, s>>>(kp, g.bpp);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {

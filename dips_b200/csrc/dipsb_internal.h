@@ -67,6 +67,7 @@ int clip_max_threads_per_sm(int regs);
 int clip_occupancy(uint32_t threads, int bpp, uint32_t stages, int regs);
 uint32_t clip_active_warps(const Geometry& g);
 cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s);
+cudaError_t launch_stream_probe(const Geometry& g, const uint8_t* frames, uint64_t stride, uint32_t n_frames, cudaStream_t s);
 
 cudaError_t launch_prime(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s);
 cudaError_t launch_prime_median4(const Geometry& g, const uint8_t* frames, uint64_t stride, uint16_t* state,

@@ -192,6 +192,10 @@ int32_t dipsb_last_plan(const dipsb_ctx *ctx, uint32_t out[8]);
  * dipsb_clip_kernel_time synchronises, returns the summed milliseconds and launch count since the last call, and resets. */
 int32_t dipsb_enable_timing(dipsb_ctx *ctx, int32_t on);
 int32_t dipsb_clip_kernel_time(dipsb_ctx *ctx, double *total_ms, uint64_t *launches);
+/* roofline probe (measurement aid): streams the clip through the clip kernel's TMA ring with the context's tile plan but
+ * computes nothing; *ms = mean kernel time over `reps` launches.  Gives the bandwidth ceiling of the access pattern. */
+int32_t dipsb_stream_probe(dipsb_ctx *ctx, const void *d_frames, uint64_t n_frames, uint64_t frame_stride_bytes,
+                           uint32_t reps, float *ms);
 /* host-only: the plan (same layout as dipsb_last_plan, [7] = active warps per block) the library would choose for a
  * geometry on a device with num_sms SMs; touches no device. */
 int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t format, uint32_t num_sms, uint32_t out[8]);

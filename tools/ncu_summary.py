@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise .ncu-rep files (read here, no GPU): python tools_ncu_summary.py rep1 rep2 ..."""
+"""Summarise .ncu-rep files (read here, no GPU): python tools/ncu_summary.py rep1 rep2 ..."""
 import csv, subprocess, sys, io
 KEYS = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','dram__bytes_read.sum.per_second',
  'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','lts__throughput.avg.pct_of_peak_sustained_elapsed',

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_sweep.sh <workload> "<extra args variants separated by ;>"   (GPU box helper, prints one summary line per variant)
+# usage: tools/sweep.sh <workload> "<extra args variants separated by ;>"   (GPU box helper, prints one summary line per variant)
 wl=$1; shift
 IFS=';' read -ra VARS <<< "$1"
 for v in "${VARS[@]}"; do
