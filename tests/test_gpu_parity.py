@@ -350,3 +350,47 @@ def test_full_size_1080p_properties(torch_cuda, oracle):
             assert np.array_equal(s2, 2 * s) and np.array_equal(c2, 2 * c) and np.array_equal(sad2, sad)
     # telescoping bound between the two modes
     assert np.all(res[0][2] <= np.cumsum(res[1][2]))
+
+
+@pytest.mark.parametrize("w,h,fmt,n", [(3840, 2160, 1, 20), (7680, 4320, 0, 6), (2560, 1440, 2, 12), (1280, 720, 3, 140)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_baseline_geometries_bit_exact(torch_cuda, oracle, w, h, fmt, n, mode):
+    """The tile plans of the BASELINE resolutions (4K RGBx: 896 threads x 4 waves; 8K RGB8: 1024 threads / 64 registers x
+    14 waves; 1440p: 2 waves; 720p: frame segments + a flush at 128 frames) on device-generated clips, every output
+    compared bit for bit with the oracle."""
+    import dips_b200
+    torch = torch_cuda
+    fb = w * h * dips_b200.bytes_per_pixel(fmt)
+    dev = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
+    dips_b200.synth_fill_device(0, dev.data_ptr(), 0, n, w, h, fmt, 0x44695073, dips_b200.SYNTH_SCENE,
+                                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = dev.cpu().numpy().reshape(n, fb)
+    want = oracle.run_clip(host, fmt, mode, 32)
+    with dips_b200.Context(w, h, fmt, mode, 32) as ctx:
+        ctx.run_clip_device(dev.data_ptr(), n)
+        ctx.synchronize()
+        s, c = ctx.get_accumulators()
+        sad, cnt = ctx.get_scalars(0, n)
+        state = ctx.get_state_plane()
+        assert ctx.last_plan()["tma_path"]
+    assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)
+    assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+    assert np.array_equal(state, want.state)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,segments", [(127, 1), (128, 1), (129, 1), (257, 1), (300, 2), (385, 3)])
+def test_flush_boundaries(torch_cuda, oracle, mode, n, segments):
+    """packed 16-bit accumulators are flushed every 128 accumulated frames: counts around the boundary, with the halo frame
+    of per-frame segments shifting the phase, and saturated differences (D = 510) so that an off-by-one overflows."""
+    w, h = 96, 64
+    clip = np.zeros((n, w * h * 3), np.uint8)
+    clip[1::2] = 255                       # overall: D alternates 510/0; per-frame: D = 510 every frame
+    clip[0] = 0
+    got = run_gpu(torch_cuda, clip, w, h, 0, mode, 509, tuning=dict(segments=segments))
+    check(oracle, got, clip, 0, mode, 509)
+    full = np.full((n, w * h * 3), 255, np.uint8)
+    full[0] = 0                            # overall: D = 510 on every frame after the first
+    got = run_gpu(torch_cuda, full, w, h, 0, 0, 0, tuning=dict(segments=segments))
+    check(oracle, got, full, 0, 0, 0)
