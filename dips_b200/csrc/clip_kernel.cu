@@ -183,9 +183,15 @@ __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one
     return d;
 }
 
+__device__ __forceinline__ uint32_t mad_fma(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // One frame for my 16 pixels: D = |cur-ref| per packed half, threshold, accumulate; returns sad | count<<20 of the thread.
 //   hi = max(cur, ref)           VIMNMX.U16x2            (ALU pipe)
-//   d  = 2*hi - cur - ref        2 x IMAD                (FMA pipe; every partial result is >= 0 per half: no borrow)
+//   d  = 2*hi - (cur + ref)      2 x IMAD                (FMA pipe; cur+ref <= 1020 and d >= 0 per half: no carry/borrow)
 //   m  = min(max(d - tau, 0), 1) VIADDMNMX.S16x2.RELU    (ALU pipe)
 //   per-frame sums with IDP.2A (adds both halves into a scalar in one FMA-pipe instruction)
 __device__ __forceinline__ uint32_t diff16(const uint32_t* cur, const uint32_t* ref, uint32_t* accD, uint32_t* accM,
@@ -194,8 +200,8 @@ __device__ __forceinline__ uint32_t diff16(const uint32_t* cur, const uint32_t* 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint32_t hi = __vmaxu2(cur[j], ref[j]);
-        const uint32_t t = hi * 2u - cur[j];
-        const uint32_t d = add_fma(t, 0u - ref[j], one);
+        const uint32_t sum = add_fma(cur[j], ref[j], one);
+        const uint32_t d = mad_fma(hi, one + one, 0u - sum);
         const uint32_t m = __viaddmin_s16x2_relu(d, negtau2, 0x00010001u);
         accD[j] = add_fma(accD[j], d, one);
         accM[j] = add_fma(accM[j], m, one);
