@@ -3,22 +3,25 @@
 // Replaces the per-frame dispatch of compute_main (reference dips/src/gpu/shaders/dips_shader.wgsl:172-240 driven by
 // dips/src/gpu/mod.rs:306-397 once per decoded frame) by one pass over the clip that reads every input byte exactly once.
 //
-// Design (B200 / sm_100a, HBM-bound, no tensor cores -- there is no contraction):
-//   * grid = (pixel tiles, frame segments).  A block owns tile_px = 16*blockDim.x pixels for its whole frame segment:
-//     thread i owns 16 consecutive pixels; their reference/previous I2 (8 packed u16x2 registers) and the packed u16
-//     accumulators (8 + 8 registers) live in registers across the frame loop, so the accumulators cost no HBM traffic
-//     per frame.
-//   * per frame the block's contiguous byte range of that frame (tile_px*bpp bytes, 6-24 KB) is brought in by ONE
-//     TMA bulk copy (cp.async.bulk global->shared, completion on an mbarrier) into a ring of `stages` buffers;
-//     thread 0 re-arms the buffer released in the previous iteration, so stages-1 frames are always in flight per
-//     block with no registers tied up by loads.
-//   * threads read their 48 B (RGB8) / 64 B (RGBx8) from shared memory with conflict-free 128-bit loads, de-interleave
-//     with PRMT into u16x2 lanes, and use the packed DPX instructions (VIMNMX3.U16x2, VIADDMNMX.S16x2.RELU) for
-//     max/min/threshold: ~4.5 ALU-pipe + ~2.5 FMA-pipe instructions per pixel.
-//   * per-frame scalars: packed per-thread sums -> IDP.2A fold -> REDUX.SUM -> one 4-byte store per warp per frame
-//     (no atomics, no block barrier in the frame loop); a small finalize kernel adds the per-warp words.
+// Design (B200 / sm_100a, HBM-bound, no tensor cores -- there is no contraction); measurements in DESIGN.md section 4:
+//   * grid = (pixel tiles, frame segments).  A block owns a contiguous slice of tile_px <= 16*blockDim.x pixels of every
+//     frame of its segment -- normally ONE block of 896 threads per SM, tile_px = npx / (148 * waves).  A thread owns 16
+//     pixels; their reference/previous I2 (8 packed u16x2 registers) and the packed u16 accumulators (8 + 8 registers)
+//     stay in registers across the frame loop, so the accumulators cost no HBM traffic per frame.
+//   * per frame the block's slice (tile_px*bpp bytes, 40-56 KB for HD and above) arrives by ONE TMA bulk copy
+//     (cp.async.bulk global->shared, completion on an mbarrier, L2 evict-first) into a ring of `stages` buffers; thread 0
+//     re-arms the buffer released one iteration earlier, so stages-1 frames are in flight per block and no registers are
+//     tied up by loads.  No __syncthreads in the loop: full/empty mbarriers only.
+//   * threads read their 48 B (RGB8, stride 48 B) / 4x16 B (RGBx8, block-strided) from shared memory with conflict-free
+//     128-bit loads, de-interleave with PRMT into u16x2 lanes, and use the packed DPX instructions (VIMNMX3.U16x2,
+//     VIMNMX.U16x2, VIADDMNMX.S16x2.RELU) for max/min/threshold.  The integer ALU pipe is the second limiter after HBM,
+//     so every add runs on the FMA pipe (IMAD with an opaque multiplier, IDP.2A for the per-frame sums).
+//   * per-frame scalars: IDP.2A sums -> REDUX.SUM -> one 4-byte store per warp per frame (no atomics, no block barrier);
+//     a small finalize kernel adds the per-warp words.
 //   * every 128 frames (510*128 < 2^16) and at the end the packed accumulators are added to the u32 planes with
 //     coalesced RED.ADD (the planes are kept in a tile order that makes thread-adjacent = address-adjacent).
+//   * consecutive frames are serialised by a fake data dependency (mbar_wait_after): without it the compiler overlaps the
+//     tail of one frame with the loads of the next and spills; with it the kernel needs 64-72 registers.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
