@@ -149,7 +149,7 @@ def cpu_port_throughput(wl, sample_frames: int, clip_host=None, budget_s: float 
     return reps * sample_frames / dt, cores, f"{sample_frames}-frame prefix of the workload x{reps} passes, {cores} OpenMP threads, oracle/dips_oracle.c"
 
 
-def reference_arm(args, wl, rank):
+def reference_arm(args, wl, rank, out):
     """--impl reference: the reference has no CPU path and cannot be built here (Rust + WGSL/wgpu); per the task contract
     this arm times the oracle port on the host cores, all threads, on a bounded sample of the same workload."""
     if rank != 0:
@@ -183,7 +183,7 @@ def reference_arm(args, wl, rank):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     return 0
 
 
@@ -198,8 +198,18 @@ def config_of(wl, args, world, sample_note=None):
     return cfg
 
 
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) may write to fd 1; the contract is ONE JSON line on stdout.  Keep a private
+    duplicate of the real stdout for that line and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
     args = parse_args()
+    out = _claim_stdout()
     wl = list(WORKLOADS[args.workload])
     if args.frames:
         wl[6] = args.frames
@@ -210,7 +220,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return reference_arm(args, wl, rank)
+        return reference_arm(args, wl, rank, out)
 
     import numpy as np
     import torch
@@ -244,9 +254,21 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     engine = sharding.GpuShardEngine(ctx, clip, torch)
 
-    def step():
+    phase_events = []
+
+    def step(record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        if ev: ev[0].record(stream)
         ctx.reset()
-        sharding.run_sharded(engine, mode, t0_frame, rank, world, dist if world > 1 else None)
+        sharding.exchange_reference(engine, mode, rank, world, dist if world > 1 else None)
+        if ev: ev[1].record(stream)
+        engine.run(t0_frame)
+        if ev: ev[2].record(stream)
+        if world > 1:
+            dist.all_reduce(engine.acc_tensor(), op=dist.ReduceOp.SUM)
+        if ev:
+            ev[3].record(stream)
+            phase_events.append(ev)
 
     def fence():
         torch.cuda.synchronize()
@@ -266,7 +288,7 @@ def main():
     fence()
     e0.record(stream)
     for _ in range(args.steps):
-        step()
+        step(record=True)
     e1.record(stream)
     fence()
     clocks = sampler.stop()
@@ -275,11 +297,19 @@ def main():
     kern_ms, kern_n = ctx.clip_kernel_time()
     ctx.enable_timing(False)
     plan = ctx.last_plan()
+    phases = {"reset+exchange_ms": sum(e[0].elapsed_time(e[1]) for e in phase_events) / len(phase_events),
+              "prime+clip+finalize_ms": sum(e[1].elapsed_time(e[2]) for e in phase_events) / len(phase_events),
+              "allreduce_ms": sum(e[2].elapsed_time(e[3]) for e in phase_events) / len(phase_events)}
     t_all = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     ms_total = float(t_all.item())
     value = world * frames * args.steps / (ms_total / 1e3)
+    per_rank = [kern_ms / max(kern_n, 1)]
+    if world > 1:                                   # the slowest GPU sets the step time: report every rank's kernel time
+        g_all = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g_all, torch.tensor([per_rank[0]], dtype=torch.float64, device=dev))
+        per_rank = [float(x.item()) for x in g_all]
 
     # sanity of the last step's results (cheap integer identity; parity proper lives in tests/)
     sad, cnt = ctx.get_scalars(t0_frame, frames)
@@ -296,7 +326,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload), "kernel": "clip_kernel", "kernel_ms": kern_avg_ms,
                 "kernel_share_of_step": kern_avg_ms / (ms_total / args.steps), "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0,
+                "kernel_ms_per_rank": per_rank, "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0,
                 "stream_probe_GBps": frames * fb / (probe_ms / 1e3) / 1e9,
                 "frac_of_stream_probe": (frames * fb / (kern_avg_ms / 1e3) / 1e9) / (frames * fb / (probe_ms / 1e3) / 1e9)}
 
@@ -391,11 +421,11 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
             "hbm_GBps_per_gpu_whole_step": frames * fb * args.steps / (ms_total / 1e3) / 1e9,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "stream": stream_info,
+            "phases": phases, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "stream": stream_info,
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     ctx.close()
     if world > 1:
         dist.barrier()

@@ -24,7 +24,7 @@ struct dipsb_ctx {
     Geometry g;
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_switch = nullptr;
     uint16_t* state[2] = {nullptr, nullptr};   // u16[n_elems] each, zero padded past npx
     int state_cur = 0;
     bool state_valid = false;
@@ -181,6 +181,7 @@ static void free_all(dipsb_ctx* c) {
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_stat) cudaFreeHost(c->h_stat);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+    if (c->ev_switch) cudaEventDestroy(c->ev_switch);
     for (auto& sl : c->slot) {
         if (sl.h_in) cudaFreeHost(sl.h_in);
         if (sl.h_out) cudaFreeHost(sl.h_out);
@@ -260,6 +261,8 @@ extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
         if (cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming) != cudaSuccess)
             rc = fail(nullptr, DIPSB_ERR_CUDA, "dipsb_create: event creation failed");
+    if (rc == DIPSB_OK && cudaEventCreateWithFlags(&c->ev_switch, cudaEventDisableTiming) != cudaSuccess)
+        rc = fail(nullptr, DIPSB_ERR_CUDA, "dipsb_create: event creation failed");
     if (rc == DIPSB_OK) rc = alloc_planes(c);
     if (rc == DIPSB_OK && cudaMallocHost(&c->h_stat, 2 * sizeof(uint64_t)) != cudaSuccess)
         rc = fail(c, DIPSB_ERR_NOMEM, "dipsb_create: pinned allocation failed");
@@ -310,7 +313,10 @@ extern "C" int32_t dipsb_set_threshold(dipsb_ctx* c, uint32_t threshold) {
 extern "C" int32_t dipsb_set_stream(dipsb_ctx* c, void* stream) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaStreamSynchronize(c->stream));   // keep ordering of already issued work
+    if ((cudaStream_t)stream == c->stream) return DIPSB_OK;
+    // keep the ordering of already issued work without blocking the host: the new stream waits for the old one
+    CK(c, cudaEventRecord(c->ev_switch, c->stream));
+    CK(c, cudaStreamWaitEvent((cudaStream_t)stream, c->ev_switch, 0));
     c->stream = (cudaStream_t)stream;
     return DIPSB_OK;
 }
@@ -318,7 +324,9 @@ extern "C" int32_t dipsb_set_stream(dipsb_ctx* c, void* stream) {
 extern "C" int32_t dipsb_use_private_stream(dipsb_ctx* c) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->stream == c->own_stream) return DIPSB_OK;
+    CK(c, cudaEventRecord(c->ev_switch, c->stream));
+    CK(c, cudaStreamWaitEvent(c->own_stream, c->ev_switch, 0));
     c->stream = c->own_stream;
     return DIPSB_OK;
 }

@@ -52,7 +52,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // same, but ordered after the computation of `token` (a fake data dependency): keeps the compiler from overlapping the
 // register-hungry tail of one frame with the loads of the next, which would cost ~16 more live registers per thread
-__device__ __forceinline__ void mbar_wait_after(uint32_t bar, uint32_t parity, uint32_t token) {
+__device__ __forceinline__ void mbar_wait_after(uint32_t bar, uint32_t parity, uint32_t token, uint32_t hint_ns) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -60,12 +60,12 @@ __device__ __forceinline__ void mbar_wait_after(uint32_t bar, uint32_t parity, u
         "and.b32 T, %2, 0;\n"
         "add.u32 T, T, %0;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [T], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [T], %1, %3;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}" ::"r"(bar),
-        "r"(parity), "r"(token)
+        "r"(parity), "r"(token), "r"(hint_ns)
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -176,6 +176,7 @@ struct KParams {
     uint32_t active_warps;   // warps per block that own pixels; the others leave after the setup
     uint32_t tau;
     uint32_t l2_evict_first; // 1: frames are fetched with an L2 evict-first policy (they are read exactly once)
+    uint32_t wait_hint_ns;   // suspend-time hint of the consumers' mbarrier.try_wait
     uint32_t one;            // the constant 1 (an IMAD multiplier the compiler cannot fold away, see add_fma)
 };
 
@@ -320,7 +321,7 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
     // consume one frame: wait for its bytes, pull my pixels into registers, release the buffer, (thread 0) refill the
     // buffer released in the previous iteration, and turn the bytes into 8 packed intensities
     auto fetch = [&](uint32_t* cur, uint32_t token) {
-        mbar_wait_after(full_bar + 8u * stage, parity, token);
+        mbar_wait_after(full_bar + 8u * stage, parity, token, P.wait_hint_ns);
         uint32_t w[kWords];
 #pragma unroll
         for (int v = 0; v < BPP; ++v) {
@@ -518,6 +519,8 @@ cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
     kp.tau = a.tau;
     static const int l2_hint = [] { const char* e = getenv("DIPSB_L2_EVICT_FIRST"); return e ? atoi(e) : 1; }();
     kp.l2_evict_first = (uint32_t)l2_hint;
+    static const int wait_hint = [] { const char* e = getenv("DIPSB_WAIT_HINT_NS"); return e ? atoi(e) : 0; }();
+    kp.wait_hint_ns = (uint32_t)wait_hint;
     kp.one = 1u;
     const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages);
     return g.bpp == 3 ? launch_c<3>(g, a, kp, smem, s) : launch_c<4>(g, a, kp, smem, s);

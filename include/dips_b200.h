@@ -107,7 +107,8 @@ const char *dipsb_last_error(const dipsb_ctx *ctx);      /* ctx may be NULL: las
 int32_t dipsb_reset(dipsb_ctx *ctx);
 /* change tau / mode between clips (accumulators are kept; call dipsb_reset to clear) */
 int32_t dipsb_set_threshold(dipsb_ctx *ctx, uint32_t threshold);
-/* all work of this context is issued on `stream` (a cudaStream_t; NULL = the CUDA default stream) */
+/* all further work of this context is issued on `stream` (a cudaStream_t; NULL = the CUDA default stream); it is ordered
+ * after the work already issued (the new stream waits on an event of the old one; the host is not blocked) */
 int32_t dipsb_set_stream(dipsb_ctx *ctx, void *stream);
 /* go back to the context's private non-blocking stream (the state after dipsb_create) */
 int32_t dipsb_use_private_stream(dipsb_ctx *ctx);
