@@ -102,10 +102,12 @@ static int chan_byte_of(int format, int chroma) {
 // 2048-pixel tile keep 2048-pixel tiles, run several blocks per SM and are split into frame segments instead.
 static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_tile_px, uint32_t force_regs = 0) {
     const uint64_t min_tile = std::min<uint64_t>(2048, (g.npx + 15) / 16 * 16);
-    for (int regs : {72, 64, 80, 96}) {
-        if (force_regs ? (uint32_t)regs != force_regs : regs > 72) continue;   // 80/96 only on request (tuning)
+    for (int regs : {72, 64, 80, 96, 128}) {
+        if (force_regs ? (uint32_t)regs != force_regs : regs > 72) continue;   // 80/96/128 only on request (tuning)
+        const int groups = clip_groups(regs);
+        const uint32_t px_thr = (uint32_t)(kPxPerThread * groups);
         const uint32_t max_thr = (uint32_t)clip_max_threads_per_sm(regs);
-        const uint64_t max_slots = (uint64_t)max_thr * kPxPerThread;
+        const uint64_t max_slots = (uint64_t)max_thr * px_thr;
         uint64_t tile_px;
         if (force_tile_px) tile_px = force_tile_px;
         else {
@@ -120,22 +122,23 @@ static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_til
             }
         }
         if (tile_px > max_slots) continue;
-        const uint32_t thr = (uint32_t)((tile_px + kPxPerThread * 32 - 1) / (kPxPerThread * 32)) * 32;
+        const uint32_t thr = (uint32_t)((tile_px + px_thr * 32 - 1) / (px_thr * 32)) * 32;
         uint32_t stages = force_stages ? force_stages : 4;
         // measured (profiles/r01_sweeps.md): 4 stages beat 3 for 42-49 KB slices, but a 4 x 56 KB ring (4K RGBx, 224 KB: all
         // of the SM's shared memory) is slower than 3 x 56 KB -- keep the ring <= 200 KB
-        if (!force_stages && clip_smem_bytes(thr, g.bpp, stages) > 200 * 1024) stages = 3;
+        if (!force_stages && clip_smem_bytes(thr, g.bpp, stages, regs) > 200 * 1024) stages = 3;
         int occ = clip_occupancy(thr, g.bpp, stages, regs);
         while (!force_stages && occ <= 0 && stages > 2) occ = clip_occupancy(thr, g.bpp, --stages, regs);
         if (occ <= 0) continue;
         g.threads = thr;
         g.tile_px = (uint32_t)tile_px;
         g.n_tiles = (uint32_t)((g.npx + tile_px - 1) / tile_px);
-        g.n_elems = (uint64_t)g.n_tiles * thr * kPxPerThread;
-        g.state_elems = g.npx + (uint64_t)thr * kPxPerThread;
+        g.n_elems = (uint64_t)g.n_tiles * thr * px_thr;
+        g.state_elems = g.npx + (uint64_t)thr * px_thr;
         g.stages = stages;
         g.blocks_per_sm = (uint32_t)occ;
         g.regs = regs;
+        g.groups = groups;
         return true;
     }
     return false;
@@ -344,7 +347,7 @@ extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile
     if (stages > (uint32_t)kMaxStages || (stages && stages < 2)) return fail(c, DIPSB_ERR_INVALID, "set_tuning: stages %u outside [2,%d]", stages, kMaxStages);
     if (tile_px && (tile_px % 16 || tile_px > 1024u * kPxPerThread))
         return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u must be a multiple of 16 and <= %d", tile_px, 1024 * kPxPerThread);
-    if (regs && regs != 64 && regs != 72 && regs != 80 && regs != 96) return fail(c, DIPSB_ERR_INVALID, "set_tuning: regs %u not one of 64/72/80/96", regs);
+    if (regs && regs != 64 && regs != 72 && regs != 80 && regs != 96 && regs != 128) return fail(c, DIPSB_ERR_INVALID, "set_tuning: regs %u not one of 64/72/80/96/128", regs);
     const bool regeo = (stages != c->tune_stages) || (tile_px != c->tune_tile_px) || (regs != c->tune_regs);
     c->tune_segments = segments;
     if (!regeo) return DIPSB_OK;
@@ -369,7 +372,7 @@ extern "C" int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t for
     g.format = format; g.bpp = bpp_of(format); g.chan_byte = -1; g.num_sms = num_sms;
     if (!plan_geometry(g, 0, 0)) return DIPSB_ERR_INVALID;
     out[0] = g.n_tiles; out[1] = 0; out[2] = g.threads; out[3] = g.stages; out[4] = g.blocks_per_sm; out[5] = g.tile_px;
-    out[6] = (uint32_t)clip_smem_bytes(g.threads, g.bpp, g.stages) | ((uint32_t)g.regs << 24); out[7] = clip_active_warps(g);
+    out[6] = (uint32_t)clip_smem_bytes(g.threads, g.bpp, g.stages, g.regs) | ((uint32_t)g.regs << 24); out[7] = clip_active_warps(g);
     return DIPSB_OK;
 }
 
@@ -377,7 +380,7 @@ extern "C" int32_t dipsb_last_plan(const dipsb_ctx* c, uint32_t out[8]) {
     if (!c || !out) return DIPSB_ERR_INVALID;
     memcpy(out, c->last_plan, sizeof c->last_plan);
     out[0] = c->g.n_tiles; out[2] = c->g.threads; out[3] = c->g.stages; out[4] = c->g.blocks_per_sm; out[5] = c->g.tile_px;
-    out[6] = (uint32_t)clip_smem_bytes(c->g.threads, c->g.bpp, c->g.stages) | ((uint32_t)c->g.regs << 24);
+    out[6] = (uint32_t)clip_smem_bytes(c->g.threads, c->g.bpp, c->g.stages, c->g.regs) | ((uint32_t)c->g.regs << 24);
     return DIPSB_OK;
 }
 

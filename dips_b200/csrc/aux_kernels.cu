@@ -86,19 +86,19 @@ __global__ void finalize_scalars_kernel(const uint32_t* __restrict__ partials, u
 }
 
 __global__ void unpermute_kernel(const uint32_t* __restrict__ internal, uint32_t* __restrict__ planar, uint64_t npx,
-                                 uint32_t tile_px, uint32_t threads, int bpp) {
+                                 uint32_t tile_px, uint32_t threads, int bpp, int groups) {
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
-        planar[p] = internal[tile_order_index(p, tile_px, threads, bpp)];
+        planar[p] = internal[tile_order_index(p, tile_px, threads, bpp, groups)];
 }
 __global__ void permute_kernel(const uint32_t* __restrict__ planar, uint32_t* __restrict__ internal, uint64_t npx,
-                               uint32_t tile_px, uint32_t threads, int bpp) {
+                               uint32_t tile_px, uint32_t threads, int bpp, int groups) {
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
-        internal[tile_order_index(p, tile_px, threads, bpp)] = planar[p];
+        internal[tile_order_index(p, tile_px, threads, bpp, groups)] = planar[p];
 }
 __global__ void intensity_map_kernel(const uint32_t* __restrict__ internal, float* __restrict__ out, uint64_t npx,
-                                     uint32_t tile_px, uint32_t threads, int bpp, double inv_den) {
+                                     uint32_t tile_px, uint32_t threads, int bpp, int groups, double inv_den) {
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
-        out[p] = (float)((double)internal[tile_order_index(p, tile_px, threads, bpp)] * inv_den);
+        out[p] = (float)((double)internal[tile_order_index(p, tile_px, threads, bpp, groups)] * inv_den);
 }
 
 // ---- visual chain: compute_main colour mapping, dips_shader.wgsl:30-62, :97-118, :213-239 -----------------------------
@@ -143,7 +143,7 @@ struct FrameK {
     const uint8_t* frame; uint64_t pitch; uint32_t width, height; int bpp, chan_byte;
     const uint16_t* state_in; uint16_t* state_out; uint32_t* acc_sum; uint32_t* acc_cnt;
     unsigned long long* sad; unsigned long long* cnt; uint8_t* out_rgba;
-    uint32_t tau, tile_px, threads; int geo_bpp; int accumulate, colorize, filter; float sig;
+    uint32_t tau, tile_px, threads; int geo_bpp, geo_groups; int accumulate, colorize, filter; float sig;
 };
 __global__ void frame_kernel(const FrameK K) {
     const uint64_t npx = (uint64_t)K.width * K.height;
@@ -156,7 +156,7 @@ __global__ void frame_kernel(const FrameK K) {
         const uint32_t d = (uint32_t)(sdiff < 0 ? -sdiff : sdiff);
         const uint32_t m = d > K.tau ? 1u : 0u;
         if (K.accumulate) {
-            const uint64_t q = tile_order_index(p, K.tile_px, K.threads, K.geo_bpp);
+            const uint64_t q = tile_order_index(p, K.tile_px, K.threads, K.geo_bpp, K.geo_groups);
             K.acc_sum[q] += d;                                          // each pixel is owned by exactly one thread
             K.acc_cnt[q] += m;
             s += d; c += m;
@@ -187,7 +187,7 @@ struct RingK {
     const uint8_t* frame; uint64_t pitch; uint32_t width, height; int bpp, chan_byte;
     uint16_t* ring; int n_slots, write_slot, grey_slot, compute_start, snapshot, median_is_max, do_diff;
     uint16_t* start; uint32_t* acc_sum; uint32_t* acc_cnt; unsigned long long* sad; unsigned long long* cnt; uint8_t* out_rgba;
-    uint32_t tau, tile_px, threads; int geo_bpp, colorize, filter; float sig;
+    uint32_t tau, tile_px, threads; int geo_bpp, geo_groups, colorize, filter; float sig;
 };
 __device__ __forceinline__ uint32_t upper_median4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {   // sorted[2]
     const uint32_t lo01 = min(a, b), hi01 = max(a, b), lo23 = min(c, d), hi23 = max(c, d);
@@ -233,7 +233,7 @@ __global__ void ring_kernel(const RingK K) {
         const int sdiff = (int)start - (int)med;
         const uint32_t d = (uint32_t)(sdiff < 0 ? -sdiff : sdiff);
         const uint32_t m = d > K.tau ? 1u : 0u;
-        const uint64_t q = tile_order_index(p, K.tile_px, K.threads, K.geo_bpp);
+        const uint64_t q = tile_order_index(p, K.tile_px, K.threads, K.geo_bpp, K.geo_groups);
         K.acc_sum[q] += d;
         K.acc_cnt[q] += m;
         s += d; c += m;
@@ -331,18 +331,18 @@ cudaError_t launch_finalize_scalars(const Geometry&, const uint32_t* partials, u
     return cudaGetLastError();
 }
 cudaError_t launch_unpermute(const Geometry& g, const uint32_t* internal, uint32_t* planar, cudaStream_t s) {
-    unpermute_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(internal, planar, g.npx, g.tile_px, g.threads, g.bpp);
+    unpermute_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(internal, planar, g.npx, g.tile_px, g.threads, g.bpp, g.groups);
     count_launch();
     return cudaGetLastError();
 }
 cudaError_t launch_permute(const Geometry& g, const uint32_t* planar, uint32_t* internal, cudaStream_t s) {
-    permute_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(planar, internal, g.npx, g.tile_px, g.threads, g.bpp);
+    permute_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(planar, internal, g.npx, g.tile_px, g.threads, g.bpp, g.groups);
     count_launch();
     return cudaGetLastError();
 }
 cudaError_t launch_intensity_map(const Geometry& g, const uint32_t* internal, uint64_t n_eff, float* out, cudaStream_t s) {
     const double inv = 1.0 / (510.0 * (double)(n_eff ? n_eff : 1));
-    intensity_map_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(internal, out, g.npx, g.tile_px, g.threads, g.bpp, inv);
+    intensity_map_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(internal, out, g.npx, g.tile_px, g.threads, g.bpp, g.groups, inv);
     count_launch();
     return cudaGetLastError();
 }
@@ -352,7 +352,7 @@ cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) 
     K.bpp = (a.format == 0 || a.format == 2) ? 3 : 4; K.chan_byte = a.chan_byte;
     K.state_in = a.state_in; K.state_out = a.state_out; K.acc_sum = a.acc_sum; K.acc_cnt = a.acc_cnt;
     K.sad = reinterpret_cast<unsigned long long*>(a.sad); K.cnt = reinterpret_cast<unsigned long long*>(a.cnt);
-    K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp;
+    K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp; K.geo_groups = g.groups;
     K.accumulate = a.accumulate; K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
     frame_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(K);
     count_launch();
@@ -366,7 +366,7 @@ cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s) {
     K.compute_start = a.compute_start; K.snapshot = a.snapshot; K.median_is_max = a.median_is_max; K.do_diff = a.do_diff;
     K.start = a.start; K.acc_sum = a.acc_sum; K.acc_cnt = a.acc_cnt;
     K.sad = reinterpret_cast<unsigned long long*>(a.sad); K.cnt = reinterpret_cast<unsigned long long*>(a.cnt);
-    K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp;
+    K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp; K.geo_groups = g.groups;
     K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
     ring_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(K);
     count_launch();

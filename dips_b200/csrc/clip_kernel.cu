@@ -26,6 +26,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "dipsb_internal.h"
 
 namespace dipsb {
@@ -193,16 +195,18 @@ __device__ __forceinline__ uint32_t mad_fma(uint32_t a, uint32_t b, uint32_t c) 
     return d;
 }
 
-// One frame for my 16 pixels: D = |cur-ref| per packed half, threshold, accumulate; returns sad | count<<20 of the thread.
+// One frame for my pixels (N packed registers = 2N pixels): D = |cur-ref| per packed half, threshold, accumulate; returns
+// sad | count<<20 of the thread.
 //   hi = max(cur, ref)           VIMNMX.U16x2            (ALU pipe)
 //   d  = 2*hi - (cur + ref)      2 x IMAD                (FMA pipe; cur+ref <= 1020 and d >= 0 per half: no carry/borrow)
 //   m  = min(max(d - tau, 0), 1) VIADDMNMX.S16x2.RELU    (ALU pipe)
 //   per-frame sums with IDP.2A (adds both halves into a scalar in one FMA-pipe instruction)
-__device__ __forceinline__ uint32_t diff16(const uint32_t* cur, const uint32_t* ref, uint32_t* accD, uint32_t* accM,
-                                           uint32_t negtau2, uint32_t one) {
+template <int N>
+__device__ __forceinline__ uint32_t diff_px(const uint32_t* cur, const uint32_t* ref, uint32_t* accD, uint32_t* accM,
+                                            uint32_t negtau2, uint32_t one) {
     uint32_t sD = 0u, sM = 0u;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < N; ++j) {
         const uint32_t hi = __vmaxu2(cur[j], ref[j]);
         const uint32_t sum = add_fma(cur[j], ref[j], one);
         const uint32_t d = mad_fma(hi, one + one, 0u - sum);
@@ -212,19 +216,23 @@ __device__ __forceinline__ uint32_t diff16(const uint32_t* cur, const uint32_t* 
         sD = __dp2a_lo(d, 0x0101u, sD);
         sM = __dp2a_lo(m, 0x0101u, sM);
     }
-    return sD + (sM << 20);   // sad <= 16*510 and cnt <= 16 per thread; x32 lanes still fits the 20/12-bit fields
+    // sad <= 32*510 and cnt <= 32 per thread; summed over 32 lanes they still fit the 20-bit / 12-bit fields
+    return sD + (sM << 20);
 }
 
-template <int BPP, int CH, int MODE, int MAXREG>
+// G = groups of 16 pixels per thread (1 or 2).  G = 2 halves the per-warp, per-frame overhead (barrier wait, loop control,
+// warp reduction) per pixel at the price of ~50 more registers per thread (fewer, fatter warps).
+template <int BPP, int CH, int MODE, int G, int MAXREG>
 __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int kWords = BPP * 4;  // 32-bit words of raw pixels per thread per frame
+    constexpr int kWords = BPP * 4;  // 32-bit words of raw pixels per thread, frame and group
+    constexpr int R = 8 * G;         // packed u16x2 registers per thread and plane
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nthr = blockDim.x;
     const uint32_t tile = blockIdx.x, seg = blockIdx.y;
     const uint32_t S = P.stages;
     const uint32_t stage_bytes = P.stage_bytes;
-    const uint32_t slots = nthr * kPxPerThread;   // accumulator slots per tile (>= tile_px)
+    const uint32_t slots = nthr * (kPxPerThread * G);   // accumulator slots per tile (>= tile_px)
 
     // frame range of this segment, and the extra leading "prime" frame of per-frame mode
     const uint32_t t0 = (uint32_t)(((uint64_t)P.n_frames * seg) / P.n_segments);
@@ -257,7 +265,7 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (warp >= P.active_warps) return;   // warps without pixels (tile_px < 16*blockDim.x); they never touch a barrier
+    if (warp >= P.active_warps) return;   // warps without pixels (tile_px small against the block); they never touch a barrier
 
     // ---- producer (thread 0): one TMA bulk copy per frame, re-arming the buffer freed one iteration ago ----------------
     // (the host only takes this kernel when frame bytes, base and stride are multiples of 16, so valid_bytes is too)
@@ -273,42 +281,47 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
         for (uint32_t j = 0; j < pre; ++j) issue(j, j);
     }
 
-    // ---- my 16 pixels: reference / previous-frame I2 (zero for slots beyond the tile's pixels) ---------------------------
-    // 3 B/px: pixels tid*16 .. +15 of the tile; 4 B/px: groups of 4 pixels at 4*(v*nthr + tid), v = 0..3.
-    uint32_t ra[8], rb[8];
+    // ---- my pixels: reference / previous-frame I2 (zero for slots beyond the tile's pixels) ------------------------------
+    // 3 B/px: group g = pixels 16*(g*nthr + tid) .. +15 of the tile (48 contiguous bytes, 128-bit shared loads at stride 48 B);
+    // 4 B/px: quad q = pixels 4*(q*nthr + tid) .. +3, q = 0 .. 4G-1 (128-bit shared loads at stride 16 B).  Both conflict-free.
+    uint32_t ra[R], rb[R];
     if constexpr (BPP == 3) {
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-        if (tid * kPxPerThread < valid_px) {
-            const uint4* sp = reinterpret_cast<const uint4*>(P.state_in + tile_first_px + (uint64_t)tid * kPxPerThread);
-            r0 = __ldg(sp); r1 = __ldg(sp + 1);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+            const uint32_t off = (g * nthr + tid) * kPxPerThread;
+            if (off < valid_px) {
+                const uint4* sp = reinterpret_cast<const uint4*>(P.state_in + tile_first_px + off);
+                r0 = __ldg(sp); r1 = __ldg(sp + 1);
+            }
+            ra[8 * g + 0] = r0.x; ra[8 * g + 1] = r0.y; ra[8 * g + 2] = r0.z; ra[8 * g + 3] = r0.w;
+            ra[8 * g + 4] = r1.x; ra[8 * g + 5] = r1.y; ra[8 * g + 6] = r1.z; ra[8 * g + 7] = r1.w;
         }
-        ra[0] = r0.x; ra[1] = r0.y; ra[2] = r0.z; ra[3] = r0.w;
-        ra[4] = r1.x; ra[5] = r1.y; ra[6] = r1.z; ra[7] = r1.w;
     } else {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int q = 0; q < 4 * G; ++q) {
             uint2 r = make_uint2(0, 0);
-            const uint32_t off = 4u * (v * nthr + tid);
+            const uint32_t off = 4u * (q * nthr + tid);
             if (off < valid_px) r = __ldg(reinterpret_cast<const uint2*>(P.state_in + tile_first_px + off));
-            ra[2 * v] = r.x; ra[2 * v + 1] = r.y;
+            ra[2 * q] = r.x; ra[2 * q + 1] = r.y;
         }
     }
-    uint32_t accD[8], accM[8];
+    uint32_t accD[R], accM[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) accD[j] = accM[j] = 0u;
+    for (int j = 0; j < R; ++j) accD[j] = accM[j] = 0u;
 
     const uint32_t tau = P.tau > 511u ? 511u : P.tau;
     const uint32_t negtau2 = ((0u - tau) & 0xFFFFu) * 0x00010001u;  // (-tau, -tau) as s16x2
     uint32_t part = first * P.words_per_frame + tile * P.active_warps + warp;   // index into P.partials (host checks < 2^32)
-    // 3 B/px: 48 contiguous bytes per thread; 4 B/px: four 16-byte groups strided by the block (both conflict-free)
     const uint32_t my_smem = smem_base + (BPP == 3 ? tid * 48u : tid * 16u);
-    const uint32_t my_step = (BPP == 3) ? 16u : nthr * 16u;
+    const uint32_t grp_step = (BPP == 3 ? 48u : 64u) * nthr;   // bytes between my consecutive groups of 16 pixels
+    const uint32_t my_step = (BPP == 3) ? 16u : nthr * 16u;    // bytes between the 128-bit pieces of one group
 
     auto flush = [&]() {
         uint32_t* const acc_sum = P.acc_sum + (uint64_t)tile * slots + tid;
         uint32_t* const acc_cnt = P.acc_cnt + (uint64_t)tile * slots + tid;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < R; ++j) {
             atomicAdd(acc_sum + (2 * j) * nthr, accD[j] & 0xFFFFu);
             atomicAdd(acc_sum + (2 * j + 1) * nthr, accD[j] >> 16);
             atomicAdd(acc_cnt + (2 * j) * nthr, accM[j] & 0xFFFFu);
@@ -319,14 +332,17 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
 
     uint32_t stage = 0, parity = 0, iter = 0;
     // consume one frame: wait for its bytes, pull my pixels into registers, release the buffer, (thread 0) refill the
-    // buffer released in the previous iteration, and turn the bytes into 8 packed intensities
+    // buffer released in the previous iteration, and turn the bytes into packed intensities
     auto fetch = [&](uint32_t* cur, uint32_t token) {
         mbar_wait_after(full_bar + 8u * stage, parity, token, P.wait_hint_ns);
-        uint32_t w[kWords];
+        uint32_t w[G][kWords];
 #pragma unroll
-        for (int v = 0; v < BPP; ++v) {
-            const uint4 x = lds128(my_smem + stage * stage_bytes + my_step * v);
-            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int v = 0; v < BPP; ++v) {
+                const uint4 x = lds128(my_smem + stage * stage_bytes + grp_step * g + my_step * v);
+                w[g][4 * v] = x.x; w[g][4 * v + 1] = x.y; w[g][4 * v + 2] = x.z; w[g][4 * v + 3] = x.w;
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
@@ -337,7 +353,8 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
         }
         ++iter;
         if (++stage == S) { stage = 0; parity ^= 1u; }
-        intensity16<BPP, CH>(w, cur);
+#pragma unroll
+        for (int g = 0; g < G; ++g) intensity16<BPP, CH>(w[g], cur + 8 * g);
     };
     auto emit = [&](uint32_t packed) {   // per-frame scalars: warp-reduce, one 4-byte store per warp per frame
         const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, packed);
@@ -356,39 +373,43 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
     // two frames per trip so that per-frame mode ping-pongs ra/rb without register moves
     while (iter + 2 <= count) {
         fetch(rb, token);
-        token = emit(diff16(rb, ra, accD, accM, negtau2, one));
+        token = emit(diff_px<R>(rb, ra, accD, accM, negtau2, one));
         if constexpr (MODE == 0) {
             fetch(rb, token);
-            token = emit(diff16(rb, ra, accD, accM, negtau2, one));
+            token = emit(diff_px<R>(rb, ra, accD, accM, negtau2, one));
         } else {
             fetch(ra, token);
-            token = emit(diff16(ra, rb, accD, accM, negtau2, one));
+            token = emit(diff_px<R>(ra, rb, accD, accM, negtau2, one));
         }
         if (((iter - iter0) & (uint32_t)(kFlushFrames - 1)) == 0u) flush();   // every 128 accumulated frames
     }
     if (iter < count) {
         fetch(rb, token);
-        emit(diff16(rb, ra, accD, accM, negtau2, one));
+        emit(diff_px<R>(rb, ra, accD, accM, negtau2, one));
         if constexpr (MODE == 1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ra[j] = rb[j];
+            for (int j = 0; j < R; ++j) ra[j] = rb[j];
         }
     }
     flush();
 
     if (MODE == 1 && seg == P.n_segments - 1) {  // chain: I2 of the last frame becomes the next call's previous frame
         if constexpr (BPP == 3) {
-            if (tid * kPxPerThread < valid_px) {
-                uint4* sp = reinterpret_cast<uint4*>(P.state_out + tile_first_px + (uint64_t)tid * kPxPerThread);
-                sp[0] = make_uint4(ra[0], ra[1], ra[2], ra[3]);
-                sp[1] = make_uint4(ra[4], ra[5], ra[6], ra[7]);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint32_t off = (g * nthr + tid) * kPxPerThread;
+                if (off < valid_px) {
+                    uint4* sp = reinterpret_cast<uint4*>(P.state_out + tile_first_px + off);
+                    sp[0] = make_uint4(ra[8 * g + 0], ra[8 * g + 1], ra[8 * g + 2], ra[8 * g + 3]);
+                    sp[1] = make_uint4(ra[8 * g + 4], ra[8 * g + 5], ra[8 * g + 6], ra[8 * g + 7]);
+                }
             }
         } else {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const uint32_t off = 4u * (v * nthr + tid);
+            for (int q = 0; q < 4 * G; ++q) {
+                const uint32_t off = 4u * (q * nthr + tid);
                 if (off < valid_px)
-                    *reinterpret_cast<uint2*>(P.state_out + tile_first_px + off) = make_uint2(ra[2 * v], ra[2 * v + 1]);
+                    *reinterpret_cast<uint2*>(P.state_out + tile_first_px + off) = make_uint2(ra[2 * q], ra[2 * q + 1]);
             }
         }
     }
@@ -430,9 +451,9 @@ __global__ void stream_probe_kernel(const __grid_constant__ KParams P, int bpp) 
     }
 }
 
-template <int BPP, int CH, int MODE, int MAXREG>
+template <int BPP, int CH, int MODE, int G, int MAXREG>
 cudaError_t launch_r(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
-    auto kfn = clip_kernel<BPP, CH, MODE, MAXREG>;
+    auto kfn = clip_kernel<BPP, CH, MODE, G, MAXREG>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // the kernel uses no L1-cached global loads in its loop: give the whole unified array to shared memory, so that the
@@ -447,11 +468,12 @@ cudaError_t launch_r(const Geometry& g, const ClipArgs& a, const KParams& kp, si
 
 template <int BPP, int CH, int MODE>
 cudaError_t launch_t(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
-    switch (g.regs) {   // register variant chosen by the planner: more registers <-> fewer resident warps
-        case 96: return launch_r<BPP, CH, MODE, 96>(g, a, kp, smem, s);
-        case 80: return launch_r<BPP, CH, MODE, 80>(g, a, kp, smem, s);
-        case 72: return launch_r<BPP, CH, MODE, 72>(g, a, kp, smem, s);
-        default: return launch_r<BPP, CH, MODE, 64>(g, a, kp, smem, s);
+    switch (g.regs) {   // kernel variant chosen by the planner: more registers <-> fewer resident warps
+        case 128: return launch_r<BPP, CH, MODE, 2, 128>(g, a, kp, smem, s);   // 32 pixels per thread
+        case 96: return launch_r<BPP, CH, MODE, 1, 96>(g, a, kp, smem, s);
+        case 80: return launch_r<BPP, CH, MODE, 1, 80>(g, a, kp, smem, s);
+        case 72: return launch_r<BPP, CH, MODE, 1, 72>(g, a, kp, smem, s);
+        default: return launch_r<BPP, CH, MODE, 1, 64>(g, a, kp, smem, s);
     }
 }
 
@@ -470,19 +492,21 @@ cudaError_t launch_c(const Geometry& g, const ClipArgs& a, const KParams& kp, si
     }
 }
 
-inline uint32_t stage_bytes_of(uint32_t threads, int bpp) { return (threads * kPxPerThread * (uint32_t)bpp + 127u) & ~127u; }
+inline uint32_t stage_bytes_of(uint32_t threads, int bpp, int groups) { return (threads * kPxPerThread * (uint32_t)groups * (uint32_t)bpp + 127u) & ~127u; }
 
 }  // namespace
 
-size_t clip_smem_bytes(uint32_t threads, int bpp, uint32_t stages) {
-    return (size_t)stages * stage_bytes_of(threads, bpp) + 16u * stages;  // buffers + full/empty mbarriers
+int clip_groups(int regs) { return regs >= 128 ? 2 : 1; }
+
+size_t clip_smem_bytes(uint32_t threads, int bpp, uint32_t stages, int regs) {
+    return (size_t)stages * stage_bytes_of(threads, bpp, clip_groups(regs)) + 16u * stages;  // buffers + full/empty mbarriers
 }
 
 // registers are allocated per warp in units of 256: warps/SM = floor(65536 / (regs*32)), e.g. 72 -> 28, 80 -> 25, 96 -> 21
 int clip_max_threads_per_sm(int regs) { return (65536 / (regs * 32)) * 32; }
 
 int clip_occupancy(uint32_t threads, int bpp, uint32_t stages, int regs) {
-    const size_t smem = clip_smem_bytes(threads, bpp, stages) + 1024;  // + per-block reservation
+    const size_t smem = clip_smem_bytes(threads, bpp, stages, regs) + 1024;  // + per-block reservation
     const size_t smem_sm = 227 * 1024;
     if (smem > smem_sm) return 0;
     const int by_smem = (int)(smem_sm / smem);
@@ -492,14 +516,16 @@ int clip_occupancy(uint32_t threads, int bpp, uint32_t stages, int regs) {
 }
 
 uint32_t clip_active_warps(const Geometry& g) {
-    return g.bpp == 3 ? (g.tile_px + 511u) / 512u : g.threads / 32u;
+    // 3 B/px: warp w owns pixels from 512*w upwards in its first group; 4 B/px: every warp owns pixels of every quad row
+    const uint32_t warps = g.threads / 32u;
+    return g.bpp == 3 ? std::min(warps, (g.tile_px + 511u) / 512u) : warps;
 }
 
 cudaError_t launch_stream_probe(const Geometry& g, const uint8_t* frames, uint64_t stride, uint32_t n_frames, cudaStream_t s) {
     KParams kp{};
     kp.frames = frames; kp.stride = stride; kp.npx = g.npx; kp.n_frames = n_frames;
-    kp.tile_px = g.tile_px; kp.stages = g.stages; kp.stage_bytes = stage_bytes_of(g.threads, g.bpp);
-    const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages);
+    kp.tile_px = g.tile_px; kp.stages = g.stages; kp.stage_bytes = stage_bytes_of(g.threads, g.bpp, clip_groups(g.regs));
+    const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages, g.regs);
     cudaError_t e = cudaFuncSetAttribute(stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     stream_probe_kernel<<<g.n_tiles, 128, smem, s>>>(kp, g.bpp);
@@ -513,7 +539,7 @@ cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
     kp.state_in = a.state_in; kp.state_out = a.state_out;
     kp.acc_sum = a.acc_sum; kp.acc_cnt = a.acc_cnt; kp.partials = a.partials;
     kp.n_frames = a.n_frames; kp.n_segments = a.n_segments;
-    kp.tile_px = g.tile_px; kp.stages = g.stages; kp.stage_bytes = stage_bytes_of(g.threads, g.bpp);
+    kp.tile_px = g.tile_px; kp.stages = g.stages; kp.stage_bytes = stage_bytes_of(g.threads, g.bpp, clip_groups(g.regs));
     kp.active_warps = clip_active_warps(g);
     kp.words_per_frame = (g.n_tiles * kp.active_warps + 3u) & ~3u;
     kp.tau = a.tau;
@@ -522,7 +548,7 @@ cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
     static const int wait_hint = [] { const char* e = getenv("DIPSB_WAIT_HINT_NS"); return e ? atoi(e) : 0; }();
     kp.wait_hint_ns = (uint32_t)wait_hint;
     kp.one = 1u;
-    const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages);
+    const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages, g.regs);
     return g.bpp == 3 ? launch_c<3>(g, a, kp, smem, s) : launch_c<4>(g, a, kp, smem, s);
 }
 

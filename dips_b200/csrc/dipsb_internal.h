@@ -16,14 +16,15 @@ struct Geometry {
     int bpp;                 // 3 or 4
     int format;              // dipsb_format
     int chan_byte;           // -1: all channels (max+min); else byte offset of the selected channel inside a pixel
-    uint32_t threads;        // threads per block (multiple of 32); a block has 16*threads accumulator slots
-    uint32_t tile_px;        // pixels per tile: multiple of 16, <= 16*threads (chosen so the tiles fill the SMs evenly)
+    uint32_t threads;        // threads per block (multiple of 32); a block has 16*groups*threads accumulator slots
+    uint32_t tile_px;        // pixels per tile: multiple of 16, <= slots (chosen so the tiles fill the SMs evenly)
     uint32_t n_tiles;        // ceil(npx / tile_px)
-    uint64_t n_elems;        // n_tiles * 16*threads: length of each accumulator plane in internal (tile) order
-    uint64_t state_elems;    // npx + 16*threads: length of a state plane (zero padded past npx)
+    uint64_t n_elems;        // n_tiles * slots: length of each accumulator plane in internal (tile) order
+    uint64_t state_elems;    // npx + slots: length of a state plane (zero padded past npx)
     uint32_t blocks_per_sm;  // resident blocks per SM the plan assumes
     uint32_t stages;         // pipeline depth
-    int regs;                // register variant of the clip kernel (64, 72, 80 or 96 registers per thread)
+    int regs;                // kernel variant: 64/72/80/96 registers with 16 pixels per thread, 128 registers with 32
+    int groups;              // groups of 16 pixels per thread (1 or 2) == clip_groups(regs)
     uint32_t num_sms;
 };
 
@@ -41,27 +42,29 @@ struct ClipArgs {
     int mode;                    // dipsb_mode
 };
 
-// Which pixel of its tile does register slot k (0..15) of thread `thread` hold?
-//   3 B/px: 16 consecutive pixels per thread (48 contiguous bytes, conflict-free 128-bit shared loads at stride 48 B).
-//   4 B/px: four groups of 4 consecutive pixels, group v at 4*(v*threads + thread) (128-bit shared loads at stride 16 B).
-// index of pixel p in the internal accumulator order: tile*(16*threads) + k*threads + thread.
-__host__ __device__ inline uint64_t tile_order_index(uint64_t p, uint32_t tile_px, uint32_t threads, int bpp) {
+// Which pixel of its tile does register slot k (0 .. 16*groups-1) of thread `thread` hold?
+//   3 B/px: group g = 16 consecutive pixels at 16*(g*threads + thread); slot k = 16*g + (pixel within the group).
+//   4 B/px: quad q = 4 consecutive pixels at 4*(q*threads + thread), q = 0 .. 4*groups-1; slot k = 4*q + (pixel within the quad).
+// index of pixel p in the internal accumulator order: tile*(16*groups*threads) + k*threads + thread.
+__host__ __device__ inline uint64_t tile_order_index(uint64_t p, uint32_t tile_px, uint32_t threads, int bpp, int groups) {
     const uint64_t tile = p / tile_px;
     const uint32_t q = (uint32_t)(p - tile * tile_px);
     uint32_t thread, k;
     if (bpp == 3) {
-        thread = q / kPxPerThread;
-        k = q % kPxPerThread;
+        const uint32_t grp = q / kPxPerThread;
+        thread = grp % threads;
+        k = (grp / threads) * kPxPerThread + q % kPxPerThread;
     } else {
-        const uint32_t v = q / (4u * threads), r = q % (4u * threads);
-        thread = r / 4u;
-        k = 4u * v + (r % 4u);
+        const uint32_t quad = q / 4u;
+        thread = quad % threads;
+        k = 4u * (quad / threads) + q % 4u;
     }
-    return tile * ((uint64_t)threads * kPxPerThread) + (uint64_t)k * threads + thread;
+    return tile * ((uint64_t)threads * kPxPerThread * groups) + (uint64_t)k * threads + thread;
 }
 
-size_t clip_smem_bytes(uint32_t threads, int bpp, uint32_t stages);
-// resident threads per SM allowed by a register variant of the clip kernel (64 -> 1024, 72 -> 896, 80 -> 800, 96 -> 672)
+int clip_groups(int regs);   // groups of 16 pixels per thread of a register variant (128 registers -> 2, else 1)
+size_t clip_smem_bytes(uint32_t threads, int bpp, uint32_t stages, int regs);
+// resident threads per SM allowed by a register variant of the clip kernel (64 -> 1024, 72 -> 896, 80 -> 800, 96 -> 672, 128 -> 512)
 int clip_max_threads_per_sm(int regs);
 // resident blocks/SM for (threads, stages, register variant), or 0 when it does not fit
 int clip_occupancy(uint32_t threads, int bpp, uint32_t stages, int regs);

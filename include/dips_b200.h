@@ -201,7 +201,7 @@ int32_t dipsb_stream_probe(dipsb_ctx *ctx, const void *d_frames, uint64_t n_fram
  * geometry on a device with num_sms SMs; touches no device. */
 int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t format, uint32_t num_sms, uint32_t out[8]);
 /* tuning knobs (0 = automatic): pipeline stages, pixels per tile (multiple of 16), frame segments, register variant of
- * the clip kernel (64/72/80/96).  Geometry knobs can only change on a fresh or reset context. */
+ * the clip kernel (64/72/80/96 registers with 16 pixels per thread, 128 registers with 32).  Geometry knobs can only change on a fresh or reset context. */
 int32_t dipsb_set_tuning(dipsb_ctx *ctx, uint32_t stages, uint32_t tile_px, uint32_t segments, uint32_t regs);
 
 #ifdef __cplusplus

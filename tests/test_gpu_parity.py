@@ -167,7 +167,8 @@ def test_forced_frame_segments(torch_cuda, oracle, mode, segments):
 
 
 @pytest.mark.parametrize("tile_px,stages,regs", [(512, 2, 0), (1040, 3, 72), (2048, 8, 64), (7008, 4, 80), (3504, 3, 96),
-                                                  (14336, 2, 72), (16384, 2, 64), (16, 3, 0)])
+                                                  (14336, 2, 72), (16384, 2, 64), (16, 3, 0), (1040, 3, 128), (7008, 4, 128),
+                                                  (16384, 3, 128)])
 def test_forced_tile_geometry(torch_cuda, oracle, tile_px, stages, regs):
     w, h, n = 300, 77, 12
     for fmt in (0, 1):
@@ -177,7 +178,7 @@ def test_forced_tile_geometry(torch_cuda, oracle, tile_px, stages, regs):
         check(oracle, got, clip, fmt, 1, 8)
 
 
-@pytest.mark.parametrize("regs", [64, 72, 80, 96])
+@pytest.mark.parametrize("regs", [64, 72, 80, 96, 128])
 @pytest.mark.parametrize("fmt,mode", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_register_variants(torch_cuda, oracle, regs, fmt, mode):
     w, h, n = 640, 360, 140          # > 128 frames: crosses the packed-accumulator flush
