@@ -38,6 +38,7 @@ struct dipsb_ctx {
     uint64_t partial_cap = 0;                  // in u32 words
     uint64_t frames_processed = 0;
     uint64_t stream_index = 0;                 // logical index of the next pushed frame
+    uint16_t* i2_scratch = nullptr;            // spatial window > 1: 5 planes of npx u16 (raw + up to 4 filtered)
     uint16_t* ring = nullptr;                  // ring flavours: 4 (dips) or 2 (dips_alt) u16 I2 planes of npx
     uint32_t ring_seen = 0, ring_index = 0;    // frames pushed since the last (re)start, next slot to overwrite
     // streaming staging
@@ -92,6 +93,11 @@ static int chan_byte_of(int format, int chroma) {
     const int rgb_index = chroma - 1;  // 0 R, 1 G, 2 B
     return bgr ? 2 - rgb_index : rgb_index;
 }
+
+static bool windowed(const dipsb_ctx* c);
+static int32_t ensure_i2_scratch(dipsb_ctx* c);
+// spatially filtered intensity plane of one tightly packed frame (N4): raw I2 -> correct median of the w x w window
+static int32_t filtered_plane(dipsb_ctx* c, const uint8_t* d_frame, int format, uint16_t* out);
 
 // ---- planning ------------------------------------------------------------------------------------------------------
 // Measured on B200 (profiles/r01_sweeps.md): the clip kernel runs fastest with ONE large block per SM -- every SM streams
@@ -154,6 +160,25 @@ static uint32_t plan_segments(const dipsb_ctx* c, uint64_t n_frames) {
     return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(segs, n_frames));
 }
 
+static bool windowed(const dipsb_ctx* c) { return c->cfg.spatial_window > 1; }
+
+static int32_t ensure_i2_scratch(dipsb_ctx* c) {
+    if (!c->i2_scratch) CK(c, cudaMalloc(&c->i2_scratch, 5 * c->g.npx * sizeof(uint16_t)));
+    return DIPSB_OK;
+}
+
+static int32_t filtered_plane(dipsb_ctx* c, const uint8_t* d_frame, int format, uint16_t* out) {
+    const Geometry& g = c->g;
+    int32_t rc0 = ensure_i2_scratch(c);
+    if (rc0) return rc0;
+    Geometry gf = g;                       // the frame may come in another pixel format than the context's (push_frame)
+    gf.bpp = bpp_of(format);
+    gf.chan_byte = chan_byte_of(format, c->cfg.chroma);
+    CK(c, launch_prime(gf, d_frame, c->i2_scratch, c->stream));
+    CK(c, launch_spatial_median(g, c->i2_scratch, out, c->cfg.spatial_window, c->stream));
+    return DIPSB_OK;
+}
+
 // ---- lifetime ------------------------------------------------------------------------------------------------------
 extern "C" int32_t dipsb_abi_version(void) { return DIPSB_ABI_VERSION; }
 
@@ -180,7 +205,7 @@ static void free_all(dipsb_ctx* c) {
         if (c->d_chunk[k]) cudaFree(c->d_chunk[k]);
     }
     cudaFree(c->acc); cudaFree(c->planar); cudaFree(c->d_sad); cudaFree(c->d_cnt); cudaFree(c->partials);
-    cudaFree(c->d_frame); cudaFree(c->d_rgba); cudaFree(c->ring);
+    cudaFree(c->d_frame); cudaFree(c->d_rgba); cudaFree(c->ring); cudaFree(c->i2_scratch);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_stat) cudaFreeHost(c->h_stat);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -226,8 +251,8 @@ extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
     if (cfg->flavor < 0 || cfg->flavor > 3) return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: bad flavor %d", cfg->flavor);
     if (cfg->flavor != DIPSB_FLAVOR_FRAME0 && cfg->mode != DIPSB_MODE_OVERALL)
         return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: the ring flavours are overall-mode only");
-    if (cfg->spatial_window != 1 && cfg->spatial_window != 0)
-        return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: spatial_window %d not implemented (only 1)", cfg->spatial_window);
+    if (cfg->spatial_window != 0 && cfg->spatial_window != 1 && cfg->spatial_window != 3 && cfg->spatial_window != 5 && cfg->spatial_window != 7)
+        return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: spatial_window %d not one of 1, 3, 5, 7", cfg->spatial_window);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -388,7 +413,12 @@ extern "C" int32_t dipsb_last_plan(const dipsb_ctx* c, uint32_t out[8]) {
 extern "C" int32_t dipsb_prime_device(dipsb_ctx* c, const void* d_frame) {
     if (!c || !d_frame) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
-    CK(c, launch_prime(c->g, (const uint8_t*)d_frame, c->state[c->state_cur], c->stream));
+    if (windowed(c)) {
+        int32_t rc = filtered_plane(c, (const uint8_t*)d_frame, c->g.format, c->state[c->state_cur]);
+        if (rc) return rc;
+    } else {
+        CK(c, launch_prime(c->g, (const uint8_t*)d_frame, c->state[c->state_cur], c->stream));
+    }
     c->state_valid = true;
     c->snapshot_pending = false;
     return DIPSB_OK;
@@ -398,7 +428,17 @@ extern "C" int32_t dipsb_prime_median4_device(dipsb_ctx* c, const void* d_frames
     if (!c || !d_frames) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     if (stride < c->g.npx * c->g.bpp) return fail(c, DIPSB_ERR_INVALID, "prime_median4: stride smaller than a frame");
-    CK(c, launch_prime_median4(c->g, (const uint8_t*)d_frames, stride, c->state[c->state_cur], c->stream));
+    if (windowed(c)) {   // each start frame is spatially filtered first (pre_compute_shader.wgsl:104-107), then the upper median
+        int32_t rc0 = ensure_i2_scratch(c);
+        if (rc0) return rc0;
+        for (int k = 0; k < 4; ++k) {
+            int32_t rc = filtered_plane(c, (const uint8_t*)d_frames + k * stride, c->g.format, c->i2_scratch + (1 + k) * c->g.npx);
+            if (rc) return rc;
+        }
+        CK(c, launch_median4_planes(c->g, c->i2_scratch + c->g.npx, c->state[c->state_cur], c->stream));
+    } else {
+        CK(c, launch_prime_median4(c->g, (const uint8_t*)d_frames, stride, c->state[c->state_cur], c->stream));
+    }
     c->state_valid = true;
     c->snapshot_pending = false;
     return DIPSB_OK;
@@ -486,11 +526,17 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
     int32_t rc = ensure_scalars(c, first + n);
     if (rc) return rc;
     if (!c->state_valid) {   // frame 0 of the call is the reference (overall) / has no predecessor (per-frame): D = 0
-        CK(c, launch_prime(g, d_frames, c->state[c->state_cur], c->stream));
+        if (windowed(c)) {
+            rc = filtered_plane(c, d_frames, g.format, c->state[c->state_cur]);
+            if (rc) return rc;
+        } else {
+            CK(c, launch_prime(g, d_frames, c->state[c->state_cur], c->stream));
+        }
         c->state_valid = true;
     }
     // the TMA bulk copies of the clip kernel need 16-byte aligned addresses and sizes
-    const bool aligned = (((uintptr_t)d_frames | stride | (g.npx * g.bpp)) & 15u) == 0;
+    // (a spatial window > 1 needs a filtered intensity plane per frame: per-frame kernels, not the clip kernel)
+    const bool aligned = !windowed(c) && (((uintptr_t)d_frames | stride | (g.npx * g.bpp)) & 15u) == 0;
     const uint32_t tau = c->cfg.threshold;
     if (aligned) {
         const uint32_t segs = plan_segments(c, n);
@@ -532,6 +578,13 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         for (uint64_t k = 0; k < n; ++k) {
             FrameArgs f;
             f.frame = d_frames + k * stride; f.pitch = (uint64_t)g.width * g.bpp; f.format = g.format; f.chan_byte = g.chan_byte;
+            if (windowed(c)) {
+                rc = ensure_i2_scratch(c);
+                if (rc) return rc;
+                rc = filtered_plane(c, f.frame, g.format, c->i2_scratch + g.npx);
+                if (rc) return rc;
+                f.i2src = c->i2_scratch + g.npx;
+            }
             f.state_in = c->state[c->state_cur];
             f.state_out = c->cfg.mode == DIPSB_MODE_PERFRAME ? c->state[c->state_cur] : nullptr;
             f.acc_sum = c->acc; f.acc_cnt = c->acc + g.n_elems;
@@ -663,10 +716,19 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     const uint64_t idx = c->stream_index;
     CK(c, cudaMemsetAsync(c->d_sad + idx, 0, sizeof(uint64_t), c->stream));
     CK(c, cudaMemsetAsync(c->d_cnt + idx, 0, sizeof(uint64_t), c->stream));
+    const uint16_t* i2src = nullptr;
+    if (windowed(c)) {   // N4: spatially filtered intensity of this frame (dips_shader.wgsl:187)
+        rc = ensure_i2_scratch(c);
+        if (rc) return rc;
+        rc = filtered_plane(c, sl.d_in, format, c->i2_scratch + g.npx);
+        if (rc) return rc;
+        i2src = c->i2_scratch + g.npx;
+    }
     bool establishes;
     if (c->cfg.flavor == DIPSB_FLAVOR_FRAME0) {
         establishes = !c->state_valid || c->snapshot_pending;
         FrameArgs f;
+        f.i2src = i2src;
         f.frame = sl.d_in; f.pitch = row; f.format = format; f.chan_byte = chan_byte_of(format, c->cfg.chroma);
         f.acc_sum = c->acc; f.acc_cnt = c->acc + g.n_elems;
         f.sad = c->d_sad + idx; f.cnt = c->d_cnt + idx;
@@ -686,6 +748,7 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
         }
     } else {
         RingArgs r;
+        r.i2src = i2src;
         r.frame = sl.d_in; r.pitch = row; r.format = format; r.chan_byte = chan_byte_of(format, c->cfg.chroma);
         r.ring = c->ring; r.start = c->state[c->state_cur];
         r.acc_sum = c->acc; r.acc_cnt = c->acc + g.n_elems; r.sad = c->d_sad + idx; r.cnt = c->d_cnt + idx;

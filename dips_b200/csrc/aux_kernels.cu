@@ -141,6 +141,7 @@ __device__ __forceinline__ uchar4 visual_pixel(int s_i2, int colorize, int filte
 // of run_clip for frames whose base/stride are not 16-byte aligned (the TMA bulk copy needs that).
 struct FrameK {
     const uint8_t* frame; uint64_t pitch; uint32_t width, height; int bpp, chan_byte;
+    const uint16_t* i2src;       // spatially filtered intensity plane of this frame (window > 1), else nullptr
     const uint16_t* state_in; uint16_t* state_out; uint32_t* acc_sum; uint32_t* acc_cnt;
     unsigned long long* sad; unsigned long long* cnt; uint8_t* out_rgba;
     uint32_t tau, tile_px, threads; int geo_bpp, geo_groups; int accumulate, colorize, filter; float sig;
@@ -150,7 +151,7 @@ __global__ void frame_kernel(const FrameK K) {
     unsigned long long s = 0, c = 0;
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t y = (uint32_t)(p / K.width), x = (uint32_t)(p - (uint64_t)y * K.width);
-        const uint32_t cur = intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
+        const uint32_t cur = K.i2src ? K.i2src[p] : intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
         const uint32_t ref = K.state_in[p];
         const int sdiff = (int)ref - (int)cur;                          // sign convention start - current
         const uint32_t d = (uint32_t)(sdiff < 0 ? -sdiff : sdiff);
@@ -185,6 +186,7 @@ __global__ void frame_kernel(const FrameK K) {
 // newest frame back as rgba8unorm grey), so the float expressions of the shader become exact integers until the colour map.
 struct RingK {
     const uint8_t* frame; uint64_t pitch; uint32_t width, height; int bpp, chan_byte;
+    const uint16_t* i2src;
     uint16_t* ring; int n_slots, write_slot, grey_slot, compute_start, snapshot, median_is_max, do_diff;
     uint16_t* start; uint32_t* acc_sum; uint32_t* acc_cnt; unsigned long long* sad; unsigned long long* cnt; uint8_t* out_rgba;
     uint32_t tau, tile_px, threads; int geo_bpp, geo_groups, colorize, filter; float sig;
@@ -198,7 +200,7 @@ __global__ void ring_kernel(const RingK K) {
     unsigned long long s = 0, c = 0;
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t y = (uint32_t)(p / K.width), x = (uint32_t)(p - (uint64_t)y * K.width);
-        const uint32_t raw = intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
+        const uint32_t raw = K.i2src ? K.i2src[p] : intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
         uint32_t v[4] = {0, 0, 0, 0};
         for (int k = 0; k < K.n_slots; ++k) v[k] = K.ring[(uint64_t)k * npx + p];
         v[K.write_slot] = raw;
@@ -251,6 +253,38 @@ __global__ void ring_kernel(const RingK K) {
         if (s) atomicAdd(K.sad, s);
         if (c) atomicAdd(K.cnt, c);
     }
+}
+
+// N4: spatial median of the intensity plane, window w in {3,5,7}.  A CORRECT median: the full symmetric window
+// [-w/2, +w/2]^2, zero for taps outside the frame (as the reference pads, dips_shader.wgsl:135-139), element w*w/2 of the
+// ascending order.  The reference's own loop covers only the half-open window [-w/2, w/2) and picks the wrong element
+//  -- a defect that is deliberately not reproduced.  Selection by bitwise binary search on the 9-bit value.
+__global__ void spatial_median_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t W, uint32_t H, int w) {
+    const uint64_t npx = (uint64_t)W * H;
+    const int r = w / 2, k = (w * w) / 2;
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(p / W), x = (int)(p - (uint64_t)y * W);
+        uint16_t v[49];
+        int n = 0;
+        for (int dy = -r; dy <= r; ++dy)
+            for (int dx = -r; dx <= r; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                v[n++] = (yy >= 0 && yy < (int)H && xx >= 0 && xx < (int)W) ? in[(uint64_t)yy * W + xx] : (uint16_t)0;
+            }
+        uint32_t lo = 0;                                   // largest value with #(v < value) <= k  ==  sorted[k]
+        for (int bit = 8; bit >= 0; --bit) {
+            const uint32_t cand = lo | (1u << bit);
+            int cnt = 0;
+            for (int i = 0; i < n; ++i) cnt += v[i] < cand;
+            if (cnt <= k) lo = cand;
+        }
+        out[p] = (uint16_t)lo;
+    }
+}
+
+__global__ void median4_planes_kernel(const uint16_t* __restrict__ planes, uint64_t npx, uint16_t* __restrict__ out) {
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
+        out[p] = (uint16_t)upper_median4(planes[p], planes[npx + p], planes[2 * npx + p], planes[3 * npx + p]);
 }
 
 // warm-up passthrough of frame_callback (dips/src/lib.rs:241-245): input converted to RGBA8, alpha 255
@@ -349,7 +383,7 @@ cudaError_t launch_intensity_map(const Geometry& g, const uint32_t* internal, ui
 cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) {
     FrameK K;
     K.frame = a.frame; K.pitch = a.pitch; K.width = g.width; K.height = g.height;
-    K.bpp = (a.format == 0 || a.format == 2) ? 3 : 4; K.chan_byte = a.chan_byte;
+    K.bpp = (a.format == 0 || a.format == 2) ? 3 : 4; K.chan_byte = a.chan_byte; K.i2src = a.i2src;
     K.state_in = a.state_in; K.state_out = a.state_out; K.acc_sum = a.acc_sum; K.acc_cnt = a.acc_cnt;
     K.sad = reinterpret_cast<unsigned long long*>(a.sad); K.cnt = reinterpret_cast<unsigned long long*>(a.cnt);
     K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp; K.geo_groups = g.groups;
@@ -358,10 +392,20 @@ cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) 
     count_launch();
     return cudaGetLastError();
 }
+cudaError_t launch_spatial_median(const Geometry& g, const uint16_t* in, uint16_t* out, int window, cudaStream_t s) {
+    spatial_median_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(in, out, g.width, g.height, window);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_median4_planes(const Geometry& g, const uint16_t* planes, uint16_t* out, cudaStream_t s) {
+    median4_planes_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(planes, g.npx, out);
+    count_launch();
+    return cudaGetLastError();
+}
 cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s) {
     RingK K;
     K.frame = a.frame; K.pitch = a.pitch; K.width = g.width; K.height = g.height;
-    K.bpp = (a.format == 0 || a.format == 2) ? 3 : 4; K.chan_byte = a.chan_byte;
+    K.bpp = (a.format == 0 || a.format == 2) ? 3 : 4; K.chan_byte = a.chan_byte; K.i2src = a.i2src;
     K.ring = a.ring; K.n_slots = a.n_slots; K.write_slot = a.write_slot; K.grey_slot = a.grey_slot;
     K.compute_start = a.compute_start; K.snapshot = a.snapshot; K.median_is_max = a.median_is_max; K.do_diff = a.do_diff;
     K.start = a.start; K.acc_sum = a.acc_sum; K.acc_cnt = a.acc_cnt;

@@ -85,6 +85,7 @@ struct FrameArgs {
     uint64_t pitch;
     int format;                  // format of this frame (may differ from the context's in push_frame)
     int chan_byte;
+    const uint16_t* i2src = nullptr;   // spatially filtered intensity plane to use instead of the raw frame (window > 1)
     const uint16_t* state_in;
     uint16_t* state_out;         // nullptr: do not update
     uint32_t* acc_sum;
@@ -101,6 +102,7 @@ cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s);
 // reference-flavour temporal rings (N1): one frame against a ring of u16 I2 planes
 struct RingArgs {
     const uint8_t* frame; uint64_t pitch; int format; int chan_byte;
+    const uint16_t* i2src = nullptr;   // see FrameArgs
     uint16_t* ring;              // n_slots planes of npx u16
     int n_slots;                 // 4 (dips) or 2 (dips_alt)
     int write_slot;              // slot that receives the raw I2 of this frame
@@ -114,6 +116,9 @@ struct RingArgs {
     uint32_t tau; int colorize, filter; float sig_scalar;
 };
 cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s);
+// N4: correct spatial median (window 3/5/7, zero padded) of a u16 intensity plane; upper median of 4 planes
+cudaError_t launch_spatial_median(const Geometry& g, const uint16_t* in, uint16_t* out, int window, cudaStream_t s);
+cudaError_t launch_median4_planes(const Geometry& g, const uint16_t* planes, uint16_t* out, cudaStream_t s);
 cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uint64_t pitch, int format,
                                     uint8_t* out_rgba, cudaStream_t s);
 cudaError_t launch_synth(uint8_t* dst, uint64_t first_frame, uint64_t n_frames, uint32_t w, uint32_t h, int bpp,

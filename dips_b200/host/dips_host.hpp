@@ -49,7 +49,8 @@ class ComputeState {
                  ChromaFilter chroma_filter, bool reference_exact = true, int32_t device = 0)
         : colorize_(colorize), window_(spatial_window_size), sensitivity_(sensitivity), filter_(filter_type),
           chroma_(chroma_filter), exact_(reference_exact), device_(device) {
-        if (spatial_window_size != 1) throw std::runtime_error("spatial_window_size != 1 is not supported by the B200 path");
+        if (spatial_window_size != 1 && spatial_window_size != 3 && spatial_window_size != 5 && spatial_window_size != 7)
+            throw std::runtime_error("spatial_window_size must be 1, 3, 5 or 7");   // > 1: correct zero-padded median
     }
     ComputeState(const ComputeState&) = delete;
     ComputeState& operator=(const ComputeState&) = delete;
@@ -130,12 +131,12 @@ class DiPsCompute {
                 bool as_shipped_median = true, int32_t device = 0)
         : width_(textures_width), height_(textures_height) {
         if (num_textures != 2) throw std::runtime_error("DiPsCompute: only num_textures == 2 (FRAME_COUNT) is implemented");
-        if (p.window_size != 1) throw std::runtime_error("DiPsCompute: window_size != 1 is not supported by the B200 path");
+
         dipsb_config cfg;
         dipsb_default_config(&cfg);
         cfg.device = device; cfg.width = width_; cfg.height = height_; cfg.format = DIPSB_FMT_RGBX8; cfg.mode = DIPSB_MODE_OVERALL;
         cfg.chroma = static_cast<int32_t>(p.chroma_filter); cfg.colorize = p.colorize; cfg.filter = static_cast<int32_t>(p.filter_type);
-        cfg.sigmoid_scalar = p.sigmoid_horizontal_scalar; cfg.spatial_window = 1;
+        cfg.sigmoid_scalar = p.sigmoid_horizontal_scalar; cfg.spatial_window = p.window_size;   // 1/3/5/7 after set_window_size
         cfg.flavor = as_shipped_median ? DIPSB_FLAVOR_ALT_RING2 : DIPSB_FLAVOR_ALT_RING2_MEDIAN;
         if (dipsb_create(&cfg, &ctx_) != DIPSB_OK) throw std::runtime_error(std::string("dipsb_create: ") + dipsb_last_error(nullptr));
     }

@@ -86,7 +86,9 @@ typedef struct dipsb_config {
     int32_t colorize;          /* COLORIZE override, dips_shader.wgsl:15 */
     int32_t filter;            /* dipsb_filter, FILTER_TYPE override */
     float sigmoid_scalar;      /* SIGMOID_HORIZONTAL_SCALAR override (UI "sensitivity") */
-    int32_t spatial_window;    /* WINDOW_SIZE override; only 1 is implemented */
+    int32_t spatial_window;    /* WINDOW_SIZE override: 1, 3, 5 or 7.  > 1 applies a CORRECT zero-padded median of the full
+                                * window to every frame's intensity (the reference's own loop is defective);
+                                * such contexts run frame by frame (no clip kernel) */
     int32_t flavor;            /* dipsb_flavor */
     uint32_t reserved[3];
 } dipsb_config;

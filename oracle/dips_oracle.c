@@ -139,6 +139,31 @@ void dipso_run_clip(const uint8_t *frames, size_t n_frames, size_t stride, size_
     free(part);
 }
 
+/* N4: see the header; insertion sort of at most 49 taps */
+void dipso_spatial_median_plane(const uint16_t *in, uint32_t width, uint32_t height, int window, uint16_t *out) {
+    const int r = window / 2, k = (window * window) / 2;
+    if (window <= 1) { memcpy(out, in, (size_t)width * height * sizeof(uint16_t)); return; }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t y = 0; y < (int64_t)height; ++y) {
+        for (int64_t x = 0; x < (int64_t)width; ++x) {
+            uint16_t v[49];
+            int n = 0;
+            for (int dy = -r; dy <= r; ++dy)
+                for (int dx = -r; dx <= r; ++dx) {
+                    const int64_t yy = y + dy, xx = x + dx;
+                    const uint16_t t = (yy >= 0 && yy < (int64_t)height && xx >= 0 && xx < (int64_t)width)
+                                           ? in[(size_t)yy * width + (size_t)xx] : (uint16_t)0;
+                    int i = n++;
+                    while (i > 0 && v[i - 1] > t) { v[i] = v[i - 1]; --i; }
+                    v[i] = t;
+                }
+            out[(size_t)y * width + (size_t)x] = v[k];
+        }
+    }
+}
+
 /* X6 */
 void dipso_intensity_map(const uint32_t *acc_sum, size_t npx, uint64_t n_eff, float *out) {
     const double den = 510.0 * (double)(n_eff ? n_eff : 1);

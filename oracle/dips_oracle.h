@@ -64,6 +64,14 @@ void dipso_run_clip(const uint8_t *frames, size_t n_frames, size_t stride, size_
                     int chroma, int mode, uint32_t tau, uint16_t *state, uint32_t *acc_sum,
                     uint32_t *acc_cnt, uint64_t *sad, uint64_t *cnt, int nthreads);
 
+/*
+ * N4: spatial median filter of an I2 plane, window w in {1,3,5,7} -- spatial_median_filter, dips_shader.wgsl:122-170,
+ * restated as the CORRECT median: full symmetric window [-w/2, +w/2]^2, zero for taps outside the frame (the reference
+ * pads with 0.0, :135-139), element w*w/2 of the ascending order.  The reference's loop only visits the half-open window
+ * [-w/2, w/2) and reads element w*w/2+1 of a mostly-zero array; that defect is deliberately not restated.
+ */
+void dipso_spatial_median_plane(const uint16_t *in, uint32_t width, uint32_t height, int window, uint16_t *out);
+
 /* X6: float outputs derived from the integers */
 void dipso_intensity_map(const uint32_t *acc_sum, size_t npx, uint64_t n_eff, float *out);
 void dipso_frame_means(const uint64_t *sad, size_t n_frames, size_t npx, float *out);

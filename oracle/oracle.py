@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         L.dipso_run_clip.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.dipso_run_clip.restype = None
+        L.dipso_spatial_median_plane.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+        L.dipso_spatial_median_plane.restype = None
         L.dipso_intensity_map.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]
         L.dipso_intensity_map.restype = None
         L.dipso_frame_means.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
@@ -118,6 +120,19 @@ def median4_plane(frames4: np.ndarray, fmt: int, chroma: int = CHROMA_NONE) -> n
     out = np.empty(npx, dtype=np.uint16)
     lib().dipso_median4_plane(ptrs, npx, fmt, chroma, _ptr(out))
     return out
+
+
+def spatial_median(i2: np.ndarray, width: int, height: int, window: int) -> np.ndarray:
+    """correct zero-padded median of the window x window neighbourhood of an I2 plane (N4)"""
+    i2 = np.ascontiguousarray(i2, dtype=np.uint16).reshape(-1)
+    assert i2.size == width * height
+    out = np.empty_like(i2)
+    lib().dipso_spatial_median_plane(_ptr(i2), width, height, window, _ptr(out))
+    return out
+
+
+def filtered_i2(frame: np.ndarray, width: int, height: int, fmt: int, window: int, chroma: int = CHROMA_NONE) -> np.ndarray:
+    return spatial_median(i2_plane(frame, fmt, chroma), width, height, window)
 
 
 class ClipResult:

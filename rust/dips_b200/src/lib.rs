@@ -80,9 +80,9 @@ impl ComputeState {
         filter_type: DiPsFilter,
         chroma_filter: ChromaFilter,
     ) -> anyhow::Result<Self> {
-        if spatial_window_size != 1 {
-            // windows > 1 are effectively broken in the reference shader; not reproduced
-            anyhow::bail!("spatial_window_size {} is not supported by the B200 path (only 1)", spatial_window_size);
+        if ![1, 3, 5, 7].contains(&spatial_window_size) {
+            // windows > 1 run a correct zero-padded median (the reference shader's own loop is defective)
+            anyhow::bail!("spatial_window_size {} is not one of 1, 3, 5, 7", spatial_window_size);
         }
         Ok(Self {
             colorize,

@@ -58,7 +58,7 @@ def test_invalid_arguments_are_rejected_before_touching_the_device():
     assert b"empty frame" in L.dipsb_last_error(None)
     cfg.width, cfg.height, cfg.format = 8, 8, 9
     assert L.dipsb_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
-    cfg.format, cfg.spatial_window = 0, 3
+    cfg.format, cfg.spatial_window = 0, 4
     assert L.dipsb_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"spatial_window" in L.dipsb_last_error(None)
     cfg.spatial_window, cfg.struct_size = 1, 12

@@ -174,3 +174,56 @@ def test_pipelined_push_equals_synchronous(oracle, flavor):
         assert rc_p == (2 if rc_s == dips_b200.NOT_READY else 0)
         assert st_p == st_s and np.array_equal(rgba_p, rgba_s), t
     assert np.array_equal(acc_sync[0], acc_pipe[0]) and np.array_equal(acc_sync[1], acc_pipe[1])
+
+
+def _expected_from_planes(planes, mode, tau, ref_plane=None):
+    """difference path on already filtered I2 planes (numpy restatement of SURVEY X1-X5)"""
+    planes = np.stack(planes).astype(np.int64)
+    if mode == 0:
+        ref = planes[0] if ref_plane is None else ref_plane.astype(np.int64)
+        d = np.abs(planes - ref[None])
+        s_signed = ref[None] - planes
+    else:
+        prev = np.concatenate([planes[:1], planes[:-1]])
+        d = np.abs(planes - prev)
+        s_signed = prev - planes
+    m = d > tau
+    return d.sum(0).astype(np.uint32), m.sum(0).astype(np.uint32), d.sum(1).astype(np.uint64), m.sum(1).astype(np.uint64), s_signed
+
+
+@pytest.mark.parametrize("window", [3, 5, 7])
+@pytest.mark.parametrize("fmt,mode", [(1, 0), (0, 1)])
+def test_spatial_window_streaming_and_batch(oracle, window, fmt, mode):
+    """N4: window > 1 filters every frame's intensity with the correct zero-padded median before differencing --
+    the streaming call (stats, visual frame) and the batch call (accumulators, scalars) against the oracle's filter."""
+    import torch
+    import dips_b200
+    w, h, n, tau = 70, 41, 6, 9
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    planes = [oracle.filtered_i2(clip[t], w, h, fmt, window) for t in range(n)]
+    acc_sum, acc_cnt, sad, cnt, s_signed = _expected_from_planes(planes, mode, tau)
+    with dips_b200.Context(w, h, fmt, mode, tau, spatial_window=window) as ctx:
+        for t in range(n):
+            rc, rgba, (idx, s, c) = ctx.push_frame(clip[t])
+            assert (s, c) == (int(sad[t]), int(cnt[t])), (t, s, c)
+            if t > 0:
+                ref = planes[0] if mode == 0 else planes[t - 1]
+                vis = oracle.visual_frame(ref, planes[t], False, oracle.FILTER_NONE, 5.0)
+                assert np.abs(vis.astype(int) - rgba.astype(int)).max() <= 1
+        gs, gc = ctx.get_accumulators()
+        assert np.array_equal(gs, acc_sum) and np.array_equal(gc, acc_cnt)
+        assert np.array_equal(ctx.get_state_plane(), planes[0] if mode == 0 else planes[-1])
+    dev = torch.from_numpy(clip).cuda()
+    with dips_b200.Context(w, h, fmt, mode, tau, spatial_window=window) as ctx:
+        ctx.run_clip_device(dev.data_ptr(), n)
+        ctx.synchronize()
+        assert not ctx.last_plan()["tma_path"]            # windowed contexts run frame by frame
+        gs, gc = ctx.get_accumulators()
+        gsad, gcnt = ctx.get_scalars(0, n)
+        assert np.array_equal(gs, acc_sum) and np.array_equal(gc, acc_cnt)
+        assert np.array_equal(gsad, sad) and np.array_equal(gcnt, cnt)
+        # reference "start" plane with a window: each of the 4 frames filtered, then the upper median
+        ctx.reset()
+        ctx.prime_median4_device(dev.data_ptr(), clip.shape[1])
+        want = np.sort(np.stack(planes[:4]), axis=0)[2]
+        assert np.array_equal(ctx.get_state_plane(), want)

@@ -210,3 +210,23 @@ def test_dips_alt_flavour(oracle):
         med = np.maximum(i2[1], i2[2]) if intended else np.minimum(i2[1], i2[2])
         assert np.all(np.abs(snap[:, 0].astype(int) - (med + 1) // 2) <= 1) and np.all(snap[:, 3] == 255)
         assert np.all(snap[:, 0] == snap[:, 1]) and np.all(snap[:, 1] == snap[:, 2])
+
+
+@pytest.mark.parametrize("window", [1, 3, 5, 7])
+def test_spatial_median_is_the_true_zero_padded_median(oracle, window):
+    """N4: against numpy (zero padding, full symmetric window, middle element) on ragged sizes."""
+    rng = np.random.default_rng(window)
+    for w, h in ((1, 1), (2, 5), (9, 4), (31, 17)):
+        plane = rng.integers(0, 511, w * h).astype(np.uint16)
+        got = oracle.spatial_median(plane, w, h, window).reshape(h, w)
+        r = window // 2
+        pad = np.pad(plane.reshape(h, w), r, constant_values=0)
+        win = np.lib.stride_tricks.sliding_window_view(pad, (window, window)).reshape(h, w, -1)
+        want = np.sort(win, axis=-1)[..., (window * window) // 2]
+        assert np.array_equal(got, want)
+    # a constant plane keeps its value in the interior and drops to 0 in corners where zeros are the majority
+    flat = np.full(11 * 11, 300, np.uint16)
+    out = oracle.spatial_median(flat, 11, 11, window).reshape(11, 11)
+    assert out[5, 5] == 300
+    if window > 1:
+        assert out[0, 0] == 0
