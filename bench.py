@@ -313,9 +313,12 @@ def main():
 
     # sanity of the last step's results (cheap integer identity; parity proper lives in tests/)
     sad, cnt = ctx.get_scalars(t0_frame, frames)
-    if world == 1:
-        acc_sum, acc_cnt = ctx.get_accumulators()
-        assert int(acc_sum.astype(np.uint64).sum()) == int(sad.sum()) and int(acc_cnt.astype(np.uint64).sum()) == int(cnt.sum())
+    acc_sum, acc_cnt = ctx.get_accumulators()
+    tot = torch.tensor([int(sad.sum()), int(cnt.sum())], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)          # per-frame scalars are per shard; the all-reduced maps must add up to all of them
+    assert int(acc_sum.astype(np.uint64).sum()) == int(tot[0]) and int(acc_cnt.astype(np.uint64).sum()) == int(tot[1]), \
+        "checksum of checksums failed"
 
     # ---- roofline of the dominant kernel --------------------------------------------------------------------------
     alg_bytes = frames * fb + npx * 2 + npx * 8      # every input byte once + reference plane + accumulators once

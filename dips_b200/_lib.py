@@ -33,6 +33,7 @@ SYMBOLS = {
     "dipsb_reset": (_i32, [_vp]),
     "dipsb_set_threshold": (_i32, [_vp, _u32]),
     "dipsb_set_stream": (_i32, [_vp, _vp]),
+    "dipsb_adopt_stream": (_i32, [_vp, _vp]),
     "dipsb_use_private_stream": (_i32, [_vp]),
     "dipsb_synchronize": (_i32, [_vp]),
     "dipsb_prime_device": (_i32, [_vp, _vp]),

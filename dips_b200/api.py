@@ -100,6 +100,10 @@ class Context:
     def set_stream(self, stream: int) -> None:
         self._ck(self._lib.dipsb_set_stream(self._h, stream))
 
+    def adopt_stream(self, stream: int) -> None:
+        """switch streams without ordering (the caller orders the streams with its own events)"""
+        self._ck(self._lib.dipsb_adopt_stream(self._h, stream))
+
     def use_private_stream(self) -> None:
         self._ck(self._lib.dipsb_use_private_stream(self._h))
 

@@ -349,6 +349,12 @@ extern "C" int32_t dipsb_set_stream(dipsb_ctx* c, void* stream) {
     return DIPSB_OK;
 }
 
+extern "C" int32_t dipsb_adopt_stream(dipsb_ctx* c, void* stream) {
+    if (!c) return DIPSB_ERR_INVALID;
+    c->stream = (cudaStream_t)stream;   // no ordering: the caller has ordered the two streams with its own events
+    return DIPSB_OK;
+}
+
 extern "C" int32_t dipsb_use_private_stream(dipsb_ctx* c) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));

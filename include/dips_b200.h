@@ -112,6 +112,9 @@ int32_t dipsb_set_threshold(dipsb_ctx *ctx, uint32_t threshold);
 /* all further work of this context is issued on `stream` (a cudaStream_t; NULL = the CUDA default stream); it is ordered
  * after the work already issued (the new stream waits on an event of the old one; the host is not blocked) */
 int32_t dipsb_set_stream(dipsb_ctx *ctx, void *stream);
+/* same without any ordering: for callers that pipeline several contexts over several streams and order them with their
+ * own events (an implicit wait here would serialise unrelated work that was queued on the old stream meanwhile) */
+int32_t dipsb_adopt_stream(dipsb_ctx *ctx, void *stream);
 /* go back to the context's private non-blocking stream (the state after dipsb_create) */
 int32_t dipsb_use_private_stream(dipsb_ctx *ctx);
 int32_t dipsb_synchronize(dipsb_ctx *ctx);

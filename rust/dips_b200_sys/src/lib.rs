@@ -67,6 +67,7 @@ extern "C" {
     pub fn dipsb_reset(ctx: *mut dipsb_ctx) -> i32;
     pub fn dipsb_set_threshold(ctx: *mut dipsb_ctx, threshold: u32) -> i32;
     pub fn dipsb_set_stream(ctx: *mut dipsb_ctx, stream: *mut c_void) -> i32;
+    pub fn dipsb_adopt_stream(ctx: *mut dipsb_ctx, stream: *mut c_void) -> i32;
     pub fn dipsb_use_private_stream(ctx: *mut dipsb_ctx) -> i32;
     pub fn dipsb_synchronize(ctx: *mut dipsb_ctx) -> i32;
     pub fn dipsb_prime_device(ctx: *mut dipsb_ctx, d_frame: *const c_void) -> i32;
