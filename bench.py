@@ -52,6 +52,7 @@ def parse_args():
     p.add_argument("--tile-px", type=int, default=0)
     p.add_argument("--segments", type=int, default=0)
     p.add_argument("--regs", type=int, default=0)
+    p.add_argument("--kernel", type=int, default=-1, help="0 clip_kernel, 1 clip_kernel_ws, -1 library default")
     return p.parse_args()
 
 
@@ -249,6 +250,8 @@ def main():
     torch.cuda.synchronize()
 
     ctx = dips_b200.Context(w, h, fmt, mode, tau, device=local_rank)
+    if args.kernel >= 0:
+        ctx.set_kernel(args.kernel)
     if args.stages or args.tile_px or args.segments or args.regs:
         ctx.set_tuning(args.stages, args.tile_px, args.segments, args.regs)
     ctx.set_stream(stream.cuda_stream)

@@ -61,6 +61,7 @@ SYMBOLS = {
     "dipsb_enable_timing": (_i32, [_vp, _i32]),
     "dipsb_clip_kernel_time": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "dipsb_stream_probe": (_i32, [_vp, _vp, _u64, _u64, _u32, C.POINTER(C.c_float)]),
+    "dipsb_set_kernel": (_i32, [_vp, _i32]),
     "dipsb_plan_query": (_i32, [_u32, _u32, _i32, _u32, C.POINTER(_u32 * 8)]),
     "dipsb_set_tuning": (_i32, [_vp, _u32, _u32, _u32, _u32]),
 }

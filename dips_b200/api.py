@@ -113,6 +113,10 @@ class Context:
     def set_tuning(self, stages: int = 0, tile_px: int = 0, segments: int = 0, regs: int = 0) -> None:
         self._ck(self._lib.dipsb_set_tuning(self._h, stages, tile_px, segments, regs))
 
+    def set_kernel(self, kernel: int) -> None:
+        """0 = clip_kernel, 1 = clip_kernel_ws (producer warp, stage-unrolled)"""
+        self._ck(self._lib.dipsb_set_kernel(self._h, kernel))
+
     def enable_timing(self, on: bool = True) -> None:
         self._ck(self._lib.dipsb_enable_timing(self._h, int(on)))
 
@@ -131,7 +135,7 @@ class Context:
     def last_plan(self) -> dict:
         out = (C.c_uint32 * 8)()
         self._ck(self._lib.dipsb_last_plan(self._h, C.byref(out)))
-        return dict(tiles=out[0], segments=out[1], threads=out[2], stages=out[3], blocks_per_sm=out[4],
+        return dict(tiles=out[0], segments=out[1], threads=out[2], stages=out[3] & 0xFFFF, kernel=out[3] >> 16, blocks_per_sm=out[4],
                     tile_px=out[5], smem_bytes=out[6] & 0xFFFFFF, regs=out[6] >> 24, tma_path=bool(out[7]))
 
     # -- state plane ------------------------------------------------------------------------------------------

@@ -59,6 +59,7 @@ struct dipsb_ctx {
     uint8_t* d_chunk[2] = {nullptr, nullptr};
     size_t chunk_bytes = 0;
     uint32_t tune_stages = 0, tune_tile_px = 0, tune_segments = 0, tune_regs = 0;
+    int tune_kernel = 0;
     uint32_t last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool timing = false;
     std::vector<cudaEvent_t> tev;              // start/stop pairs around clip kernel launches
@@ -106,13 +107,18 @@ static int32_t filtered_plane(dipsb_ctx* c, const uint8_t* d_frame, int format, 
 // npx / (num_sms * waves) rounded up to 16 pixels with the fewest waves that fit a block (<= 896 threads at 72 registers,
 // <= 1024 at 64); deepest pipeline (<= 4 stages) that fits in shared memory.  Frames too small to give every SM a
 // 2048-pixel tile keep 2048-pixel tiles, run several blocks per SM and are split into frame segments instead.
-static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_tile_px, uint32_t force_regs = 0) {
+static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_tile_px, uint32_t force_regs = 0, int kernel = 0) {
     const uint64_t min_tile = std::min<uint64_t>(2048, (g.npx + 15) / 16 * 16);
+    if (kernel == 1) {   // warp-specialised variant: 64 registers, 16 px/thread, block = consumers + one producer warp
+        if (force_regs && force_regs != 64) return false;
+        if (force_stages && force_stages != 3 && force_stages != 4) return false;
+        force_regs = 64;
+    }
     for (int regs : {72, 64, 80, 96, 128}) {
         if (force_regs ? (uint32_t)regs != force_regs : regs > 72) continue;   // 80/96/128 only on request (tuning)
         const int groups = clip_groups(regs);
         const uint32_t px_thr = (uint32_t)(kPxPerThread * groups);
-        const uint32_t max_thr = (uint32_t)clip_max_threads_per_sm(regs);
+        const uint32_t max_thr = (uint32_t)clip_max_threads_per_sm(regs) - (kernel == 1 ? 32u : 0u);
         const uint64_t max_slots = (uint64_t)max_thr * px_thr;
         uint64_t tile_px;
         if (force_tile_px) tile_px = force_tile_px;
@@ -121,7 +127,7 @@ static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_til
             tile_px = (g.npx + g.num_sms * waves - 1) / (g.num_sms * waves);
             tile_px = std::max<uint64_t>((tile_px + 15) / 16 * 16, min_tile);
             // 72 registers (896 threads) unless only the 64-register variant (1024 threads) saves a whole wave
-            if (!force_regs && regs == 72) {
+            if (!force_regs && regs == 72 && kernel == 0) {
                 const uint64_t slots64 = 1024ull * kPxPerThread;
                 const uint64_t waves64 = (g.npx + g.num_sms * slots64 - 1) / (g.num_sms * slots64);
                 if (waves64 < waves) continue;
@@ -133,8 +139,8 @@ static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_til
         // measured (profiles/r01_sweeps.md): 4 stages beat 3 for 42-49 KB slices, but a 4 x 56 KB ring (4K RGBx, 224 KB: all
         // of the SM's shared memory) is slower than 3 x 56 KB -- keep the ring <= 200 KB
         if (!force_stages && clip_smem_bytes(thr, g.bpp, stages, regs) > 200 * 1024) stages = 3;
-        int occ = clip_occupancy(thr, g.bpp, stages, regs);
-        while (!force_stages && occ <= 0 && stages > 2) occ = clip_occupancy(thr, g.bpp, --stages, regs);
+        int occ = clip_occupancy(thr + (kernel == 1 ? 32u : 0u), g.bpp, stages, regs);
+        while (!force_stages && occ <= 0 && stages > (kernel == 1 ? 3u : 2u)) occ = clip_occupancy(thr + (kernel == 1 ? 32u : 0u), g.bpp, --stages, regs);
         if (occ <= 0) continue;
         g.threads = thr;
         g.tile_px = (uint32_t)tile_px;
@@ -145,6 +151,7 @@ static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_til
         g.blocks_per_sm = (uint32_t)occ;
         g.regs = regs;
         g.groups = groups;
+        g.kernel = kernel;
         return true;
     }
     return false;
@@ -385,7 +392,7 @@ extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile
     if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_tuning: geometry can only change on a fresh or reset context");
     CK(c, cudaStreamSynchronize(c->stream));
     Geometry g = c->g;
-    if (!plan_geometry(g, stages, tile_px, regs)) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u / regs %u do not fit", tile_px, stages, regs);
+    if (!plan_geometry(g, stages, tile_px, regs, c->tune_kernel)) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u / regs %u do not fit", tile_px, stages, regs);
     for (int k = 0; k < 2; ++k) { cudaFree(c->state[k]); c->state[k] = nullptr; }
     cudaFree(c->acc); c->acc = nullptr;
     cudaFree(c->planar); c->planar = nullptr;
@@ -407,10 +414,29 @@ extern "C" int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t for
     return DIPSB_OK;
 }
 
+extern "C" int32_t dipsb_set_kernel(dipsb_ctx* c, int32_t kernel) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (kernel < 0 || kernel > 1) return fail(c, DIPSB_ERR_INVALID, "set_kernel: %d is not 0 (clip_kernel) or 1 (clip_kernel_ws)", kernel);
+    if (kernel == c->g.kernel) return DIPSB_OK;
+    if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_kernel: only on a fresh or reset context");
+    CK(c, cudaStreamSynchronize(c->stream));
+    Geometry g = c->g;
+    if (!plan_geometry(g, c->tune_stages, c->tune_tile_px, c->tune_regs, kernel))
+        return fail(c, DIPSB_ERR_INVALID, "set_kernel: the current tuning (stages %u, regs %u) does not fit kernel %d", c->tune_stages, c->tune_regs, kernel);
+    for (int k = 0; k < 2; ++k) { cudaFree(c->state[k]); c->state[k] = nullptr; }
+    cudaFree(c->acc); c->acc = nullptr;
+    cudaFree(c->planar); c->planar = nullptr;
+    c->g = g;
+    c->tune_kernel = kernel;
+    c->state_valid = false;
+    return alloc_planes(c);
+}
+
 extern "C" int32_t dipsb_last_plan(const dipsb_ctx* c, uint32_t out[8]) {
     if (!c || !out) return DIPSB_ERR_INVALID;
     memcpy(out, c->last_plan, sizeof c->last_plan);
-    out[0] = c->g.n_tiles; out[2] = c->g.threads; out[3] = c->g.stages; out[4] = c->g.blocks_per_sm; out[5] = c->g.tile_px;
+    out[0] = c->g.n_tiles; out[2] = c->g.threads; out[3] = c->g.stages | ((uint32_t)c->g.kernel << 16); out[4] = c->g.blocks_per_sm; out[5] = c->g.tile_px;
     out[6] = (uint32_t)clip_smem_bytes(c->g.threads, c->g.bpp, c->g.stages, c->g.regs) | ((uint32_t)c->g.regs << 24);
     return DIPSB_OK;
 }

@@ -415,6 +415,222 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
     }
 }
 
+// ---- warp-specialised variant ----------------------------------------------------------------------------------------
+// Same arithmetic, tiles, accumulator order and barriers as clip_kernel, restructured to spend fewer instructions per frame
+// (under the 1 kW power cap the SMs run at ~1.6 GHz and the RGB8 kernel becomes issue-bound, profiles/r01_sweeps.md):
+//   * a dedicated producer warp (the last warp of the block) issues the TMA copies, so the consumer warps carry no
+//     divergent "am I thread 0" branch and all S buffers are in flight;
+//   * the frame loop is unrolled over the S pipeline stages (x2 for odd S, for the prev/cur ping-pong): stage index,
+//     barrier addresses and mbarrier parities are compile-time, no per-frame stage bookkeeping;
+//   * per-frame sums use 3-input adds on the packed lanes and one IDP.2A fold instead of an IDP.2A per register.
+template <int N>
+__device__ __forceinline__ uint32_t diff_px_ws(const uint32_t* cur, const uint32_t* ref, uint32_t* accD, uint32_t* accM,
+                                               uint32_t negtau2, uint32_t one) {
+    uint32_t d[N], m[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const uint32_t hi = __vmaxu2(cur[j], ref[j]);
+        const uint32_t sum = add_fma(cur[j], ref[j], one);
+        d[j] = mad_fma(hi, one + one, 0u - sum);
+        m[j] = __viaddmin_s16x2_relu(d[j], negtau2, 0x00010001u);
+        accD[j] = add_fma(accD[j], d[j], one);
+        accM[j] = add_fma(accM[j], m[j], one);
+    }
+    uint32_t sD = 0u, sM = 0u;   // packed lane sums: <= 8*510 and <= 8 per lane
+#pragma unroll
+    for (int j = 0; j + 1 < N; j += 2) { sD = sD + d[j] + d[j + 1]; sM = sM + m[j] + m[j + 1]; }
+    return __dp2a_lo(sD, 0x0101u, __dp2a_lo(sM, 0x0101u, 0u) << 20);
+}
+
+template <int BPP, int CH, int MODE, int S>
+__global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int kWords = BPP * 4;
+    constexpr int R = 8;
+    constexpr int U = (S % 2 == 0) ? S : 2 * S;                  // frames per trip
+    constexpr uint32_t kFlushEvery = (uint32_t)(kFlushFrames / U) * U;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t nthr = blockDim.x - 32u;                      // consumer threads; the last warp is the producer
+    const uint32_t tile = blockIdx.x, seg = blockIdx.y;
+    const uint32_t stage_bytes = P.stage_bytes;
+    const uint32_t slots = nthr * kPxPerThread;
+
+    const uint32_t t0 = (uint32_t)(((uint64_t)P.n_frames * seg) / P.n_segments);
+    const uint32_t t1 = (uint32_t)(((uint64_t)P.n_frames * (seg + 1)) / P.n_segments);
+    const bool prime_first = (MODE == 1) && (seg > 0);
+    const uint32_t first = t0 - (prime_first ? 1u : 0u);
+    const uint32_t count = t1 - first;
+
+    const uint64_t tile_first_px = (uint64_t)tile * P.tile_px;
+    const uint64_t remain_px = P.npx - tile_first_px;
+    const uint32_t valid_px = remain_px < P.tile_px ? (uint32_t)remain_px : P.tile_px;
+    const uint32_t valid_bytes = valid_px * BPP;
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_bar = smem_base + S * stage_bytes;
+    const uint32_t empty_bar = full_bar + 8u * S;
+
+    if (valid_px < slots) {
+        for (uint32_t o = tid * 16u; o < S * stage_bytes; o += blockDim.x * 16u)
+            *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (uint32_t s = 0; s < (uint32_t)S; ++s) {
+            mbar_init(full_bar + 8u * s, 1);
+            mbar_init(empty_bar + 8u * s, P.active_warps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == nthr / 32u) {   // ---- producer warp: one TMA bulk copy per frame, S frames in flight ----
+        if (lane == 0) {
+            const uint8_t* src = P.frames + (uint64_t)first * P.stride + tile_first_px * BPP;
+            uint32_t stage = 0, par = 1;   // the wait on a never-used buffer falls through (parity of the preceding phase)
+            for (uint32_t it = 0; it < count; ++it) {
+                mbar_wait(empty_bar + 8u * stage, par);
+                mbar_arrive_expect_tx(full_bar + 8u * stage, valid_bytes);
+                if (P.l2_evict_first) bulk_g2s(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage, policy_evict_first());
+                else bulk_g2s_nohint(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage);
+                src += P.stride;
+                if (++stage == (uint32_t)S) { stage = 0; par ^= 1u; }
+            }
+        }
+        return;
+    }
+    if (warp >= P.active_warps) return;
+
+    uint32_t ra[R], rb[R];
+    if constexpr (BPP == 3) {
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        const uint32_t off = tid * kPxPerThread;
+        if (off < valid_px) {
+            const uint4* sp = reinterpret_cast<const uint4*>(P.state_in + tile_first_px + off);
+            r0 = __ldg(sp); r1 = __ldg(sp + 1);
+        }
+        ra[0] = r0.x; ra[1] = r0.y; ra[2] = r0.z; ra[3] = r0.w;
+        ra[4] = r1.x; ra[5] = r1.y; ra[6] = r1.z; ra[7] = r1.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint2 r = make_uint2(0, 0);
+            const uint32_t off = 4u * (q * nthr + tid);
+            if (off < valid_px) r = __ldg(reinterpret_cast<const uint2*>(P.state_in + tile_first_px + off));
+            ra[2 * q] = r.x; ra[2 * q + 1] = r.y;
+        }
+    }
+    uint32_t accD[R], accM[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) accD[j] = accM[j] = 0u;
+
+    const uint32_t tau = P.tau > 511u ? 511u : P.tau;
+    const uint32_t negtau2 = ((0u - tau) & 0xFFFFu) * 0x00010001u;
+    uint32_t part = first * P.words_per_frame + tile * P.active_warps + warp;
+    const uint32_t my_smem = smem_base + (BPP == 3 ? tid * 48u : tid * 16u);
+    const uint32_t my_step = (BPP == 3) ? 16u : nthr * 16u;
+    const uint32_t one = P.one;
+    const uint32_t hint = P.wait_hint_ns;
+
+    auto flush = [&]() {
+        uint32_t* const acc_sum = P.acc_sum + (uint64_t)tile * slots + tid;
+        uint32_t* const acc_cnt = P.acc_cnt + (uint64_t)tile * slots + tid;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            atomicAdd(acc_sum + (2 * j) * nthr, accD[j] & 0xFFFFu);
+            atomicAdd(acc_sum + (2 * j + 1) * nthr, accD[j] >> 16);
+            atomicAdd(acc_cnt + (2 * j) * nthr, accM[j] & 0xFFFFu);
+            atomicAdd(acc_cnt + (2 * j + 1) * nthr, accM[j] >> 16);
+            accD[j] = accM[j] = 0u;
+        }
+    };
+    // bytes -> packed intensities of one frame sitting in buffer `stage` (compile-time or run-time index)
+    auto fetch = [&](uint32_t stage, uint32_t par, uint32_t* cur, uint32_t token) {
+        mbar_wait_after(full_bar + 8u * stage, par, token, hint);
+        uint32_t w[kWords];
+#pragma unroll
+        for (int v = 0; v < BPP; ++v) {
+            const uint4 x = lds128(my_smem + stage * stage_bytes + my_step * v);
+            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
+        intensity16<BPP, CH>(w, cur);
+    };
+    auto emit = [&](uint32_t packed) {
+        const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, packed);
+        if (lane == 0) P.partials[part] = wsum;
+        part += P.words_per_frame;
+        return wsum;
+    };
+
+    uint32_t iter = 0, token = 0, since_flush = 0;
+    // ---- lead-in with run-time stage index: the halo frame of a per-frame segment, then up to the next trip boundary
+    if (prime_first) {
+        fetch(0u, 0u, ra, token);
+        part += P.words_per_frame;
+        iter = 1;
+        while (iter % U != 0 && iter < count) {
+            fetch(iter % S, (iter / S) & 1u, rb, token);
+            token = emit(diff_px_ws<R>(rb, ra, accD, accM, negtau2, one));
+#pragma unroll
+            for (int j = 0; j < R; ++j) ra[j] = rb[j];
+            ++iter; ++since_flush;
+        }
+    }
+    // ---- main loop: U frames per trip, compile-time stages; iter is a multiple of U here
+    uint32_t par = (iter / S) & 1u;
+    while (iter + U <= count) {
+#pragma unroll
+        for (int u = 0; u < U; u += 2) {
+            fetch((uint32_t)(u % S), par ^ (uint32_t)((u / S) & 1), rb, token);
+            token = emit(diff_px_ws<R>(rb, ra, accD, accM, negtau2, one));
+            if constexpr (MODE == 0) {
+                fetch((uint32_t)((u + 1) % S), par ^ (uint32_t)(((u + 1) / S) & 1), rb, token);
+                token = emit(diff_px_ws<R>(rb, ra, accD, accM, negtau2, one));
+            } else {
+                fetch((uint32_t)((u + 1) % S), par ^ (uint32_t)(((u + 1) / S) & 1), ra, token);
+                token = emit(diff_px_ws<R>(ra, rb, accD, accM, negtau2, one));
+            }
+        }
+        iter += U;
+        par ^= (uint32_t)((U / S) & 1);
+        since_flush += U;
+        if (since_flush + U > (uint32_t)kFlushFrames) { flush(); since_flush = 0; }
+    }
+    // ---- tail with run-time stage index
+    while (iter < count) {
+        fetch(iter % S, (iter / S) & 1u, rb, token);
+        token = emit(diff_px_ws<R>(rb, ra, accD, accM, negtau2, one));
+        if constexpr (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) ra[j] = rb[j];
+        }
+        ++iter;
+        if (++since_flush >= (uint32_t)kFlushFrames) { flush(); since_flush = 0; }
+    }
+    flush();
+    (void)kFlushEvery;
+
+    if (MODE == 1 && seg == P.n_segments - 1) {
+        if constexpr (BPP == 3) {
+            const uint32_t off = tid * kPxPerThread;
+            if (off < valid_px) {
+                uint4* sp = reinterpret_cast<uint4*>(P.state_out + tile_first_px + off);
+                sp[0] = make_uint4(ra[0], ra[1], ra[2], ra[3]);
+                sp[1] = make_uint4(ra[4], ra[5], ra[6], ra[7]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t off = 4u * (q * nthr + tid);
+                if (off < valid_px)
+                    *reinterpret_cast<uint2*>(P.state_out + tile_first_px + off) = make_uint2(ra[2 * q], ra[2 * q + 1]);
+            }
+        }
+    }
+}
+
 // Roofline probe: the clip kernel's memory side only -- same tiles, same TMA ring, same barriers, but the consumers just
 // release each buffer without reading it.  Its bandwidth is the ceiling of this access pattern on this GPU.
 __global__ void stream_probe_kernel(const __grid_constant__ KParams P, int bpp) {
@@ -477,8 +693,26 @@ cudaError_t launch_t(const Geometry& g, const ClipArgs& a, const KParams& kp, si
     }
 }
 
+template <int BPP, int CH, int MODE, int S>
+cudaError_t launch_ws(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
+    auto kfn = clip_kernel_ws<BPP, CH, MODE, S>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    dim3 grid(g.n_tiles, a.n_segments, 1), block(g.threads + 32, 1, 1);   // + the producer warp
+    kfn<<<grid, block, smem, s>>>(kp);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int BPP, int CH>
 cudaError_t launch_m(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
+    if (g.kernel == 1) {   // warp-specialised variant: 16 px/thread, 64 registers, 3 or 4 compile-time stages
+        if (g.stages == 4) return a.mode == 0 ? launch_ws<BPP, CH, 0, 4>(g, a, kp, smem, s) : launch_ws<BPP, CH, 1, 4>(g, a, kp, smem, s);
+        if (g.stages == 3) return a.mode == 0 ? launch_ws<BPP, CH, 0, 3>(g, a, kp, smem, s) : launch_ws<BPP, CH, 1, 3>(g, a, kp, smem, s);
+        return cudaErrorInvalidValue;
+    }
     return a.mode == 0 ? launch_t<BPP, CH, 0>(g, a, kp, smem, s) : launch_t<BPP, CH, 1>(g, a, kp, smem, s);
 }
 

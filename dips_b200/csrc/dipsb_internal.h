@@ -25,6 +25,7 @@ struct Geometry {
     uint32_t stages;         // pipeline depth
     int regs;                // kernel variant: 64/72/80/96 registers with 16 pixels per thread, 128 registers with 32
     int groups;              // groups of 16 pixels per thread (1 or 2) == clip_groups(regs)
+    int kernel;              // 0: clip_kernel (thread 0 of the block produces); 1: clip_kernel_ws (producer warp, stage-unrolled)
     uint32_t num_sms;
 };
 

@@ -191,7 +191,7 @@ int32_t dipsb_synth_fill_device(int32_t device, void *d_dst, uint64_t first_fram
                                 void *stream);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t dipsb_launch_count(void);
-/* last clip kernel geometry, for reports: [0] tiles, [1] frame segments, [2] threads per block, [3] stages, [4] blocks per
+/* last clip kernel geometry, for reports: [0] tiles, [1] frame segments, [2] threads per block, [3] stages | kernel << 16, [4] blocks per
  * SM, [5] pixels per tile, [6] dynamic shared memory bytes | registers << 24, [7] 1 = TMA clip kernel / 0 = fallback */
 int32_t dipsb_last_plan(const dipsb_ctx *ctx, uint32_t out[8]);
 /* optional device-side timing of the clip kernel alone (cudaEvent pairs on the context's stream around each launch).
@@ -202,6 +202,9 @@ int32_t dipsb_clip_kernel_time(dipsb_ctx *ctx, double *total_ms, uint64_t *launc
  * computes nothing; *ms = mean kernel time over `reps` launches.  Gives the bandwidth ceiling of the access pattern. */
 int32_t dipsb_stream_probe(dipsb_ctx *ctx, const void *d_frames, uint64_t n_frames, uint64_t frame_stride_bytes,
                            uint32_t reps, float *ms);
+/* which clip kernel runs the batch path: 0 = clip_kernel (thread 0 of each block issues the TMA copies), 1 = clip_kernel_ws
+ * (dedicated producer warp, frame loop unrolled over the pipeline stages; 64 registers, 3 or 4 stages).  Same results. */
+int32_t dipsb_set_kernel(dipsb_ctx *ctx, int32_t kernel);
 /* host-only: the plan (same layout as dipsb_last_plan, [7] = active warps per block) the library would choose for a
  * geometry on a device with num_sms SMs; touches no device. */
 int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t format, uint32_t num_sms, uint32_t out[8]);

@@ -95,6 +95,7 @@ extern "C" {
     pub fn dipsb_enable_timing(ctx: *mut dipsb_ctx, on: i32) -> i32;
     pub fn dipsb_clip_kernel_time(ctx: *mut dipsb_ctx, total_ms: *mut f64, launches: *mut u64) -> i32;
     pub fn dipsb_stream_probe(ctx: *mut dipsb_ctx, d_frames: *const c_void, n_frames: u64, frame_stride_bytes: u64, reps: u32, ms: *mut f32) -> i32;
+    pub fn dipsb_set_kernel(ctx: *mut dipsb_ctx, kernel: i32) -> i32;
     pub fn dipsb_plan_query(width: u32, height: u32, format: i32, num_sms: u32, out: *mut u32) -> i32;
     pub fn dipsb_set_tuning(ctx: *mut dipsb_ctx, stages: u32, tile_px: u32, segments: u32, regs: u32) -> i32;
 }

@@ -45,7 +45,12 @@ def run_gpu(torch, clip, w, h, fmt, mode, tau, chroma=0, chunks=None, tuning=Non
         base = dev.data_ptr()
     with dips_b200.Context(w, h, fmt, mode, tau, chroma) as ctx:
         if tuning:
-            ctx.set_tuning(**tuning)
+            tuning = dict(tuning)
+            kernel = tuning.pop("kernel", None)
+            if kernel is not None:
+                ctx.set_kernel(kernel)
+            if tuning:
+                ctx.set_tuning(**tuning)
         bounds = [0, n] if not chunks else chunks
         for a, b in zip(bounds, bounds[1:]):
             ctx.run_clip_device(base + a * stride, b - a, stride, a)
@@ -395,3 +400,57 @@ def test_flush_boundaries(torch_cuda, oracle, mode, n, segments):
     full[0] = 0                            # overall: D = 510 on every frame after the first
     got = run_gpu(torch_cuda, full, w, h, 0, 0, 0, tuning=dict(segments=segments))
     check(oracle, got, full, 0, 0, 0)
+
+
+# ---- the warp-specialised clip kernel (clip_kernel_ws): same results as clip_kernel on every path ----------------------
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("chroma", [0, 1, 3])
+def test_ws_kernel_all_variants(torch_cuda, oracle, fmt, mode, chroma):
+    w, h, n = 208, 75, 11      # frame bytes are a multiple of 16 for 3 and 4 B/px (TMA path)
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE, seed=23 + fmt)
+    got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 24, chroma, tuning=dict(kernel=1))
+    assert got[5]["kernel"] == 1 and got[5]["tma_path"]
+    check(oracle, got, clip, fmt, mode, 24, chroma)
+
+
+@pytest.mark.parametrize("stages", [3, 4])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,segments,w,h", [(1, 1, 64, 32), (2, 1, 64, 32), (5, 1, 512, 7), (13, 3, 96, 64), (129, 1, 96, 64),
+                                            (300, 2, 96, 64), (385, 3, 48, 32), (140, 1, 640, 360)])
+def test_ws_kernel_frame_counts_segments_and_flush(torch_cuda, oracle, stages, mode, n, segments, w, h):
+    """lead-in (halo frame of a segment), unrolled trips and the run-time tail of clip_kernel_ws for both stage counts;
+    saturated differences across the 128-frame flush"""
+    clip = np.zeros((n, w * h * 3), np.uint8)
+    clip[1::2] = 255
+    clip[0] = 0
+    got = run_gpu(torch_cuda, clip, w, h, 0, mode, 509, tuning=dict(kernel=1, stages=stages, segments=segments))
+    assert got[5]["kernel"] == 1 and got[5]["stages"] == stages
+    check(oracle, got, clip, 0, mode, 509)
+    scene = oracle.synth_clip(n, w, h, 1, profile=oracle.SYNTH_SCENE)
+    got = run_gpu(torch_cuda, scene, w, h, 1, mode, 20, tuning=dict(kernel=1, stages=stages, segments=segments))
+    check(oracle, got, scene, 1, mode, 20)
+
+
+@pytest.mark.parametrize("w,h,fmt,n", [(1920, 1080, 0, 24), (3840, 2160, 1, 10), (7680, 4320, 0, 5)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_ws_kernel_baseline_geometries(torch_cuda, oracle, w, h, fmt, n, mode):
+    import dips_b200
+    torch = torch_cuda
+    fb = w * h * dips_b200.bytes_per_pixel(fmt)
+    dev = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
+    dips_b200.synth_fill_device(0, dev.data_ptr(), 0, n, w, h, fmt, 0x44695073, dips_b200.SYNTH_SCENE,
+                                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = dev.cpu().numpy().reshape(n, fb)
+    want = oracle.run_clip(host, fmt, mode, 32)
+    with dips_b200.Context(w, h, fmt, mode, 32) as ctx:
+        ctx.set_kernel(1)
+        ctx.run_clip_device(dev.data_ptr(), n)
+        ctx.synchronize()
+        s, c = ctx.get_accumulators()
+        sad, cnt = ctx.get_scalars(0, n)
+        state = ctx.get_state_plane()
+        assert ctx.last_plan()["kernel"] == 1
+    assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)
+    assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt) and np.array_equal(state, want.state)
