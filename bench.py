@@ -52,7 +52,7 @@ def parse_args():
     p.add_argument("--tile-px", type=int, default=0)
     p.add_argument("--segments", type=int, default=0)
     p.add_argument("--regs", type=int, default=0)
-    p.add_argument("--kernel", type=int, default=-1, help="0 clip_kernel, 1 clip_kernel_ws, -1 library default")
+    p.add_argument("--kernel", type=int, default=-1, help="0 clip_kernel, 1 clip_kernel_ws, -1 automatic (library default)")
     return p.parse_args()
 
 

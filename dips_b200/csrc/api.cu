@@ -59,7 +59,7 @@ struct dipsb_ctx {
     uint8_t* d_chunk[2] = {nullptr, nullptr};
     size_t chunk_bytes = 0;
     uint32_t tune_stages = 0, tune_tile_px = 0, tune_segments = 0, tune_regs = 0;
-    int tune_kernel = 0;
+    int tune_kernel = -1;                      // -1: automatic (clip_kernel_ws whenever the tuning allows it)
     uint32_t last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool timing = false;
     std::vector<cudaEvent_t> tev;              // start/stop pairs around clip kernel launches
@@ -186,6 +186,13 @@ static int32_t filtered_plane(dipsb_ctx* c, const uint8_t* d_frame, int format, 
     return DIPSB_OK;
 }
 
+// clip_kernel_ws (producer warp, stage-unrolled; +7-10 % sustained on 3 B/px clips, equal elsewhere: profiles/r01_sweeps.md)
+// exists for 64 registers and 3 or 4 stages; any other forced tuning selects clip_kernel
+static int pick_kernel(int requested, uint32_t stages, uint32_t regs) {
+    if (requested >= 0) return requested;
+    return ((regs == 0 || regs == 64) && (stages == 0 || stages == 3 || stages == 4)) ? 1 : 0;
+}
+
 // ---- lifetime ------------------------------------------------------------------------------------------------------
 extern "C" int32_t dipsb_abi_version(void) { return DIPSB_ABI_VERSION; }
 
@@ -283,7 +290,7 @@ extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
     g.width = cfg->width; g.height = cfg->height; g.npx = (uint64_t)cfg->width * cfg->height;
     g.format = cfg->format; g.bpp = bpp_of(cfg->format); g.chan_byte = chan_byte_of(cfg->format, cfg->chroma);
     g.num_sms = (uint32_t)prop.multiProcessorCount;
-    if (!plan_geometry(g, 0, 0)) {
+    if (!plan_geometry(g, 0, 0, 0, 1)) {
         delete c;
         return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: no kernel geometry fits %ux%u", cfg->width, cfg->height);
     }
@@ -392,7 +399,7 @@ extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile
     if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_tuning: geometry can only change on a fresh or reset context");
     CK(c, cudaStreamSynchronize(c->stream));
     Geometry g = c->g;
-    if (!plan_geometry(g, stages, tile_px, regs, c->tune_kernel)) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u / regs %u do not fit", tile_px, stages, regs);
+    if (!plan_geometry(g, stages, tile_px, regs, pick_kernel(c->tune_kernel, stages, regs))) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u / regs %u do not fit", tile_px, stages, regs);
     for (int k = 0; k < 2; ++k) { cudaFree(c->state[k]); c->state[k] = nullptr; }
     cudaFree(c->acc); c->acc = nullptr;
     cudaFree(c->planar); c->planar = nullptr;
@@ -408,8 +415,8 @@ extern "C" int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t for
     Geometry g{};
     g.width = width; g.height = height; g.npx = (uint64_t)width * height;
     g.format = format; g.bpp = bpp_of(format); g.chan_byte = -1; g.num_sms = num_sms;
-    if (!plan_geometry(g, 0, 0)) return DIPSB_ERR_INVALID;
-    out[0] = g.n_tiles; out[1] = 0; out[2] = g.threads; out[3] = g.stages; out[4] = g.blocks_per_sm; out[5] = g.tile_px;
+    if (!plan_geometry(g, 0, 0, 0, 1)) return DIPSB_ERR_INVALID;
+    out[0] = g.n_tiles; out[1] = 0; out[2] = g.threads; out[3] = g.stages | ((uint32_t)g.kernel << 16); out[4] = g.blocks_per_sm; out[5] = g.tile_px;
     out[6] = (uint32_t)clip_smem_bytes(g.threads, g.bpp, g.stages, g.regs) | ((uint32_t)g.regs << 24); out[7] = clip_active_warps(g);
     return DIPSB_OK;
 }
@@ -417,8 +424,10 @@ extern "C" int32_t dipsb_plan_query(uint32_t width, uint32_t height, int32_t for
 extern "C" int32_t dipsb_set_kernel(dipsb_ctx* c, int32_t kernel) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
-    if (kernel < 0 || kernel > 1) return fail(c, DIPSB_ERR_INVALID, "set_kernel: %d is not 0 (clip_kernel) or 1 (clip_kernel_ws)", kernel);
-    if (kernel == c->g.kernel) return DIPSB_OK;
+    if (kernel < -1 || kernel > 1) return fail(c, DIPSB_ERR_INVALID, "set_kernel: %d is not -1 (automatic), 0 (clip_kernel) or 1 (clip_kernel_ws)", kernel);
+    const int requested = kernel;
+    kernel = pick_kernel(requested, c->tune_stages, c->tune_regs);
+    if (kernel == c->g.kernel) { c->tune_kernel = requested; return DIPSB_OK; }
     if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_kernel: only on a fresh or reset context");
     CK(c, cudaStreamSynchronize(c->stream));
     Geometry g = c->g;
@@ -428,7 +437,7 @@ extern "C" int32_t dipsb_set_kernel(dipsb_ctx* c, int32_t kernel) {
     cudaFree(c->acc); c->acc = nullptr;
     cudaFree(c->planar); c->planar = nullptr;
     c->g = g;
-    c->tune_kernel = kernel;
+    c->tune_kernel = requested;
     c->state_valid = false;
     return alloc_planes(c);
 }

@@ -202,7 +202,8 @@ int32_t dipsb_clip_kernel_time(dipsb_ctx *ctx, double *total_ms, uint64_t *launc
  * computes nothing; *ms = mean kernel time over `reps` launches.  Gives the bandwidth ceiling of the access pattern. */
 int32_t dipsb_stream_probe(dipsb_ctx *ctx, const void *d_frames, uint64_t n_frames, uint64_t frame_stride_bytes,
                            uint32_t reps, float *ms);
-/* which clip kernel runs the batch path: 0 = clip_kernel (thread 0 of each block issues the TMA copies), 1 = clip_kernel_ws
+/* which clip kernel runs the batch path: -1 = automatic (default: clip_kernel_ws whenever the tuning allows it),
+ * 0 = clip_kernel (thread 0 of each block issues the TMA copies; any stage count / register variant), 1 = clip_kernel_ws
  * (dedicated producer warp, frame loop unrolled over the pipeline stages; 64 registers, 3 or 4 stages).  Same results. */
 int32_t dipsb_set_kernel(dipsb_ctx *ctx, int32_t kernel);
 /* host-only: the plan (same layout as dipsb_last_plan, [7] = active warps per block) the library would choose for a

@@ -14,7 +14,7 @@ int main(void) {
     dipsb_default_config(&cfg);
     if (cfg.struct_size != sizeof cfg) return 3;
     if (dipsb_plan_query(1920, 1080, DIPSB_FMT_RGB8, 148, plan) != DIPSB_OK) return 4;
-    printf("plan: %u tiles x %u px, %u threads, %u stages\n", plan[0], plan[5], plan[2], plan[3]);
+    printf("plan: %u tiles x %u px, %u threads, %u stages\n", plan[0], plan[5], plan[2], plan[3] & 0xFFFF);
     cfg.width = 64; cfg.height = 48; cfg.format = DIPSB_FMT_RGBX8;
     int32_t rc = dipsb_create(&cfg, &ctx);
     if (rc == DIPSB_OK) {

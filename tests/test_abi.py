@@ -83,7 +83,8 @@ def test_planner_fills_the_sms_evenly():
     for (w, h, fmt) in [(1920, 1080, 0), (3840, 2160, 1), (7680, 4320, 0), (640, 480, 0), (1, 1, 0), (37, 5, 0), (8192, 8192, 1)]:
         out = (ctypes.c_uint32 * 8)()
         assert L.dipsb_plan_query(w, h, fmt, 148, ctypes.byref(out)) == 0
-        tiles, threads, stages, occ, tile_px = out[0], out[2], out[3], out[4], out[5]
+        tiles, threads, stages, occ, tile_px = out[0], out[2], out[3] & 0xFFFF, out[4], out[5]
+        threads += 32 * (out[3] >> 16)             # clip_kernel_ws adds a producer warp to the block
         smem, regs = out[6] & 0xFFFFFF, out[6] >> 24
         npx = w * h
         assert threads % 32 == 0 and 32 <= threads <= 1024 and tile_px % 16 == 0 and tile_px <= 16 * threads
