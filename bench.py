@@ -129,20 +129,29 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+def host_cores() -> int:
+    """threads the CPU arm uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1; the thread count
+    is therefore passed to the oracle explicitly)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_throughput(wl, sample_frames: int, clip_host=None, budget_s: float = 20.0):
     """The oracle (C port of the reference's shader arithmetic) on the host cores: frames/s on a bounded sample."""
     import numpy as np
     from oracle import oracle as O
     desc, w, h, fmt, mode, tau, _ = wl
-    cores = O.num_threads()
+    cores = host_cores()
     if clip_host is None:
         clip_host = O.synth_clip(sample_frames, w, h, fmt, seed=SEED, profile=O.SYNTH_SCENE)
     clip_host = np.ascontiguousarray(clip_host[:sample_frames])
-    O.run_clip(clip_host[: min(8, sample_frames)], fmt, mode, tau)        # warm the threads and caches
+    O.run_clip(clip_host[: min(8, sample_frames)], fmt, mode, tau, nthreads=cores)        # warm the threads and caches
     t = time.perf_counter()
     reps = 0
     while True:
-        O.run_clip(clip_host, fmt, mode, tau)
+        O.run_clip(clip_host, fmt, mode, tau, nthreads=cores)
         reps += 1
         dt = time.perf_counter() - t
         if dt > budget_s / 2 or reps >= 20:
@@ -160,15 +169,15 @@ def reference_arm(args, wl, rank, out):
     desc, w, h, fmt, mode, tau, frames = wl
     fb = w * h * O.bpp(fmt)
     sample = max(8, min(frames, int(1.5e9 // fb)))          # ~1.5 GB of frames per step
-    clip = O.synth_clip(sample, w, h, fmt, seed=SEED, profile=O.SYNTH_SCENE)
-    cores = O.num_threads()
+    cores = host_cores()
+    clip = O.synth_clip(sample, w, h, fmt, seed=SEED, profile=O.SYNTH_SCENE, nthreads=cores)
     for _ in range(max(1, min(args.warmup, 2))):
-        O.run_clip(clip[: max(8, sample // 8)], fmt, mode, tau)
+        O.run_clip(clip[: max(8, sample // 8)], fmt, mode, tau, nthreads=cores)
     steps = max(1, args.steps)
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        O.run_clip(clip, fmt, mode, tau)
+        O.run_clip(clip, fmt, mode, tau, nthreads=cores)
         done += 1
         if time.perf_counter() - t0 > 120 and done >= 3:      # keep the whole run within a few minutes
             break
