@@ -375,7 +375,7 @@ def main():
         def e2e_step():
             ctx.reset()
             sharding.run_sharded(hengine, mode, t0_frame, rank, world, dist if world > 1 else None)
-            ctx._ck(ctx._lib.dipsb_get_accumulators(ctx._h, h_sum.data_ptr(), h_cnt.data_ptr()))   # D2H of the maps
+            ctx.get_accumulators_into(h_sum.data_ptr(), h_cnt.data_ptr())                           # D2H of the maps
             return ctx.get_scalars(t0_frame, e2e_frames)                                            # D2H of the scalars
 
         e2e_step()

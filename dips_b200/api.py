@@ -230,6 +230,10 @@ class Context:
         self._ck(self._lib.dipsb_get_accumulators(self._h, _host_ptr(s), _host_ptr(c)))
         return s, c
 
+    def get_accumulators_into(self, host_sum: int, host_cnt: int) -> None:
+        """same, into caller-owned host memory given as raw addresses (e.g. pinned torch tensors' data_ptr())"""
+        self._ck(self._lib.dipsb_get_accumulators(self._h, host_sum, host_cnt))
+
     def set_accumulators(self, acc_sum: np.ndarray, acc_cnt: np.ndarray) -> None:
         s = np.ascontiguousarray(acc_sum, dtype=np.uint32)
         c = np.ascontiguousarray(acc_cnt, dtype=np.uint32)

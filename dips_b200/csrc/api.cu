@@ -101,12 +101,13 @@ static int32_t ensure_i2_scratch(dipsb_ctx* c);
 static int32_t filtered_plane(dipsb_ctx* c, const uint8_t* d_frame, int format, uint16_t* out);
 
 // ---- planning ------------------------------------------------------------------------------------------------------
-// Measured on B200 (profiles/r01_sweeps.md): the clip kernel runs fastest with ONE large block per SM -- every SM streams
-// one contiguous 40-56 KB slice of each frame through a 3-4 deep TMA ring, all SMs advance frame by frame together -- and
-// is co-limited by HBM and the integer ALU pipe, so every SM must get the same number of pixels.  Plan: tile_px =
-// npx / (num_sms * waves) rounded up to 16 pixels with the fewest waves that fit a block (<= 896 threads at 72 registers,
-// <= 1024 at 64); deepest pipeline (<= 4 stages) that fits in shared memory.  Frames too small to give every SM a
-// 2048-pixel tile keep 2048-pixel tiles, run several blocks per SM and are split into frame segments instead.
+// Measured on B200 (profiles/r01_sweeps.md): the clip kernels run fastest with ONE large block per SM -- every
+// SM streams one contiguous 40-56 KB slice of each frame through a 3-4 deep TMA ring -- and they are co-limited by HBM and
+// by instruction issue, so every SM must get the same number of pixels.  Plan: tile_px = npx / (num_sms * waves) rounded
+// up to 16 pixels, with the fewest waves that fit a block (clip_kernel_ws: 992 consumer threads at 64 registers;
+// clip_kernel: 896 threads at 72 registers or 1024 at 64); 4 pipeline stages unless the ring would exceed 200 KB.  Frames
+// too small to give every SM a 2048-pixel tile keep 2048-pixel tiles, run several blocks per SM and are split into frame
+// segments instead (plan_segments).
 static bool plan_geometry(Geometry& g, uint32_t force_stages, uint32_t force_tile_px, uint32_t force_regs = 0, int kernel = 0) {
     const uint64_t min_tile = std::min<uint64_t>(2048, (g.npx + 15) / 16 * 16);
     if (kernel == 1) {   // warp-specialised variant: 64 registers, 16 px/thread, block = consumers + one producer warp
