@@ -264,7 +264,7 @@ def main():
     if args.stages or args.tile_px or args.segments or args.regs:
         ctx.set_tuning(args.stages, args.tile_px, args.segments, args.regs)
     ctx.set_stream(stream.cuda_stream)
-    engine = sharding.GpuShardEngine(ctx, clip, torch)
+    engine = sharding.GpuShardEngine(ctx, clip, torch, total_frames=world * frames)
 
     phase_events = []
 
@@ -278,6 +278,7 @@ def main():
         if ev: ev[2].record(stream)
         if world > 1:
             dist.all_reduce(engine.acc_tensor(), op=dist.ReduceOp.SUM)
+            engine.after_reduce()
         if ev:
             ev[3].record(stream)
             phase_events.append(ev)
@@ -370,7 +371,7 @@ def main():
             def run(self, first_frame_index):
                 ctx.run_clip_host(host.data_ptr(), e2e_frames, fb, first_frame_index)
 
-        hengine = HostEngine(ctx, clip, torch)
+        hengine = HostEngine(ctx, clip, torch, total_frames=world * e2e_frames)
 
         def e2e_step():
             ctx.reset()

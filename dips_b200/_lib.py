@@ -52,6 +52,8 @@ SYMBOLS = {
     "dipsb_get_accumulators": (_i32, [_vp, _vp, _vp]),
     "dipsb_set_accumulators": (_i32, [_vp, _vp, _vp]),
     "dipsb_accumulators_device": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
+    "dipsb_pack_accumulators_device": (_i32, [_vp, _u64, C.POINTER(_vp), C.POINTER(_u64)]),
+    "dipsb_unpack_accumulators_device": (_i32, [_vp]),
     "dipsb_get_scalars": (_i32, [_vp, _u64, _u64, _vp, _vp]),
     "dipsb_get_intensity_map": (_i32, [_vp, _u64, _vp]),
     "dipsb_get_frame_means": (_i32, [_vp, _u64, _u64, _vp]),

@@ -247,6 +247,15 @@ class Context:
         self._ck(self._lib.dipsb_accumulators_device(self._h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
+    def pack_accumulators_device(self, total_frames: int):
+        """(device address, n_words) of the packed exchange buffer: all-reduce it as int32, then unpack_accumulators_device()"""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._lib.dipsb_pack_accumulators_device(self._h, total_frames, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def unpack_accumulators_device(self) -> None:
+        self._ck(self._lib.dipsb_unpack_accumulators_device(self._h))
+
     def get_scalars(self, first: int, n: int):
         sad = np.empty(n, np.uint64)
         cnt = np.empty(n, np.uint64)

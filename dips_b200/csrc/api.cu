@@ -38,6 +38,8 @@ struct dipsb_ctx {
     uint64_t partial_cap = 0;                  // in u32 words
     uint64_t frames_processed = 0;
     uint64_t stream_index = 0;                 // logical index of the next pushed frame
+    uint32_t* xchg = nullptr;                  // packed accumulators for the cross-GPU sum (dipsb_pack_accumulators_device)
+    int xchg_layout = 0, xchg_sum_bits = 0;
     uint16_t* i2_scratch = nullptr;            // spatial window > 1: 5 planes of npx u16 (raw + up to 4 filtered)
     uint16_t* ring = nullptr;                  // ring flavours: 4 (dips) or 2 (dips_alt) u16 I2 planes of npx
     uint32_t ring_seen = 0, ring_index = 0;    // frames pushed since the last (re)start, next slot to overwrite
@@ -220,7 +222,7 @@ static void free_all(dipsb_ctx* c) {
         if (c->d_chunk[k]) cudaFree(c->d_chunk[k]);
     }
     cudaFree(c->acc); cudaFree(c->planar); cudaFree(c->d_sad); cudaFree(c->d_cnt); cudaFree(c->partials);
-    cudaFree(c->d_frame); cudaFree(c->d_rgba); cudaFree(c->ring); cudaFree(c->i2_scratch);
+    cudaFree(c->d_frame); cudaFree(c->d_rgba); cudaFree(c->ring); cudaFree(c->i2_scratch); cudaFree(c->xchg);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_stat) cudaFreeHost(c->h_stat);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -404,6 +406,7 @@ extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile
     for (int k = 0; k < 2; ++k) { cudaFree(c->state[k]); c->state[k] = nullptr; }
     cudaFree(c->acc); c->acc = nullptr;
     cudaFree(c->planar); c->planar = nullptr;
+    cudaFree(c->xchg); c->xchg = nullptr;
     c->g = g;
     c->tune_stages = stages; c->tune_tile_px = tile_px; c->tune_regs = regs;
     c->state_valid = false;
@@ -437,6 +440,7 @@ extern "C" int32_t dipsb_set_kernel(dipsb_ctx* c, int32_t kernel) {
     for (int k = 0; k < 2; ++k) { cudaFree(c->state[k]); c->state[k] = nullptr; }
     cudaFree(c->acc); c->acc = nullptr;
     cudaFree(c->planar); c->planar = nullptr;
+    cudaFree(c->xchg); c->xchg = nullptr;
     c->g = g;
     c->tune_kernel = requested;
     c->state_valid = false;
@@ -919,6 +923,40 @@ extern "C" int32_t dipsb_accumulators_device(dipsb_ctx* c, void** d_acc, uint64_
     if (!c || !d_acc || !n_elems) return DIPSB_ERR_INVALID;
     *d_acc = c->acc;
     *n_elems = c->g.n_elems;
+    return DIPSB_OK;
+}
+
+static int bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+
+extern "C" int32_t dipsb_pack_accumulators_device(dipsb_ctx* c, uint64_t total_frames, void** d_packed, uint64_t* n_words) {
+    if (!c || !d_packed || !n_words || total_frames == 0) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const Geometry& g = c->g;
+    // after the sum over all ranks: acc_sum <= 510*total_frames, acc_cnt <= total_frames (every frame counts at most once)
+    const int sum_bits = bit_length(510ull * total_frames), cnt_bits = bit_length(total_frames);
+    int layout;
+    if (sum_bits + cnt_bits <= 32) layout = 1;
+    else if (total_frames < 65536 && sum_bits <= 32) layout = 2;
+    else {   // totals too large for a packed format: exchange the planes themselves
+        c->xchg_layout = 0;
+        *d_packed = c->acc;
+        *n_words = 2 * g.n_elems;
+        return DIPSB_OK;
+    }
+    if (!c->xchg) CK(c, cudaMalloc(&c->xchg, (g.n_elems + g.n_elems / 2) * sizeof(uint32_t)));
+    CK(c, launch_pack_acc(g, c->acc, c->xchg, layout, sum_bits, c->stream));
+    c->xchg_layout = layout; c->xchg_sum_bits = sum_bits;
+    *d_packed = c->xchg;
+    *n_words = layout == 1 ? g.n_elems : g.n_elems + g.n_elems / 2;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_unpack_accumulators_device(dipsb_ctx* c) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (c->xchg_layout == 0) return DIPSB_OK;   // the planes were exchanged in place
+    CK(c, launch_unpack_acc(c->g, c->xchg, c->acc, c->xchg_layout, c->xchg_sum_bits, c->stream));
+    c->xchg_layout = 0;
     return DIPSB_OK;
 }
 

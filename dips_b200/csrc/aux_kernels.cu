@@ -95,6 +95,44 @@ __global__ void permute_kernel(const uint32_t* __restrict__ planar, uint32_t* __
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
         internal[tile_order_index(p, tile_px, threads, bpp, groups)] = planar[p];
 }
+// Accumulator exchange format for the cross-GPU sum: fewer bytes over NVLink than the two u32 planes.
+//   layout 1: one u32 per element, sum | count << sum_bits (valid while both totals fit their fields: no carry can cross);
+//   layout 2: sum plane as is + counts as u16 pairs packed two per u32 (valid while the total count < 65536).
+// Element-wise int32 addition of packed buffers == addition of the fields.
+__global__ void pack_acc_kernel(const uint32_t* __restrict__ acc, uint64_t n_elems, uint32_t* __restrict__ out, int layout,
+                                int sum_bits) {
+    const uint32_t* sum = acc;
+    const uint32_t* cnt = acc + n_elems;
+    if (layout == 1) {
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_elems; i += (uint64_t)gridDim.x * blockDim.x)
+            out[i] = sum[i] | (cnt[i] << sum_bits);
+    } else {
+        const uint64_t half = n_elems / 2;   // n_elems is a multiple of 512
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_elems + half; i += (uint64_t)gridDim.x * blockDim.x)
+            out[i] = i < n_elems ? sum[i] : (cnt[2 * (i - n_elems)] | (cnt[2 * (i - n_elems) + 1] << 16));
+    }
+}
+__global__ void unpack_acc_kernel(const uint32_t* __restrict__ in, uint64_t n_elems, uint32_t* __restrict__ acc, int layout,
+                                  int sum_bits) {
+    uint32_t* sum = acc;
+    uint32_t* cnt = acc + n_elems;
+    if (layout == 1) {
+        const uint32_t mask = (sum_bits >= 32) ? 0xFFFFFFFFu : ((1u << sum_bits) - 1u);
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_elems; i += (uint64_t)gridDim.x * blockDim.x) {
+            const uint32_t w = in[i];
+            sum[i] = w & mask;
+            cnt[i] = w >> sum_bits;
+        }
+    } else {
+        const uint64_t half = n_elems / 2;
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_elems + half; i += (uint64_t)gridDim.x * blockDim.x) {
+            const uint32_t w = in[i];
+            if (i < n_elems) sum[i] = w;
+            else { cnt[2 * (i - n_elems)] = w & 0xFFFFu; cnt[2 * (i - n_elems) + 1] = w >> 16; }
+        }
+    }
+}
+
 __global__ void intensity_map_kernel(const uint32_t* __restrict__ internal, float* __restrict__ out, uint64_t npx,
                                      uint32_t tile_px, uint32_t threads, int bpp, int groups, double inv_den) {
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
@@ -371,6 +409,16 @@ cudaError_t launch_unpermute(const Geometry& g, const uint32_t* internal, uint32
 }
 cudaError_t launch_permute(const Geometry& g, const uint32_t* planar, uint32_t* internal, cudaStream_t s) {
     permute_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(planar, internal, g.npx, g.tile_px, g.threads, g.bpp, g.groups);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_acc(const Geometry& g, const uint32_t* acc, uint32_t* out, int layout, int sum_bits, cudaStream_t s) {
+    pack_acc_kernel<<<grid_for(g.n_elems, g), kThreads, 0, s>>>(acc, g.n_elems, out, layout, sum_bits);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack_acc(const Geometry& g, const uint32_t* in, uint32_t* acc, int layout, int sum_bits, cudaStream_t s) {
+    unpack_acc_kernel<<<grid_for(g.n_elems, g), kThreads, 0, s>>>(in, g.n_elems, acc, layout, sum_bits);
     count_launch();
     return cudaGetLastError();
 }

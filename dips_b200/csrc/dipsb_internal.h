@@ -124,6 +124,9 @@ cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uin
                                     uint8_t* out_rgba, cudaStream_t s);
 cudaError_t launch_synth(uint8_t* dst, uint64_t first_frame, uint64_t n_frames, uint32_t w, uint32_t h, int bpp,
                          uint64_t seed, int profile, cudaStream_t s);
+// accumulator exchange format for the cross-GPU sum (see aux_kernels.cu)
+cudaError_t launch_pack_acc(const Geometry& g, const uint32_t* acc, uint32_t* out, int layout, int sum_bits, cudaStream_t s);
+cudaError_t launch_unpack_acc(const Geometry& g, const uint32_t* in, uint32_t* acc, int layout, int sum_bits, cudaStream_t s);
 cudaError_t launch_intensity_map(const Geometry& g, const uint32_t* acc_internal, uint64_t n_eff, float* out,
                                  cudaStream_t s);
 

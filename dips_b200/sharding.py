@@ -15,7 +15,11 @@ Per-frame scalars are disjoint by shard and stay on their rank.
     frame_buffer() -> tensor     scratch tensor of one frame (receive buffer)
     prime(tensor) -> None        state plane := I2(frame)
     run(first_frame_index) -> None   process the local shard
-    acc_tensor() -> tensor       int32 view of the accumulators, reduced in place
+    acc_tensor() -> tensor       int32 tensor whose element-wise sum over the ranks is the combined accumulators
+optional:
+    after_reduce() -> None       called after the all-reduce (unpacks an exchange format into the accumulators)
+    state_tensor() -> tensor     the reference plane itself (as bytes); when present it is broadcast instead of raw frame 0
+    mark_primed() -> None        the state plane was filled by the broadcast
 """
 from __future__ import annotations
 
@@ -44,7 +48,14 @@ def exchange_reference(engine: ShardEngine, mode: int, rank: int, world: int, di
     """Give every rank what it needs before its first frame (no-op for a single rank)."""
     if world == 1:
         return
-    if mode == MODE_OVERALL:
+    if mode == MODE_OVERALL and hasattr(engine, "state_tensor"):
+        # rank 0 builds the reference plane and broadcasts it (2 B/px instead of the raw frame's 3-4 B/px)
+        if rank == 0:
+            engine.prime(engine.first_frame())
+        dist.broadcast(engine.state_tensor(), src=0, group=group)
+        if rank > 0:
+            engine.mark_primed()
+    elif mode == MODE_OVERALL:
         buf = engine.frame_buffer()
         if rank == 0:
             buf.copy_(engine.first_frame())
@@ -70,6 +81,8 @@ def run_sharded(engine: ShardEngine, mode: int, first_frame_index: int, rank: in
     engine.run(first_frame_index)
     if world > 1:
         dist.all_reduce(engine.acc_tensor(), op=dist.ReduceOp.SUM, group=group)
+        if hasattr(engine, "after_reduce"):
+            engine.after_reduce()
 
 
 class _DeviceBuffer:
@@ -82,10 +95,13 @@ class _DeviceBuffer:
 class GpuShardEngine:
     """ShardEngine over a dips_b200.Context and a device-resident shard (a torch uint8 tensor [n, frame_bytes])."""
 
-    def __init__(self, ctx, frames, torch):
+    def __init__(self, ctx, frames, torch, total_frames=None):
+        """total_frames: frames of the whole clip over all ranks -- enables the packed accumulator exchange
+        (dipsb_pack_accumulators_device); None exchanges the two u32 planes as they are."""
         self.ctx, self.frames, self.torch = ctx, frames, torch
+        self.total_frames = total_frames
         self._buf = None
-        self._acc = None
+        self._views = {}
 
     def first_frame(self):
         return self.frames[0]
@@ -104,8 +120,25 @@ class GpuShardEngine:
     def run(self, first_frame_index: int) -> None:
         self.ctx.run_clip_device(self.frames.data_ptr(), self.frames.shape[0], self.frames.stride(0), first_frame_index)
 
+    def _view(self, ptr, n_items, typestr):
+        key = (ptr, n_items, typestr)
+        if key not in self._views:
+            self._views[key] = self.torch.as_tensor(_DeviceBuffer(ptr, n_items, typestr), device=self.frames.device)
+        return self._views[key]
+
     def acc_tensor(self):
-        if self._acc is None:
+        if self.total_frames is None:
             ptr, n = self.ctx.accumulators_device()
-            self._acc = self.torch.as_tensor(_DeviceBuffer(ptr, 2 * n, "<i4"), device=self.frames.device)
-        return self._acc
+            return self._view(ptr, 2 * n, "<i4")
+        ptr, n_words = self.ctx.pack_accumulators_device(self.total_frames)
+        return self._view(ptr, n_words, "<i4")
+
+    def after_reduce(self) -> None:
+        if self.total_frames is not None:
+            self.ctx.unpack_accumulators_device()
+
+    def state_tensor(self):
+        return self._view(self.ctx.state_plane_device(), 2 * self.ctx.npx, "|u1")   # u16 plane as bytes (any backend moves bytes)
+
+    def mark_primed(self) -> None:
+        self.ctx.mark_state_valid(True)

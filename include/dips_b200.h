@@ -178,6 +178,15 @@ int32_t dipsb_set_accumulators(dipsb_ctx *ctx, const uint32_t *acc_sum, const ui
  * element-wise NCCL sum across ranks is exact).  Finalises pending work first.
  */
 int32_t dipsb_accumulators_device(dipsb_ctx *ctx, void **d_acc, uint64_t *n_elems);
+/*
+ * The same for a cheaper cross-GPU sum: packs the accumulators of this context into an exchange buffer whose element-wise
+ * int32 sum over all ranks equals the packed sum of the fields -- `total_frames` = number of frames of the WHOLE clip (all
+ * ranks), which bounds the totals: one u32 per element (sum | count << bits) while both fit 32 bits (<= 2056 frames),
+ * else the sum plane + counts as u16 pairs (6 bytes per element, < 65536 frames), else the planes themselves.  All-reduce
+ * (sum, int32) the n_words returned, then call dipsb_unpack_accumulators_device on every rank.
+ */
+int32_t dipsb_pack_accumulators_device(dipsb_ctx *ctx, uint64_t total_frames, void **d_packed, uint64_t *n_words);
+int32_t dipsb_unpack_accumulators_device(dipsb_ctx *ctx);
 /* per-frame scalars of logical frames first..first+n-1; either pointer may be NULL. */
 int32_t dipsb_get_scalars(dipsb_ctx *ctx, uint64_t first, uint64_t n, uint64_t *sad, uint64_t *cnt);
 /* X6 float outputs: acc_sum/(510*n_eff) per pixel, sad[t]/(510*W*H) per frame */

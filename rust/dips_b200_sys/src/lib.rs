@@ -86,6 +86,8 @@ extern "C" {
     pub fn dipsb_get_accumulators(ctx: *mut dipsb_ctx, acc_sum: *mut u32, acc_cnt: *mut u32) -> i32;
     pub fn dipsb_set_accumulators(ctx: *mut dipsb_ctx, acc_sum: *const u32, acc_cnt: *const u32) -> i32;
     pub fn dipsb_accumulators_device(ctx: *mut dipsb_ctx, d_acc: *mut *mut c_void, n_elems: *mut u64) -> i32;
+    pub fn dipsb_pack_accumulators_device(ctx: *mut dipsb_ctx, total_frames: u64, d_packed: *mut *mut c_void, n_words: *mut u64) -> i32;
+    pub fn dipsb_unpack_accumulators_device(ctx: *mut dipsb_ctx) -> i32;
     pub fn dipsb_get_scalars(ctx: *mut dipsb_ctx, first: u64, n: u64, sad: *mut u64, cnt: *mut u64) -> i32;
     pub fn dipsb_get_intensity_map(ctx: *mut dipsb_ctx, n_eff: u64, out: *mut f32) -> i32;
     pub fn dipsb_get_frame_means(ctx: *mut dipsb_ctx, first: u64, n: u64, out: *mut f32) -> i32;

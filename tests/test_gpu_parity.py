@@ -454,3 +454,38 @@ def test_ws_kernel_baseline_geometries(torch_cuda, oracle, w, h, fmt, n, mode):
         assert ctx.last_plan()["kernel"] == 1
     assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)
     assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt) and np.array_equal(state, want.state)
+
+
+@pytest.mark.parametrize("total_frames,expect_words", [(40, 1.0), (3000, 1.5), (70000, 2.0)])
+def test_packed_accumulator_exchange(torch_cuda, oracle, total_frames, expect_words):
+    """dipsb_pack_accumulators_device: summing the packed buffers of two shards as int32 and unpacking equals the
+    combined accumulators, for the 4-byte, 6-byte and unpacked exchange formats."""
+    import dips_b200
+    from dips_b200 import sharding
+    torch = torch_cuda
+    w, h, n, fmt, tau = 256, 120, 40, 0, 12
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    want = oracle.run_clip(clip, fmt, 0, tau)
+    dev = to_device(torch, clip)
+    ctxs = [dips_b200.Context(w, h, fmt, 0, tau) for _ in range(2)]
+    try:
+        packed = []
+        for r, ctx in enumerate(ctxs):
+            t0, t1 = sharding.shard_range(r, 2, n)
+            ctx.prime_device(dev[0].data_ptr())
+            ctx.run_clip_device(dev[t0].data_ptr(), t1 - t0, clip.shape[1], t0)
+            ptr, nw = ctx.pack_accumulators_device(total_frames)
+            _, ne = ctx.accumulators_device()
+            assert nw == int(expect_words * ne)
+            ctx.synchronize()
+            packed.append(torch.as_tensor(sharding._DeviceBuffer(ptr, nw, "<i4"), device="cuda"))
+        total = packed[0] + packed[1]                      # what the all-reduce computes
+        for ctx, buf in zip(ctxs, packed):
+            buf.copy_(total)
+            torch.cuda.synchronize()
+            ctx.unpack_accumulators_device()
+            s, c = ctx.get_accumulators()
+            assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+    finally:
+        for ctx in ctxs:
+            ctx.close()

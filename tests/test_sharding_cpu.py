@@ -33,6 +33,9 @@ class OracleEngine:
         self.O, self.frames, self.fmt, self.mode, self.tau = O, frames, fmt, mode, tau
         npx = frames.shape[1] // O.bpp(fmt)
         self.acc = np.zeros(2 * npx, np.int32)
+        self._state_buf = np.zeros(npx, np.int16)
+        self.primed_by_broadcast = False
+        self.reduced = False
         self.state = None
         self.sad = self.cnt = None
 
@@ -47,6 +50,14 @@ class OracleEngine:
 
     def prime(self, frame):
         self.state = self.O.i2_plane(frame.numpy(), self.fmt)
+        self._state_buf[:] = self.state.view(np.int16)
+
+    def state_tensor(self):
+        return torch.from_numpy(self._state_buf.view(np.uint8))
+
+    def mark_primed(self):
+        self.state = self._state_buf.view(np.uint16).copy()
+        self.primed_by_broadcast = True
 
     def run(self, first_frame_index):
         r = self.O.run_clip(self.frames, self.fmt, self.mode, self.tau, state=self.state)
@@ -57,6 +68,9 @@ class OracleEngine:
 
     def acc_tensor(self):
         return torch.from_numpy(self.acc)
+
+    def after_reduce(self):
+        self.reduced = True
 
 
 def _worker(rank, world, port, mode, tmpdir):
@@ -75,6 +89,7 @@ def _worker(rank, world, port, mode, tmpdir):
         assert np.array_equal(eng.acc[:npx].view(np.uint32), whole.acc_sum), "acc_sum differs after all-reduce"
         assert np.array_equal(eng.acc[npx:].view(np.uint32), whole.acc_cnt), "acc_cnt differs after all-reduce"
         assert np.array_equal(eng.sad, whole.sad[t0:t1]) and np.array_equal(eng.cnt, whole.cnt[t0:t1])
+        assert eng.reduced and eng.primed_by_broadcast == (mode == sharding.MODE_OVERALL and rank > 0)
         open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
