@@ -489,3 +489,67 @@ def test_packed_accumulator_exchange(torch_cuda, oracle, total_frames, expect_wo
     finally:
         for ctx in ctxs:
             ctx.close()
+
+
+def test_threshold_change_between_chunks_and_thread_migration(torch_cuda, oracle):
+    """tau may change between calls (accumulators are kept), and a context may be driven from another thread than the one
+    that created it (the reference moves its ComputeState to a GStreamer streaming thread, frame_extractor.rs:76, :232)."""
+    import threading
+    import dips_b200
+    torch = torch_cuda
+    w, h, n, fmt = 192, 100, 30, 0
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    a = oracle.run_clip(clip[:12], fmt, 1, 5)
+    b = oracle.run_clip(clip[12:], fmt, 1, 40, state=a.state, acc_sum=a.acc_sum, acc_cnt=a.acc_cnt)
+    dev = to_device(torch, clip)
+    ctx = dips_b200.Context(w, h, fmt, 1, 5)
+    errors = []
+
+    def second_half():
+        try:
+            ctx.set_threshold(40)
+            ctx.run_clip_device(dev[12].data_ptr(), n - 12, clip.shape[1], 12)
+            ctx.synchronize()
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+
+    try:
+        ctx.run_clip_device(dev.data_ptr(), 12, clip.shape[1], 0)
+        t = threading.Thread(target=second_half)
+        t.start()
+        t.join()
+        assert not errors, errors
+        s, c = ctx.get_accumulators()
+        sad, cnt = ctx.get_scalars(0, n)
+    finally:
+        ctx.close()
+    assert np.array_equal(s, b.acc_sum) and np.array_equal(c, b.acc_cnt)
+    assert np.array_equal(sad, np.concatenate([a.sad, b.sad])) and np.array_equal(cnt, np.concatenate([a.cnt, b.cnt]))
+
+
+def test_two_contexts_on_two_streams(torch_cuda, oracle):
+    """independent contexts on their own streams do not interfere"""
+    import dips_b200
+    torch = torch_cuda
+    w, h, n = 320, 180, 50
+    clips = [oracle.synth_clip(n, w, h, f, profile=oracle.SYNTH_SCENE, seed=5 + f) for f in (0, 1)]
+    devs = [to_device(torch, c) for c in clips]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ctxs = [dips_b200.Context(w, h, f, m, 16) for f, m in ((0, 0), (1, 1))]
+    try:
+        for ctx, st in zip(ctxs, streams):
+            ctx.set_stream(st.cuda_stream)
+        for rep in range(3):
+            for ctx, dev in zip(ctxs, devs):
+                ctx.reset()
+                ctx.run_clip_device(dev.data_ptr(), n)
+        for ctx, clip, (f, m) in zip(ctxs, clips, ((0, 0), (1, 1))):
+            ctx.synchronize()
+            want = oracle.run_clip(clip, f, m, 16)
+            s, c = ctx.get_accumulators()
+            sad, cnt = ctx.get_scalars(0, n)
+            assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+            assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)
+    finally:
+        for ctx in ctxs:
+            ctx.close()
