@@ -553,3 +553,33 @@ def test_two_contexts_on_two_streams(torch_cuda, oracle):
     finally:
         for ctx in ctxs:
             ctx.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_run_clip_host_multi_chunk(torch_cuda, oracle, mode):
+    """dipsb_run_clip_host splits long clips into <=256 MB chunks that are uploaded on a copy stream while the previous
+    chunk is processed: 100 frames of 1080p RGB8 = 622 MB = 3 chunks; results must equal the one-shot oracle run."""
+    import dips_b200
+    torch = torch_cuda
+    w, h, n, fmt = 1920, 1080, 100, 0
+    fb = w * h * 3
+    dev = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
+    dips_b200.synth_fill_device(0, dev.data_ptr(), 0, n, w, h, fmt, 0x44695073, dips_b200.SYNTH_SCENE,
+                                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = dev.cpu().numpy().reshape(n, fb)
+    del dev
+    want = oracle.run_clip(host, fmt, mode, 32)
+    pinned = torch.from_numpy(host).pin_memory()
+    for src in ("pageable", "pinned"):
+        with dips_b200.Context(w, h, fmt, mode, 32) as ctx:
+            if src == "pinned":
+                ctx.run_clip_host(pinned.data_ptr(), n, fb)
+            else:
+                ctx.run_clip_host(host)
+            ctx.synchronize()
+            s, c = ctx.get_accumulators()
+            sad, cnt = ctx.get_scalars(0, n)
+            assert ctx.frames_processed == n
+        assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt), src
+        assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt), src
