@@ -400,7 +400,7 @@ def main():
     # ---- streaming boundary (the reference's per-frame callback shape): RGBA8 frame in -> RGBA8 difference frame out ----
     stream_info = None
     if not args.no_e2e and world == 1:
-        sw, sh, sn = 1920, 1080, 60
+        sw, sh, sn = 1920, 1080, 120
         frames_rgba = np.empty((8, sw * sh * 4), np.uint8)
         tmp = torch.empty(8 * sw * sh * 4, dtype=torch.uint8, device=dev)
         dips_b200.synth_fill_device(local_rank, tmp.data_ptr(), 0, 8, sw, sh, dips_b200.FMT_RGBX8, SEED,
@@ -408,18 +408,30 @@ def main():
         torch.cuda.synchronize()
         frames_rgba[:] = tmp.cpu().numpy().reshape(8, -1)
         del tmp
-        stream_info = {"geometry": "1920x1080 RGBx8 in, RGBA8 difference frame out, per-frame call", "frames": sn}
-        for name in ("dipsb_push_frame", "dipsb_push_frame_pipelined"):
-            with dips_b200.Context(sw, sh, dips_b200.FMT_RGBX8, 0, tau, device=local_rank) as sctx:
-                fn = sctx.push_frame if name == "dipsb_push_frame" else sctx.push_frame_pipelined
-                for k in range(4):
-                    fn(frames_rgba[k % 8])
-                t0 = time.perf_counter()
-                for k in range(sn):
-                    fn(frames_rgba[k % 8])
-                if name != "dipsb_push_frame":
-                    sctx.flush_frame()
-                stream_info[name + "_fps"] = sn / (time.perf_counter() - t0)
+        stream_info = {"geometry": "1920x1080 RGBx8 in, RGBA8 difference frame out, per-frame call", "frames": sn,
+                       "buffers": "pageable = ordinary host memory (staged by a CPU memcpy each way); pinned = "
+                                  "dipsb_host_alloc buffers (copy engine reads/writes them directly)"}
+        pin_in = dips_b200.PinnedBuffer(8 * sw * sh * 4, device=local_rank)
+        pin_out = dips_b200.PinnedBuffer(2 * sw * sh * 4, device=local_rank)
+        pin_in.array[:] = frames_rgba.reshape(-1)
+        for kind in ("pageable", "pinned"):
+            src = frames_rgba if kind == "pageable" else pin_in.array.reshape(8, -1)
+            dst = (np.empty((2, sw * sh * 4), np.uint8) if kind == "pageable" else pin_out.array.reshape(2, -1))
+            dst[:] = 0
+            for name in ("dipsb_push_frame", "dipsb_push_frame_pipelined"):
+                with dips_b200.Context(sw, sh, dips_b200.FMT_RGBX8, 0, tau, device=local_rank) as sctx:
+                    fn = sctx.push_frame if name == "dipsb_push_frame" else sctx.push_frame_pipelined
+                    for k in range(4):
+                        fn(src[k % 8], out=dst[k & 1])
+                    t0 = time.perf_counter()
+                    for k in range(sn):
+                        fn(src[k % 8], out=dst[k & 1])
+                    if name != "dipsb_push_frame":
+                        sctx.flush_frame(out=dst[sn & 1])
+                    key = name + ("_fps" if kind == "pageable" else "_pinned_fps")
+                    stream_info[key] = sn / (time.perf_counter() - t0)
+        pin_in.close()
+        pin_out.close()
 
     # ---- CPU baseline (rank 0, N == 1 only) -----------------------------------------------------------------------
     cpu = None

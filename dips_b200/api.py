@@ -42,6 +42,38 @@ def synth_fill_device(device: int, d_dst: int, first_frame: int, n_frames: int, 
         raise DipsError(rc, _lib.load().dipsb_last_error(None).decode())
 
 
+class PinnedBuffer:
+    """A page-locked host buffer from dipsb_host_alloc, exposed as a numpy uint8 array (`.array`).  The frame calls
+    recognise it and skip their staging copy.  Free it with close() (or a `with` block) once no array view is in use."""
+
+    def __init__(self, nbytes: int, device: int = 0):
+        self._lib = _lib.load()
+        p = C.c_void_p()
+        rc = self._lib.dipsb_host_alloc(device, nbytes, C.byref(p))
+        if rc != 0:
+            raise DipsError(rc, self._lib.dipsb_last_error(None).decode())
+        self._p, self.nbytes = p, nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value))
+
+    def close(self) -> None:
+        if self._p is not None:
+            self.array = None
+            self._lib.dipsb_host_free(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _host_ptr(a: np.ndarray) -> int:
     if not a.flags["C_CONTIGUOUS"]:
         raise ValueError("array must be C-contiguous")
@@ -181,26 +213,36 @@ class Context:
         self._ck(self._lib.dipsb_run_clip_host(self._h, ptr, n, st, first_frame))
 
     # -- streaming --------------------------------------------------------------------------------------------
-    def push_frame(self, frame: np.ndarray, fmt: int | None = None, want_rgba: bool = True, stride: int | None = None):
-        """Returns (status, rgba or None, (frame_index, sad, count)).  status NOT_READY == passthrough frame."""
+    def _out_buffer(self, out):
+        if out is None:
+            return np.empty(self.npx * 4, np.uint8)
+        if out.dtype != np.uint8 or out.size < self.npx * 4 or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+            raise ValueError("out must be a writable C-contiguous uint8 array of width*height*4 bytes")
+        return out
+
+    def push_frame(self, frame: np.ndarray, fmt: int | None = None, want_rgba: bool = True, stride: int | None = None,
+                   out: np.ndarray | None = None):
+        """Returns (status, rgba or None, (frame_index, sad, count)).  status NOT_READY == passthrough frame.
+        `out`: caller-owned RGBA8 buffer to fill (a PinnedBuffer's array avoids the staging copies)."""
         fmt = self.fmt if fmt is None else fmt
         frame = np.ascontiguousarray(frame, dtype=np.uint8)
         stride = stride or self.width * bytes_per_pixel(fmt)
         if frame.size < stride * self.height:
             raise ValueError("frame smaller than height*stride")
-        out = np.empty(self.npx * 4, np.uint8) if want_rgba else None
+        out = self._out_buffer(out) if want_rgba else None
         st = _lib.FrameStats()
         rc = self._ck(self._lib.dipsb_push_frame(self._h, _host_ptr(frame), self.width, self.height, stride, fmt,
                                                  _host_ptr(out) if want_rgba else None, C.byref(st)))
         return rc, out, (int(st.frame_index), int(st.sad), int(st.count))
 
-    def push_frame_pipelined(self, frame: np.ndarray, fmt: int | None = None, stride: int | None = None):
+    def push_frame_pipelined(self, frame: np.ndarray, fmt: int | None = None, stride: int | None = None,
+                             out: np.ndarray | None = None):
         """Submit `frame`, get back the previous frame's result: (status, rgba or None, stats or None).
         status: NOT_READY (first call), 0 (difference frame of t-1), 2 (t-1 was a passed-through warm-up frame)."""
         fmt = self.fmt if fmt is None else fmt
         frame = np.ascontiguousarray(frame, dtype=np.uint8)
         stride = stride or self.width * bytes_per_pixel(fmt)
-        out = np.empty(self.npx * 4, np.uint8)
+        out = self._out_buffer(out)
         st = _lib.FrameStats()
         rc = self._ck(self._lib.dipsb_push_frame_pipelined(self._h, _host_ptr(frame), self.width, self.height, stride,
                                                            fmt, _host_ptr(out), C.byref(st)))
@@ -208,8 +250,8 @@ class Context:
             return rc, None, None
         return rc, out, (int(st.frame_index), int(st.sad), int(st.count))
 
-    def flush_frame(self):
-        out = np.empty(self.npx * 4, np.uint8)
+    def flush_frame(self, out: np.ndarray | None = None):
+        out = self._out_buffer(out)
         st = _lib.FrameStats()
         rc = self._ck(self._lib.dipsb_flush_frame(self._h, _host_ptr(out), C.byref(st)))
         if rc == NOT_READY:

@@ -54,8 +54,11 @@ struct dipsb_ctx {
         uint8_t* d_out = nullptr; uint8_t* h_out = nullptr; uint64_t* h_stat = nullptr;
         cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
         bool pending = false, want_rgba = false; int32_t status = 0; uint64_t idx = 0;
+        bool out_direct = false;               // the read-back already targets the caller's (pinned) buffer
+        bool out_deferred = false;             // the read-back is enqueued at collection time (pipelined, pinned caller)
     } slot[2];
     int next_slot = 0;
+    bool out_pinned_hint = false;              // the pipelined caller's output buffers are page-locked
     // host clip staging
     uint8_t* h_chunk[2] = {nullptr, nullptr};
     uint8_t* d_chunk[2] = {nullptr, nullptr};
@@ -734,10 +737,21 @@ static int32_t ensure_slot(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, size_t in_byt
     return DIPSB_OK;
 }
 
+// page-locked host memory (dipsb_host_alloc, cudaHostAlloc/cudaHostRegister, torch pin_memory): the copy engine can
+// reach it directly, so the staging memcpy -- the dominant cost of a 1080p per-frame call -- is skipped
+static bool host_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 // Stage one frame into `sl` and enqueue upload, kernel and read-back.  `overlap`: upload on the copy stream so that it runs
 // concurrently with the previous frame's kernel / read-back (pipelined mode); otherwise everything on the context's stream.
+// `out_direct`: page-locked caller buffer the difference frame is read back into (synchronous mode), `defer_out`: leave
+// the read-back to collect_frame.
 static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_t* px, uint32_t width, uint32_t height,
-                            uint32_t stride, int32_t format, bool want_rgba, bool overlap) {
+                            uint32_t stride, int32_t format, bool want_rgba, bool overlap, uint8_t* out_direct = nullptr,
+                            bool defer_out = false) {
     const Geometry& g = c->g;
     if (width != g.width || height != g.height) return fail(c, DIPSB_ERR_INVALID, "push_frame: %ux%u does not match the context's %ux%u", width, height, g.width, g.height);
     if (format < 0 || format > 3) return fail(c, DIPSB_ERR_INVALID, "push_frame: bad format %d", format);
@@ -749,15 +763,21 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     if (rc) return rc;
     rc = ensure_scalars(c, c->stream_index + 1);
     if (rc) return rc;
-    // the input slice is borrowed for the call only (frame_extractor.rs:224-226): copy it out before returning
-    if (stride == row) memcpy(sl.h_in, px, fb);
-    else for (uint32_t y = 0; y < height; ++y) memcpy(sl.h_in + (uint64_t)y * row, px + (uint64_t)y * stride, row);
+    // the input slice is borrowed for the call only (frame_extractor.rs:224-226): it is either staged now or, when it is
+    // page-locked, uploaded straight from the caller's buffer and the upload awaited before this call returns
+    const bool in_direct = stride == row && host_pinned(px);
+    const uint8_t* src = px;
+    if (!in_direct) {
+        if (stride == row) memcpy(sl.h_in, px, fb);
+        else for (uint32_t y = 0; y < height; ++y) memcpy(sl.h_in + (uint64_t)y * row, px + (uint64_t)y * stride, row);
+        src = sl.h_in;
+    }
     if (overlap) {
-        CK(c, cudaMemcpyAsync(sl.d_in, sl.h_in, fb, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(c, cudaMemcpyAsync(sl.d_in, src, fb, cudaMemcpyHostToDevice, c->copy_stream));
         CK(c, cudaEventRecord(sl.ev_h2d, c->copy_stream));
         CK(c, cudaStreamWaitEvent(c->stream, sl.ev_h2d, 0));
     } else {
-        CK(c, cudaMemcpyAsync(sl.d_in, sl.h_in, fb, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(sl.d_in, src, fb, cudaMemcpyHostToDevice, c->stream));
     }
     const uint64_t idx = c->stream_index;
     CK(c, cudaMemsetAsync(c->d_sad + idx, 0, sizeof(uint64_t), c->stream));
@@ -828,7 +848,10 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
         if (establishes && want_rgba) CK(c, launch_passthrough_rgba(g, sl.d_in, row, format, sl.d_out, c->stream));
         c->state_valid = true;
     }
-    if (want_rgba) CK(c, cudaMemcpyAsync(sl.h_out, sl.d_out, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    sl.out_direct = want_rgba && out_direct != nullptr;
+    sl.out_deferred = want_rgba && !sl.out_direct && defer_out;
+    if (want_rgba && !sl.out_deferred)
+        CK(c, cudaMemcpyAsync(sl.out_direct ? out_direct : sl.h_out, sl.d_out, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaMemcpyAsync(&sl.h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaMemcpyAsync(&sl.h_stat[1], c->d_cnt + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaEventRecord(sl.ev_done, c->stream));
@@ -836,14 +859,29 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     c->stream_index = idx + 1;
     c->frames_processed += 1;
     c->scal_hi = std::max(c->scal_hi, idx + 1);
+    if (in_direct && overlap) CK(c, cudaEventSynchronize(sl.ev_h2d));   // the caller's buffer is free again on return
+    return DIPSB_OK;
+}
+
+// deferred read-back (pipelined mode, page-locked caller): enqueue it now, behind whatever the stream already holds
+static int32_t start_readback(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, uint8_t* out_rgba) {
+    if (!sl.pending || !sl.out_deferred || !out_rgba) return DIPSB_OK;
+    const bool direct = host_pinned(out_rgba);
+    CK(c, cudaMemcpyAsync(direct ? out_rgba : sl.h_out, sl.d_out, c->g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaEventRecord(sl.ev_done, c->stream));
+    sl.out_deferred = false;
+    sl.out_direct = direct;
     return DIPSB_OK;
 }
 
 // wait for the frame in `sl` and hand its output to the caller; returns the frame's own status (OK / NOT_READY)
 static int32_t collect_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, uint8_t* out_rgba, dipsb_frame_stats* stats) {
     if (!sl.pending) return fail(c, DIPSB_ERR_STATE, "no frame in flight");
+    int32_t rb = start_readback(c, sl, out_rgba);
+    if (rb) return rb;
+    const bool copy_out = out_rgba && sl.want_rgba && !sl.out_direct && !sl.out_deferred;
     CK(c, cudaEventSynchronize(sl.ev_done));
-    if (out_rgba && sl.want_rgba) memcpy(out_rgba, sl.h_out, c->g.npx * 4);
+    if (copy_out) memcpy(out_rgba, sl.h_out, c->g.npx * 4);
     if (stats) { stats->frame_index = sl.idx; stats->sad = sl.h_stat[0]; stats->count = sl.h_stat[1]; }
     sl.pending = false;
     return sl.status;
@@ -854,7 +892,8 @@ extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t wi
     if (!c || !px) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     if (c->slot[0].pending || c->slot[1].pending) return fail(c, DIPSB_ERR_STATE, "push_frame: a pipelined frame is in flight; call dipsb_flush_frame first");
-    int32_t rc = submit_frame(c, c->slot[0], px, width, height, stride, format, out_rgba != nullptr, false);
+    int32_t rc = submit_frame(c, c->slot[0], px, width, height, stride, format, out_rgba != nullptr, false,
+                              out_rgba && host_pinned(out_rgba) ? out_rgba : nullptr);
     if (rc) return rc;
     return collect_frame(c, c->slot[0], out_rgba, stats);
 }
@@ -866,8 +905,13 @@ extern "C" int32_t dipsb_push_frame_pipelined(dipsb_ctx* c, const uint8_t* px, u
     dipsb_ctx::FrameSlot& cur = c->slot[c->next_slot];
     dipsb_ctx::FrameSlot& prev = c->slot[c->next_slot ^ 1];
     if (cur.pending) return fail(c, DIPSB_ERR_STATE, "push_frame_pipelined: slot still in flight");
-    // output planes are requested for every frame in this mode (the caller decides at collection time)
-    int32_t rc = submit_frame(c, cur, px, width, height, stride, format, true, true);
+    // output planes are requested for every frame in this mode (the caller decides at collection time); a caller that
+    // hands in page-locked output buffers gets the read-back issued at collection, straight into its buffer
+    if (out_rgba_prev) c->out_pinned_hint = host_pinned(out_rgba_prev);
+    // the previous frame's read-back goes first so that it overlaps this frame's upload (separate copy engines)
+    int32_t rc = start_readback(c, prev, out_rgba_prev);
+    if (rc) return rc;
+    rc = submit_frame(c, cur, px, width, height, stride, format, true, true, nullptr, c->out_pinned_hint);
     if (rc) return rc;
     c->next_slot ^= 1;
     if (!prev.pending) return DIPSB_NOT_READY;          // first call: nothing to hand back yet
@@ -1002,6 +1046,22 @@ extern "C" int32_t dipsb_synth_fill_device(int32_t device, void* d_dst, uint64_t
     if (cudaSetDevice(device) != cudaSuccess) return DIPSB_ERR_CUDA;
     cudaError_t e = launch_synth((uint8_t*)d_dst, first_frame, n_frames, width, height, bpp_of(format), seed, profile, (cudaStream_t)stream);
     return e == cudaSuccess ? DIPSB_OK : fail(nullptr, DIPSB_ERR_CUDA, "synth_fill: %s", cudaGetErrorString(e));
+}
+
+extern "C" int32_t dipsb_host_alloc(int32_t device, uint64_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(nullptr, DIPSB_ERR_INVALID, "host_alloc: null or empty request");
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DIPSB_ERR_CUDA, "host_alloc: no CUDA device %d", device); }
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return fail(nullptr, DIPSB_ERR_NOMEM, "host_alloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e)); }
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_host_free(void* p) {
+    if (!p) return DIPSB_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DIPSB_ERR_INVALID, "host_free: %s", cudaGetErrorString(e)); }
+    return DIPSB_OK;
 }
 
 extern "C" int32_t dipsb_enable_timing(dipsb_ctx* c, int32_t on) {

@@ -198,6 +198,15 @@ int32_t dipsb_get_frame_means(dipsb_ctx *ctx, uint64_t first, uint64_t n, float 
 int32_t dipsb_synth_fill_device(int32_t device, void *d_dst, uint64_t first_frame, uint64_t n_frames,
                                 uint32_t width, uint32_t height, int32_t format, uint64_t seed, int32_t profile,
                                 void *stream);
+/*
+ * Page-locked host buffers for the frame paths.  dipsb_push_frame / dipsb_push_frame_pipelined / dipsb_run_clip_host
+ * recognise page-locked pointers (these, cudaHostAlloc / cudaHostRegister memory, torch pin_memory tensors) and let the
+ * copy engine read and write them directly; any other host pointer is staged through an internal page-locked buffer with
+ * a CPU memcpy first, which for a 1080p frame costs several times the PCIe transfer itself.  A decoder that writes its
+ * frames into such a buffer (the role of frame_extractor.rs:216-226's mapped gst buffer) removes that copy.
+ */
+int32_t dipsb_host_alloc(int32_t device, uint64_t bytes, void **out);
+int32_t dipsb_host_free(void *p);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t dipsb_launch_count(void);
 /* last clip kernel geometry, for reports: [0] tiles, [1] frame segments, [2] threads per block, [3] stages | kernel << 16, [4] blocks per

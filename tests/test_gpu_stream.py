@@ -227,3 +227,64 @@ def test_spatial_window_streaming_and_batch(oracle, window, fmt, mode):
         ctx.prime_median4_device(dev.data_ptr(), clip.shape[1])
         want = np.sort(np.stack(planes[:4]), axis=0)[2]
         assert np.array_equal(ctx.get_state_plane(), want)
+
+
+@pytest.mark.parametrize("flavor", [0, 1, 2])
+@pytest.mark.parametrize("pin_in,pin_out", [(True, True), (True, False), (False, True)])
+def test_page_locked_buffers_take_the_direct_path_with_identical_results(oracle, flavor, pin_in, pin_out):
+    """dipsb_host_alloc buffers are read and written by the copy engine directly (no staging memcpy); results are the
+    same bytes as with ordinary memory, and the input buffer is free for reuse as soon as each call returns (the
+    reference borrows the slice for the callback only, frame_extractor.rs:224-226)."""
+    import dips_b200
+    w, h, n, fmt = 128, 72, 10, 1
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    with dips_b200.Context(w, h, fmt, 0, 7, flavor=flavor) as ctx:
+        want = [ctx.push_frame(clip[t]) for t in range(n)]
+        acc_want = ctx.get_accumulators()
+    fb = w * h * 4
+    with dips_b200.PinnedBuffer(fb) as pin, dips_b200.PinnedBuffer(2 * fb) as pout:
+        src = pin.array if pin_in else np.empty(fb, np.uint8)
+        outs = [pout.array[:fb], pout.array[fb:]] if pin_out else [np.empty(fb, np.uint8), np.empty(fb, np.uint8)]
+        # synchronous
+        with dips_b200.Context(w, h, fmt, 0, 7, flavor=flavor) as ctx:
+            for t in range(n):
+                src[:] = clip[t]
+                rc, rgba, st = ctx.push_frame(src, out=outs[0])
+                src[:] = 0xA5                               # scribble: the library must be done with it
+                assert rgba is outs[0]
+                assert rc == want[t][0] and st == want[t][2] and np.array_equal(rgba, want[t][1]), t
+            acc = ctx.get_accumulators()
+            assert np.array_equal(acc[0], acc_want[0]) and np.array_equal(acc[1], acc_want[1])
+        # pipelined
+        with dips_b200.Context(w, h, fmt, 0, 7, flavor=flavor) as ctx:
+            for t in range(n + 1):
+                if t < n:
+                    src[:] = clip[t]
+                    rc, rgba, st = ctx.push_frame_pipelined(src, out=outs[t & 1])
+                    src[:] = 0x5A
+                else:
+                    rc, rgba, st = ctx.flush_frame(out=outs[t & 1])
+                if t == 0:
+                    assert rc == dips_b200.NOT_READY
+                    continue
+                assert rc == (2 if want[t - 1][0] == dips_b200.NOT_READY else 0)
+                assert st == want[t - 1][2] and np.array_equal(rgba, want[t - 1][1]), t
+            acc = ctx.get_accumulators()
+            assert np.array_equal(acc[0], acc_want[0]) and np.array_equal(acc[1], acc_want[1])
+
+
+def test_pinned_buffer_lifecycle_and_errors():
+    import dips_b200
+    from dips_b200 import _lib
+    import ctypes as C
+    b = dips_b200.PinnedBuffer(1 << 20)
+    b.array[:] = 7
+    assert int(b.array.sum()) == 7 << 20
+    b.close()
+    b.close()                                               # idempotent
+    lib = _lib.load()
+    p = C.c_void_p()
+    assert lib.dipsb_host_alloc(0, 0, C.byref(p)) == -1     # empty request
+    assert lib.dipsb_host_alloc(0, 16, None) == -1
+    assert lib.dipsb_host_alloc(9999, 16, C.byref(p)) == -2 and not p.value
+    assert lib.dipsb_host_free(None) == 0
