@@ -256,3 +256,44 @@ impl Drop for DiPsCompute {
         unsafe { sys::dipsb_destroy(self.ctx) };
     }
 }
+
+/// Page-locked host buffer (`dipsb_host_alloc`).  A decoder that writes its frames here -- and a caller that receives
+/// the difference frame here -- lets `dipsb_push_frame*` skip its two staging copies (the role of the mapped gst buffer
+/// in dips/src/frame_extractor.rs:216-226).  Derefs to a byte slice.
+pub struct PinnedFrame {
+    ptr: *mut u8,
+    len: usize,
+}
+
+unsafe impl Send for PinnedFrame {}
+
+impl PinnedFrame {
+    pub fn new(device: i32, len: usize) -> anyhow::Result<Self> {
+        let mut p: *mut std::ffi::c_void = ptr::null_mut();
+        let rc = unsafe { sys::dipsb_host_alloc(device, len as u64, &mut p) };
+        if rc != 0 {
+            let msg = unsafe { CStr::from_ptr(sys::dipsb_last_error(ptr::null_mut())) };
+            anyhow::bail!("dipsb_host_alloc failed ({rc}): {}", msg.to_string_lossy());
+        }
+        Ok(Self { ptr: p as *mut u8, len })
+    }
+}
+
+impl std::ops::Deref for PinnedFrame {
+    type Target = [u8];
+    fn deref(&self) -> &[u8] {
+        unsafe { std::slice::from_raw_parts(self.ptr, self.len) }
+    }
+}
+
+impl std::ops::DerefMut for PinnedFrame {
+    fn deref_mut(&mut self) -> &mut [u8] {
+        unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) }
+    }
+}
+
+impl Drop for PinnedFrame {
+    fn drop(&mut self) {
+        unsafe { sys::dipsb_host_free(self.ptr as *mut std::ffi::c_void) };
+    }
+}
