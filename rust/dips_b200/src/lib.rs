@@ -272,7 +272,7 @@ impl PinnedFrame {
         let mut p: *mut std::ffi::c_void = ptr::null_mut();
         let rc = unsafe { sys::dipsb_host_alloc(device, len as u64, &mut p) };
         if rc != 0 {
-            let msg = unsafe { CStr::from_ptr(sys::dipsb_last_error(ptr::null_mut())) };
+            let msg = unsafe { CStr::from_ptr(sys::dipsb_last_error(ptr::null())) };
             anyhow::bail!("dipsb_host_alloc failed ({rc}): {}", msg.to_string_lossy());
         }
         Ok(Self { ptr: p as *mut u8, len })
