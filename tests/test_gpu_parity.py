@@ -583,3 +583,39 @@ def test_run_clip_host_multi_chunk(torch_cuda, oracle, mode):
             assert ctx.frames_processed == n
         assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt), src
         assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt), src
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_geometry_and_call_patterns(torch_cuda, oracle, seed):
+    """Seeded fuzz: random frame sizes (aligned and ragged), formats, modes, chroma filters, thresholds, pitches, call
+    splits, kernels and tunings -- every case bit-exact against the oracle."""
+    rng = np.random.default_rng(0xD1B5 + seed)
+    for case in range(8):
+        fmt = int(rng.integers(0, 4))
+        mode = int(rng.integers(0, 2))
+        chroma = int(rng.integers(0, 4))
+        tau = int(rng.choice([0, 1, 3, 17, 64, 200, 509, 600]))
+        w = int(rng.integers(1, 41)) * 16 if rng.random() < 0.6 else int(rng.integers(1, 700))
+        h = int(rng.integers(1, 48))
+        n = int(rng.integers(1, 36))
+        profile = oracle.SYNTH_SCENE if rng.random() < 0.5 else oracle.SYNTH_UNIFORM
+        clip = oracle.synth_clip(n, w, h, fmt, seed=int(rng.integers(1, 1 << 30)), profile=profile)
+        fb = clip.shape[1]
+        pad = int(rng.choice([0, 0, (-fb) % 16, (-fb) % 16 + 32, 7]))
+        cuts = sorted(set(int(x) for x in rng.integers(1, n + 1, size=int(rng.integers(0, 4)))) - {n})
+        chunks = [0] + cuts + [n]
+        tuning = {}
+        if rng.random() < 0.5:
+            tuning["kernel"] = int(rng.integers(0, 2))
+        if rng.random() < 0.4:
+            tuning["segments"] = int(rng.integers(1, 5))
+        if rng.random() < 0.3 and tuning.get("kernel") != 1:
+            tuning["regs"] = int(rng.choice([64, 72, 80, 96, 128]))
+        if rng.random() < 0.3:
+            tuning["stages"] = int(rng.choice([3, 4]))
+        got = run_gpu(torch_cuda, clip, w, h, fmt, mode, tau, chroma, chunks=chunks, tuning=tuning or None, stride_pad=pad)
+        try:
+            check(oracle, got, clip, fmt, mode, tau, chroma)
+        except AssertionError as e:
+            raise AssertionError(f"seed {seed} case {case}: {w}x{h}x{n} fmt {fmt} mode {mode} chroma {chroma} tau {tau} "
+                                 f"pad {pad} chunks {chunks} tuning {tuning} plan {got[5]}: {e}") from e
