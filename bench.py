@@ -409,7 +409,7 @@ def main():
         frames_rgba[:] = tmp.cpu().numpy().reshape(8, -1)
         del tmp
         stream_info = {"geometry": "1920x1080 RGBx8 in, RGBA8 difference frame out, per-frame call", "frames": sn,
-                       "buffers": "pageable = ordinary host memory (staged by a CPU memcpy each way); pinned = "
+                       "buffers": "pageable = ordinary host memory (staged by the library's threaded host copy each way); pinned = "
                                   "dipsb_host_alloc buffers (copy engine reads/writes them directly)"}
         pin_in = dips_b200.PinnedBuffer(8 * sw * sh * 4, device=local_rank)
         pin_out = dips_b200.PinnedBuffer(2 * sw * sh * 4, device=local_rank)

@@ -517,7 +517,7 @@ extern "C" int32_t dipsb_prime_host(dipsb_ctx* c, const uint8_t* frame) {
     const size_t fb = c->g.npx * c->g.bpp;
     int32_t rc = ensure_frame_staging(c, fb);
     if (rc) return rc;
-    memcpy(c->h_pin, frame, fb);
+    host_copy2d(c->h_pin, fb, frame, fb, fb, 1);
     CK(c, cudaMemcpyAsync(c->d_frame, c->h_pin, fb, cudaMemcpyHostToDevice, c->stream));
     rc = dipsb_prime_device(c, c->d_frame);
     if (rc) return rc;
@@ -697,7 +697,7 @@ extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint
             CK(c, cudaMemcpy2DAsync(c->d_chunk[slot], dpitch, src, stride, fb, m, cudaMemcpyHostToDevice, c->copy_stream));
         } else {
             if (used[slot]) CK(c, cudaEventSynchronize(c->ev_copy[slot]));                 // previous H2D from h_chunk[slot] done
-            for (uint64_t k = 0; k < m; ++k) memcpy(c->h_chunk[slot] + k * dpitch, src + k * stride, fb);
+            host_copy2d(c->h_chunk[slot], dpitch, src, stride, fb, m);
             CK(c, cudaMemcpyAsync(c->d_chunk[slot], c->h_chunk[slot], m * dpitch, cudaMemcpyHostToDevice, c->copy_stream));
         }
         CK(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
@@ -768,8 +768,7 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     const bool in_direct = stride == row && host_pinned(px);
     const uint8_t* src = px;
     if (!in_direct) {
-        if (stride == row) memcpy(sl.h_in, px, fb);
-        else for (uint32_t y = 0; y < height; ++y) memcpy(sl.h_in + (uint64_t)y * row, px + (uint64_t)y * stride, row);
+        host_copy2d(sl.h_in, row, px, stride, row, height);
         src = sl.h_in;
     }
     if (overlap) {
@@ -881,7 +880,7 @@ static int32_t collect_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, uint8_t* ou
     if (rb) return rb;
     const bool copy_out = out_rgba && sl.want_rgba && !sl.out_direct && !sl.out_deferred;
     CK(c, cudaEventSynchronize(sl.ev_done));
-    if (copy_out) memcpy(out_rgba, sl.h_out, c->g.npx * 4);
+    if (copy_out) host_copy2d(out_rgba, c->g.npx * 4, sl.h_out, c->g.npx * 4, c->g.npx * 4, 1);
     if (stats) { stats->frame_index = sl.idx; stats->sad = sl.h_stat[0]; stats->count = sl.h_stat[1]; }
     sl.pending = false;
     return sl.status;
@@ -1063,6 +1062,15 @@ extern "C" int32_t dipsb_host_free(void* p) {
     if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DIPSB_ERR_INVALID, "host_free: %s", cudaGetErrorString(e)); }
     return DIPSB_OK;
 }
+
+extern "C" int32_t dipsb_host_copy2d(void* dst, uint64_t dpitch, const void* src, uint64_t spitch, uint64_t row_bytes, uint64_t rows) {
+    if (!rows || !row_bytes) return DIPSB_OK;
+    if (!dst || !src || dpitch < row_bytes || spitch < row_bytes) return fail(nullptr, DIPSB_ERR_INVALID, "host_copy2d: null pointer or pitch smaller than a row");
+    host_copy2d(dst, dpitch, src, spitch, row_bytes, rows);
+    return DIPSB_OK;
+}
+
+extern "C" uint32_t dipsb_host_copy_threads(void) { return host_copy_threads(); }
 
 extern "C" int32_t dipsb_enable_timing(dipsb_ctx* c, int32_t on) {
     if (!c) return DIPSB_ERR_INVALID;

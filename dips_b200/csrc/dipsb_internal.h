@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libdips_b200.so (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace dipsb {
@@ -131,5 +132,9 @@ cudaError_t launch_intensity_map(const Geometry& g, const uint32_t* acc_internal
                                  cudaStream_t s);
 
 void count_launch(uint64_t n = 1);
+
+// host_copy.cu: staging copy on a small persistent thread pool (DIPSB_COPY_THREADS, default min(4, cores/2); 1 = caller only)
+void host_copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows);
+unsigned host_copy_threads();
 
 }  // namespace dipsb

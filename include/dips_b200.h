@@ -207,6 +207,15 @@ int32_t dipsb_synth_fill_device(int32_t device, void *d_dst, uint64_t first_fram
  */
 int32_t dipsb_host_alloc(int32_t device, uint64_t bytes, void **out);
 int32_t dipsb_host_free(void *p);
+/*
+ * The staging copy the frame calls use for ordinary host memory: rows of row_bytes from src (pitch spitch) to dst (pitch
+ * dpitch) on a small persistent thread pool -- the caller plus DIPSB_COPY_THREADS-1 helpers (environment variable, default
+ * min(4, cores/2); 1 = the calling thread only); copies under 1 MB stay on the caller.  After a copy the helpers poll for
+ * DIPSB_COPY_SPIN_US microseconds (default 500, 0 = sleep at once) before they block, so that a per-frame caller finds them
+ * awake.  Host only, no device involved.
+ */
+int32_t dipsb_host_copy2d(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t row_bytes, uint64_t rows);
+uint32_t dipsb_host_copy_threads(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t dipsb_launch_count(void);
 /* last clip kernel geometry, for reports: [0] tiles, [1] frame segments, [2] threads per block, [3] stages | kernel << 16, [4] blocks per

@@ -117,3 +117,47 @@ def test_header_is_valid_c_and_links(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "plan:" in res.stdout
+
+
+def test_host_copy_pool_is_exact_and_thread_safe():
+    """The staging copy (host only): contiguous, pitched and small copies are byte-exact, also from concurrent callers."""
+    import threading
+    import numpy as np
+    from dips_b200 import _lib
+    lib = _lib.load()
+    assert 1 <= lib.dipsb_host_copy_threads() <= 64
+    rng = np.random.default_rng(5)
+
+    def one(rows, row_bytes, spitch, dpitch, seed):
+        r = np.random.default_rng(seed)
+        src = r.integers(0, 256, rows * spitch, dtype=np.uint8)
+        dst = np.full(rows * dpitch, 0xEE, np.uint8)
+        assert lib.dipsb_host_copy2d(dst.ctypes.data, dpitch, src.ctypes.data, spitch, row_bytes, rows) == 0
+        s2, d2 = src.reshape(rows, spitch), dst.reshape(rows, dpitch)
+        assert np.array_equal(d2[:, :row_bytes], s2[:, :row_bytes])
+        assert (d2[:, row_bytes:] == 0xEE).all()           # padding untouched
+
+    one(1, 100, 100, 100, 1)                               # small: caller only
+    one(1, 8_294_400, 8_294_400, 8_294_400, 2)             # one 1080p RGBA frame, contiguous
+    one(1080, 7680, 7680 + 64, 7680, 3)                    # pitched source
+    one(7, 1_000_003, 1_000_003, 1_000_003 + 13, 4)        # odd sizes, pitched destination
+    for _ in range(4):
+        rows = int(rng.integers(1, 40)); rb = int(rng.integers(1, 300_000))
+        one(rows, rb, rb + int(rng.integers(0, 100)), rb + int(rng.integers(0, 100)), int(rng.integers(1 << 30)))
+    errs = []
+
+    def worker(k):
+        try:
+            for i in range(5):
+                one(3, 1_500_000 + k, 1_500_000 + k, 1_500_000 + k + 8, 100 * k + i)
+        except BaseException as e:                          # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    assert lib.dipsb_host_copy2d(None, 8, None, 8, 8, 1) == -1
+    src = np.zeros(64, np.uint8)
+    assert lib.dipsb_host_copy2d(src.ctypes.data, 4, src.ctypes.data, 8, 8, 2) == -1       # pitch < row
+    assert lib.dipsb_host_copy2d(None, 0, None, 0, 0, 0) == 0                              # empty copy
