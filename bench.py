@@ -395,6 +395,22 @@ def main():
                "frames_per_gpu": e2e_frames, "steps": args.e2e_steps,
                "api": "dipsb_run_clip_host (pinned host clip, chunked H2D overlapped with the clip kernel) + dipsb_get_accumulators + dipsb_get_scalars",
                "h2d_GBps_per_gpu": e2e_frames * fb * args.e2e_steps / dt / 1e9}
+        if world == 1:
+            # the same call from ORDINARY host memory (what a caller without page-locked buffers has): every chunk is first
+            # staged into a page-locked bounce buffer by the library's threaded host copy
+            pn = min(e2e_frames, max(32, int(2.5e9 // fb)))
+            pageable = np.empty((pn, fb), np.uint8)
+            pageable[:] = host[:pn].numpy()
+            ctx.reset(); ctx.run_clip_host(pageable.ctypes.data, pn, fb, 0); ctx.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ctx.reset()
+                ctx.run_clip_host(pageable.ctypes.data, pn, fb, 0)
+                ctx.get_accumulators_into(h_sum.data_ptr(), h_cnt.data_ptr())
+                ctx.get_scalars(0, pn)
+            e2e["pageable_host_fps"] = 2 * pn / (time.perf_counter() - t0)
+            e2e["pageable_host_frames"] = pn
+            del pageable
         del host
 
     # ---- streaming boundary (the reference's per-frame callback shape): RGBA8 frame in -> RGBA8 difference frame out ----
