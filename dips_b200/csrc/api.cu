@@ -53,6 +53,8 @@ struct dipsb_ctx {
         uint8_t* h_in = nullptr; uint8_t* d_in = nullptr; size_t in_bytes = 0;
         uint8_t* d_out = nullptr; uint8_t* h_out = nullptr; uint64_t* h_stat = nullptr;
         cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
+        cudaEvent_t ev_out[4] = {nullptr, nullptr, nullptr, nullptr};   // read-back pieces (staged output)
+        int out_pieces = 0;
         bool pending = false, want_rgba = false; int32_t status = 0; uint64_t idx = 0;
         bool out_direct = false;               // the read-back already targets the caller's (pinned) buffer
         bool out_deferred = false;             // the read-back is enqueued at collection time (pipelined, pinned caller)
@@ -237,6 +239,7 @@ static void free_all(dipsb_ctx* c) {
         cudaFree(sl.d_in); cudaFree(sl.d_out);
         if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        for (auto& e : sl.ev_out) if (e) cudaEventDestroy(e);
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -734,7 +737,17 @@ static int32_t ensure_slot(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, size_t in_byt
     if (!sl.h_stat) CK(c, cudaMallocHost(&sl.h_stat, 2 * sizeof(uint64_t)));
     if (!sl.ev_h2d) CK(c, cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
     if (!sl.ev_done) CK(c, cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    for (auto& e : sl.ev_out) if (!e) CK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return DIPSB_OK;
+}
+
+// staged frames of 2 MB and more move in up to 4 pieces so that the CPU copy and the PCIe transfer overlap
+static uint32_t stage_pieces(uint64_t bytes, uint32_t rows) {
+    const uint64_t p = std::min<uint64_t>(4, bytes >> 20);
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(p, rows));
+}
+static uint64_t piece_offset(uint64_t bytes, int k, int pieces) {
+    return k >= pieces ? bytes : (bytes / pieces * k) & ~uint64_t(4095);
 }
 
 // page-locked host memory (dipsb_host_alloc, cudaHostAlloc/cudaHostRegister, torch pin_memory): the copy engine can
@@ -766,17 +779,22 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     // the input slice is borrowed for the call only (frame_extractor.rs:224-226): it is either staged now or, when it is
     // page-locked, uploaded straight from the caller's buffer and the upload awaited before this call returns
     const bool in_direct = stride == row && host_pinned(px);
-    const uint8_t* src = px;
-    if (!in_direct) {
-        host_copy2d(sl.h_in, row, px, stride, row, height);
-        src = sl.h_in;
+    cudaStream_t up = overlap ? c->copy_stream : c->stream;
+    if (in_direct) {
+        CK(c, cudaMemcpyAsync(sl.d_in, px, fb, cudaMemcpyHostToDevice, up));
+    } else {
+        // staged in row bands: the upload of one band runs while the CPU copies the next (synchronous call only: in the
+        // pipelined call transfers already overlap the neighbouring frame's copies and the extra calls only cost)
+        const uint32_t pieces = overlap ? 1 : stage_pieces(fb, height);
+        for (uint32_t k = 0; k < pieces; ++k) {
+            const uint32_t r0 = (uint64_t)height * k / pieces, r1 = (uint64_t)height * (k + 1) / pieces;
+            host_copy2d(sl.h_in + (uint64_t)r0 * row, row, px + (uint64_t)r0 * stride, stride, row, r1 - r0);
+            CK(c, cudaMemcpyAsync(sl.d_in + (uint64_t)r0 * row, sl.h_in + (uint64_t)r0 * row, (uint64_t)(r1 - r0) * row, cudaMemcpyHostToDevice, up));
+        }
     }
     if (overlap) {
-        CK(c, cudaMemcpyAsync(sl.d_in, src, fb, cudaMemcpyHostToDevice, c->copy_stream));
         CK(c, cudaEventRecord(sl.ev_h2d, c->copy_stream));
         CK(c, cudaStreamWaitEvent(c->stream, sl.ev_h2d, 0));
-    } else {
-        CK(c, cudaMemcpyAsync(sl.d_in, src, fb, cudaMemcpyHostToDevice, c->stream));
     }
     const uint64_t idx = c->stream_index;
     CK(c, cudaMemsetAsync(c->d_sad + idx, 0, sizeof(uint64_t), c->stream));
@@ -849,8 +867,19 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     }
     sl.out_direct = want_rgba && out_direct != nullptr;
     sl.out_deferred = want_rgba && !sl.out_direct && defer_out;
-    if (want_rgba && !sl.out_deferred)
-        CK(c, cudaMemcpyAsync(sl.out_direct ? out_direct : sl.h_out, sl.d_out, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    sl.out_pieces = 0;
+    if (sl.out_direct) {
+        CK(c, cudaMemcpyAsync(out_direct, sl.d_out, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    } else if (want_rgba && !sl.out_deferred) {
+        // staged read-back in pieces, each with its own event: collect_frame copies piece k out while piece k+1 is in flight
+        const uint64_t bytes = g.npx * 4;
+        sl.out_pieces = overlap ? 1 : (int)stage_pieces(bytes, g.height);
+        for (int k = 0; k < sl.out_pieces; ++k) {
+            const uint64_t b0 = piece_offset(bytes, k, sl.out_pieces), b1 = piece_offset(bytes, k + 1, sl.out_pieces);
+            CK(c, cudaMemcpyAsync(sl.h_out + b0, sl.d_out + b0, b1 - b0, cudaMemcpyDeviceToHost, c->stream));
+            CK(c, cudaEventRecord(sl.ev_out[k], c->stream));
+        }
+    }
     CK(c, cudaMemcpyAsync(&sl.h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaMemcpyAsync(&sl.h_stat[1], c->d_cnt + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaEventRecord(sl.ev_done, c->stream));
@@ -879,8 +908,18 @@ static int32_t collect_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, uint8_t* ou
     int32_t rb = start_readback(c, sl, out_rgba);
     if (rb) return rb;
     const bool copy_out = out_rgba && sl.want_rgba && !sl.out_direct && !sl.out_deferred;
-    CK(c, cudaEventSynchronize(sl.ev_done));
-    if (copy_out) host_copy2d(out_rgba, c->g.npx * 4, sl.h_out, c->g.npx * 4, c->g.npx * 4, 1);
+    if (copy_out && sl.out_pieces > 1) {
+        const uint64_t bytes = c->g.npx * 4;
+        for (int k = 0; k < sl.out_pieces; ++k) {
+            const uint64_t b0 = piece_offset(bytes, k, sl.out_pieces), b1 = piece_offset(bytes, k + 1, sl.out_pieces);
+            CK(c, cudaEventSynchronize(sl.ev_out[k]));
+            host_copy2d(out_rgba + b0, b1 - b0, sl.h_out + b0, b1 - b0, b1 - b0, 1);
+        }
+        CK(c, cudaEventSynchronize(sl.ev_done));
+    } else {
+        CK(c, cudaEventSynchronize(sl.ev_done));
+        if (copy_out) host_copy2d(out_rgba, c->g.npx * 4, sl.h_out, c->g.npx * 4, c->g.npx * 4, 1);
+    }
     if (stats) { stats->frame_index = sl.idx; stats->sad = sl.h_stat[0]; stats->count = sl.h_stat[1]; }
     sl.pending = false;
     return sl.status;

@@ -106,6 +106,27 @@ inline std::vector<uint8_t> frame_callback(uint32_t width, uint32_t height, cons
     return std::vector<uint8_t>(frame_data, frame_data + len);
 }
 
+// Page-locked frame buffer (dipsb_host_alloc): a decoder that writes here, and a caller that receives the difference frame
+// here, let dipsb_push_frame* skip its staging copies (the role of the mapped gst buffer, dips/src/frame_extractor.rs:216-226).
+class PinnedFrame {
+  public:
+    PinnedFrame(size_t len, int32_t device = 0) : len_(len) {
+        void* p = nullptr;
+        if (dipsb_host_alloc(device, len, &p) != DIPSB_OK) throw std::runtime_error(dipsb_last_error(nullptr));
+        ptr_ = static_cast<uint8_t*>(p);
+    }
+    ~PinnedFrame() { dipsb_host_free(ptr_); }
+    PinnedFrame(const PinnedFrame&) = delete;
+    PinnedFrame& operator=(const PinnedFrame&) = delete;
+    uint8_t* data() { return ptr_; }
+    const uint8_t* data() const { return ptr_; }
+    size_t size() const { return len_; }
+
+  private:
+    uint8_t* ptr_ = nullptr;
+    size_t len_ = 0;
+};
+
 }  // namespace dips
 
 namespace dips_alt {
