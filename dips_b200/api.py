@@ -42,6 +42,50 @@ def synth_fill_device(device: int, d_dst: int, first_frame: int, n_frames: int, 
         raise DipsError(rc, _lib.load().dipsb_last_error(None).decode())
 
 
+FRAME_COUNT = 2      # dips_alt/src/lib.rs:36
+
+
+class SnapshotSchedule:
+    """When the caller loops of dips_alt ask for a snapshot: on the frame where index == FRAME_COUNT (the third frame, and
+    the third after every refresh marker); index saturates one past it and a marker -- a 1-based count of frames processed
+    so far -- resets it (dips_alt/src/lib.rs:222-232 live mode, :560-561 and :662-670 file mode)."""
+
+    def __init__(self, refresh_markers=()):
+        self.refresh_markers = set(int(m) for m in refresh_markers)
+        self.index = 0
+        self.overall_frame = 0
+
+    def snapshot_now(self) -> bool:
+        """Ask before sending the frame."""
+        return self.index == FRAME_COUNT
+
+    def frame_sent(self) -> None:
+        """Call after sending it."""
+        if self.index <= FRAME_COUNT:
+            self.index += 1
+        self.overall_frame += 1
+        if self.overall_frame in self.refresh_markers:
+            self.index = 0
+
+
+def run_dips_on_frames(ctx: "Context", frames, refresh_markers=(), sink=None):
+    """The compute part of run_dips_on_file (dips_alt/src/lib.rs:553-690) without the OpenCV capture / writer around it:
+    every frame goes through push_frame on a FLAVOR_ALT_RING2[_MEDIAN] context with the reference's snapshot schedule.
+    Returns the list of difference frames, or hands each (t, rgba) to `sink`."""
+    schedule = SnapshotSchedule(refresh_markers)
+    outs = []
+    for t, frame in enumerate(frames):
+        if schedule.snapshot_now():
+            ctx.snapshot()
+        _, rgba, _ = ctx.push_frame(frame)
+        schedule.frame_sent()
+        if sink is None:
+            outs.append(rgba)
+        else:
+            sink(t, rgba)
+    return outs
+
+
 class PinnedBuffer:
     """A page-locked host buffer from dipsb_host_alloc, exposed as a numpy uint8 array (`.array`).  The frame calls
     recognise it and skip their staging copy.  Free it with close() (or a `with` block) once no array view is in use."""

@@ -14,6 +14,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "dips_b200.h"
@@ -179,5 +180,39 @@ class DiPsCompute {
     dipsb_ctx* ctx_ = nullptr;
     uint32_t width_, height_;
 };
+
+constexpr size_t FRAME_COUNT = 2;                                 // dips_alt/src/lib.rs:36
+
+// When the caller loops of dips_alt ask for a snapshot: the frame on which `index == FRAME_COUNT` (the third frame, and the
+// third frame after every refresh marker); `index` saturates one past it and a marker -- a 1-based count of frames
+// processed so far -- resets it (dips_alt/src/lib.rs:222-232 live, :560-561 and :662-670 file mode).
+class SnapshotSchedule {
+  public:
+    explicit SnapshotSchedule(std::vector<size_t> refresh_markers = {}) : markers_(std::move(refresh_markers)) {}
+    bool snapshot_now() const { return index_ == FRAME_COUNT; }   // ask BEFORE sending the frame
+    void frame_sent() {                                           // call AFTER sending it
+        if (index_ <= FRAME_COUNT) ++index_;
+        ++overall_frame_;
+        for (size_t m : markers_) if (m == overall_frame_) { index_ = 0; break; }
+    }
+    size_t overall_frame() const { return overall_frame_; }
+
+  private:
+    std::vector<size_t> markers_;
+    size_t index_ = 0, overall_frame_ = 0;
+};
+
+// The compute part of run_dips_on_file (dips_alt/src/lib.rs:553-690) without the OpenCV capture/writer around it:
+// every RGBA frame goes through send_frame with that schedule; `sink(frame_number, rgba)` receives the difference frames.
+template <class Sink>
+inline void run_dips_on_frames(DiPsCompute& compute, const uint8_t* frames, size_t n_frames, size_t frame_len,
+                               const std::vector<size_t>& refresh_markers, Sink&& sink) {
+    SnapshotSchedule schedule(refresh_markers);
+    for (size_t t = 0; t < n_frames; ++t) {
+        std::vector<uint8_t> out = compute.send_frame(frames + t * frame_len, frame_len, schedule.snapshot_now());
+        schedule.frame_sent();
+        sink(t, out);
+    }
+}
 
 }  // namespace dips_alt

@@ -257,6 +257,55 @@ impl Drop for DiPsCompute {
     }
 }
 
+/// dips_alt/src/lib.rs:36
+pub const FRAME_COUNT: usize = 2;
+
+/// When the caller loops of `dips_alt` ask for a snapshot: on the frame where `index == FRAME_COUNT` (the third frame, and
+/// the third after every refresh marker); `index` saturates one past it, a marker -- a 1-based count of frames processed --
+/// resets it (dips_alt/src/lib.rs:222-232 live mode, :560-561 and :662-670 file mode).
+#[derive(Debug, Default, Clone)]
+pub struct SnapshotSchedule {
+    refresh_markers: Vec<usize>,
+    index: usize,
+    overall_frame: usize,
+}
+
+impl SnapshotSchedule {
+    pub fn new(refresh_markers: Vec<usize>) -> Self {
+        Self { refresh_markers, index: 0, overall_frame: 0 }
+    }
+
+    /// Ask before sending the frame.
+    pub fn snapshot_now(&self) -> Option<()> {
+        if self.index == FRAME_COUNT { Some(()) } else { None }
+    }
+
+    /// Call after sending it.
+    pub fn frame_sent(&mut self) {
+        if self.index <= FRAME_COUNT {
+            self.index += 1;
+        }
+        self.overall_frame += 1;
+        if self.refresh_markers.contains(&self.overall_frame) {
+            self.index = 0;
+        }
+    }
+}
+
+/// The compute part of `run_dips_on_file` (dips_alt/src/lib.rs:553-690) without the OpenCV capture / writer around it.
+pub fn run_dips_on_frames<'a, I, F>(compute: &mut DiPsCompute, frames: I, refresh_markers: Vec<usize>, mut sink: F)
+where
+    I: IntoIterator<Item = &'a [u8]>,
+    F: FnMut(usize, Vec<u8>),
+{
+    let mut schedule = SnapshotSchedule::new(refresh_markers);
+    for (t, frame) in frames.into_iter().enumerate() {
+        let out = compute.send_frame(frame, schedule.snapshot_now());
+        schedule.frame_sent();
+        sink(t, out);
+    }
+}
+
 /// Page-locked host buffer (`dipsb_host_alloc`).  A decoder that writes its frames here -- and a caller that receives
 /// the difference frame here -- lets `dipsb_push_frame*` skip its two staging copies (the role of the mapped gst buffer
 /// in dips/src/frame_extractor.rs:216-226).  Derefs to a byte slice.
