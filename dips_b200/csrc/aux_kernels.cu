@@ -239,9 +239,9 @@ __global__ void ring_kernel(const RingK K) {
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t y = (uint32_t)(p / K.width), x = (uint32_t)(p - (uint64_t)y * K.width);
         const uint32_t raw = K.i2src ? K.i2src[p] : intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
-        uint32_t v[4] = {0, 0, 0, 0};
-        for (int k = 0; k < K.n_slots; ++k) v[k] = K.ring[(uint64_t)k * npx + p];
-        v[K.write_slot] = raw;
+        uint32_t v[4];                                              // compile-time indices only: stays in registers
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = k == K.write_slot ? raw : (k < K.n_slots ? K.ring[(uint64_t)k * npx + p] : 0u);
         uint32_t start = K.start[p], med;
         bool grey_out = false;
         if (K.n_slots == 4) {                                       // `dips`
@@ -249,11 +249,12 @@ __global__ void ring_kernel(const RingK K) {
                 start = 2u * ((upper_median4(v[0], v[1], v[2], v[3]) + 1u) >> 1);
                 K.start[p] = (uint16_t)start;
             }
-            if (K.grey_slot >= 0) {                                  // dips_shader.wgsl:187
-                v[K.grey_slot] = 2u * ((v[K.grey_slot] + 1u) >> 1);
-                K.ring[(uint64_t)K.grey_slot * npx + p] = (uint16_t)v[K.grey_slot];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t grey = 2u * ((v[k] + 1u) >> 1);          // dips_shader.wgsl:187
+                v[k] = k == K.grey_slot ? grey : v[k];
+                if (k == K.grey_slot || k == K.write_slot) K.ring[(uint64_t)k * npx + p] = (uint16_t)v[k];
             }
-            if (K.grey_slot != K.write_slot) K.ring[(uint64_t)K.write_slot * npx + p] = (uint16_t)v[K.write_slot];
             med = upper_median4(v[0], v[1], v[2], v[3]);             // :191-214
         } else {                                                     // `dips_alt`, NUM_TEXTURES = 2
             K.ring[(uint64_t)K.write_slot * npx + p] = (uint16_t)raw;
@@ -297,22 +298,25 @@ __global__ void ring_kernel(const RingK K) {
 // [-w/2, +w/2]^2, zero for taps outside the frame (as the reference pads, dips_shader.wgsl:135-139), element w*w/2 of the
 // ascending order.  The reference's own loop covers only the half-open window [-w/2, w/2) and picks the wrong element
 //  -- a defect that is deliberately not reproduced.  Selection by bitwise binary search on the 9-bit value.
-__global__ void spatial_median_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t W, uint32_t H, int w) {
+template <int w>
+__global__ void spatial_median_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t W, uint32_t H) {
     const uint64_t npx = (uint64_t)W * H;
-    const int r = w / 2, k = (w * w) / 2;
+    constexpr int r = w / 2, k = (w * w) / 2, n = w * w;        // compile-time window: the taps live in registers
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
         const int y = (int)(p / W), x = (int)(p - (uint64_t)y * W);
-        uint16_t v[49];
-        int n = 0;
+        uint32_t v[n];
+#pragma unroll
         for (int dy = -r; dy <= r; ++dy)
+#pragma unroll
             for (int dx = -r; dx <= r; ++dx) {
                 const int yy = y + dy, xx = x + dx;
-                v[n++] = (yy >= 0 && yy < (int)H && xx >= 0 && xx < (int)W) ? in[(uint64_t)yy * W + xx] : (uint16_t)0;
+                v[(dy + r) * w + dx + r] = (yy >= 0 && yy < (int)H && xx >= 0 && xx < (int)W) ? in[(uint64_t)yy * W + xx] : 0u;
             }
         uint32_t lo = 0;                                   // largest value with #(v < value) <= k  ==  sorted[k]
         for (int bit = 8; bit >= 0; --bit) {
             const uint32_t cand = lo | (1u << bit);
             int cnt = 0;
+#pragma unroll
             for (int i = 0; i < n; ++i) cnt += v[i] < cand;
             if (cnt <= k) lo = cand;
         }
@@ -441,7 +445,12 @@ cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) 
     return cudaGetLastError();
 }
 cudaError_t launch_spatial_median(const Geometry& g, const uint16_t* in, uint16_t* out, int window, cudaStream_t s) {
-    spatial_median_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(in, out, g.width, g.height, window);
+    switch (window) {
+        case 3: spatial_median_kernel<3><<<grid_for(g.npx, g), kThreads, 0, s>>>(in, out, g.width, g.height); break;
+        case 5: spatial_median_kernel<5><<<grid_for(g.npx, g), kThreads, 0, s>>>(in, out, g.width, g.height); break;
+        case 7: spatial_median_kernel<7><<<grid_for(g.npx, g), kThreads, 0, s>>>(in, out, g.width, g.height); break;
+        default: return cudaErrorInvalidValue;
+    }
     count_launch();
     return cudaGetLastError();
 }
