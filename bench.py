@@ -340,7 +340,8 @@ def main():
     peak, peak_src = measured_peak()
     probe_ms = ctx.stream_probe(clip.data_ptr(), frames, clip.stride(0), 5)      # compute-free TMA stream, same tiles
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload), "kernel": "clip_kernel", "kernel_ms": kern_avg_ms,
+                "traffic": ncu_traffic(args.workload),
+                "kernel": "clip_kernel_ws" if plan.get("kernel") == 1 else "clip_kernel", "kernel_ms": kern_avg_ms,
                 "kernel_share_of_step": kern_avg_ms / (ms_total / args.steps), "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms_per_rank": per_rank, "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0,
                 "stream_probe_GBps": frames * fb / (probe_ms / 1e3) / 1e9,
