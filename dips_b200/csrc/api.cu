@@ -574,6 +574,9 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
     if (n == 0) return DIPSB_OK;
     if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0) return fail(c, DIPSB_ERR_STATE, "run_clip: the ring flavours are streaming-only (dipsb_push_frame)");
     if (n > 0x7FFFFFFFull) return fail(c, DIPSB_ERR_INVALID, "run_clip: too many frames in one call");
+    if (c->frames_processed + n > DIPSB_MAX_ACCUMULATED_FRAMES)
+        return fail(c, DIPSB_ERR_STATE, "run_clip: %llu frames accumulated, %llu more would overflow the u32 sums; read the results and dipsb_reset",
+                    (unsigned long long)c->frames_processed, (unsigned long long)n);
     if (stride < g.npx * g.bpp) return fail(c, DIPSB_ERR_INVALID, "run_clip: stride %llu smaller than a frame", (unsigned long long)stride);
     int32_t rc = ensure_scalars(c, first + n);
     if (rc) return rc;
@@ -772,6 +775,9 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     const uint64_t row = (uint64_t)width * bpp;
     if (stride < row) return fail(c, DIPSB_ERR_INVALID, "push_frame: stride %u smaller than a row (%llu)", stride, (unsigned long long)row);
     const size_t fb = row * height;
+    if (c->frames_processed + 1 > DIPSB_MAX_ACCUMULATED_FRAMES)
+        return fail(c, DIPSB_ERR_STATE, "push_frame: %llu frames accumulated, one more would overflow the u32 sums; read the results and dipsb_reset",
+                    (unsigned long long)c->frames_processed);
     int32_t rc = ensure_slot(c, sl, fb);
     if (rc) return rc;
     rc = ensure_scalars(c, c->stream_index + 1);

@@ -41,6 +41,9 @@ extern "C" {
 #endif
 
 #define DIPSB_ABI_VERSION 1
+/* frames one context may accumulate between resets: 510 * this still fits the u32 per-pixel sums (~39 h of 60 fps video);
+ * a call that would exceed it fails with DIPSB_ERR_STATE instead of wrapping */
+#define DIPSB_MAX_ACCUMULATED_FRAMES 8421504ull
 
 typedef struct dipsb_ctx dipsb_ctx;
 

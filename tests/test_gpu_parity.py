@@ -619,3 +619,28 @@ def test_randomised_geometry_and_call_patterns(torch_cuda, oracle, seed):
         except AssertionError as e:
             raise AssertionError(f"seed {seed} case {case}: {w}x{h}x{n} fmt {fmt} mode {mode} chroma {chroma} tau {tau} "
                                  f"pad {pad} chunks {chunks} tuning {tuning} plan {got[5]}: {e}") from e
+
+
+def test_accumulator_range_guard(torch_cuda, oracle):
+    """A context refuses to accumulate more frames than its u32 per-pixel sums can hold (DIPSB_MAX_ACCUMULATED_FRAMES)
+    instead of wrapping; results so far stay intact and dipsb_reset clears the condition."""
+    import dips_b200
+    limit = 8421504
+    w, h, fmt = 4, 1, 1                                        # 16-byte frames
+    clip = oracle.synth_clip(10, w, h, fmt, profile=oracle.SYNTH_UNIFORM)
+    want = oracle.run_clip(clip, fmt, 0, 5)
+    big = torch_cuda.zeros((limit + 1) * 16, dtype=torch_cuda.uint8, device="cuda")
+    big[:160] = torch_cuda.from_numpy(clip.reshape(-1)).cuda()
+    with dips_b200.Context(w, h, fmt, 0, 5) as ctx:
+        with pytest.raises(dips_b200.DipsError) as e:
+            ctx.run_clip_device(big.data_ptr(), limit + 1, 16, 0)
+        assert e.value.code == -4 and "overflow" in str(e.value)
+        ctx.run_clip_device(big.data_ptr(), 10, 16, 0)
+        with pytest.raises(dips_b200.DipsError):
+            ctx.run_clip_device(big.data_ptr(), limit - 9, 16, 10)
+        acc_sum, acc_cnt = ctx.get_accumulators()
+        assert np.array_equal(acc_sum, want.acc_sum) and np.array_equal(acc_cnt, want.acc_cnt)
+        assert ctx.frames_processed == 10
+        ctx.reset()
+        ctx.run_clip_device(big.data_ptr(), 10, 16, 0)
+        assert np.array_equal(ctx.get_accumulators()[0], want.acc_sum)
