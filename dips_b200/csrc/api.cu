@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -23,7 +24,7 @@ struct dipsb_ctx {
     dipsb_config cfg;
     Geometry g;
     int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, out_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_switch = nullptr;
     uint16_t* state[2] = {nullptr, nullptr};   // u16[n_elems] each, zero padded past npx
     int state_cur = 0;
@@ -52,8 +53,11 @@ struct dipsb_ctx {
     struct FrameSlot {
         uint8_t* h_in = nullptr; uint8_t* d_in = nullptr; size_t in_bytes = 0;
         uint8_t* d_out = nullptr; uint8_t* h_out = nullptr; uint64_t* h_stat = nullptr;
-        cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
-        cudaEvent_t ev_out[4] = {nullptr, nullptr, nullptr, nullptr};   // read-back pieces (staged output)
+        cudaEvent_t ev_done = nullptr;
+        cudaEvent_t ev_in[8] = {};    // per row band: uploaded
+        cudaEvent_t ev_k[8] = {};     //               kernels done
+        cudaEvent_t ev_out[8] = {};   //               read back into the staging buffer
+        uint64_t out_off[9] = {};                          // byte offsets of the bands in the RGBA frame
         int out_pieces = 0;
         bool pending = false, want_rgba = false; int32_t status = 0; uint64_t idx = 0;
         bool out_direct = false;               // the read-back already targets the caller's (pinned) buffer
@@ -237,12 +241,14 @@ static void free_all(dipsb_ctx* c) {
         if (sl.h_out) cudaFreeHost(sl.h_out);
         if (sl.h_stat) cudaFreeHost(sl.h_stat);
         cudaFree(sl.d_in); cudaFree(sl.d_out);
-        if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        for (auto& e : sl.ev_in) if (e) cudaEventDestroy(e);
+        for (auto& e : sl.ev_k) if (e) cudaEventDestroy(e);
         for (auto& e : sl.ev_out) if (e) cudaEventDestroy(e);
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->out_stream) cudaStreamDestroy(c->out_stream);
 }
 
 static int32_t alloc_planes(dipsb_ctx* c) {
@@ -305,7 +311,8 @@ extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
     }
     int32_t rc = DIPSB_OK;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(nullptr, DIPSB_ERR_CUDA, "dipsb_create: stream creation failed");
     c->stream = c->own_stream;
     for (int k = 0; k < 2 && rc == DIPSB_OK; ++k)
@@ -738,19 +745,22 @@ static int32_t ensure_slot(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, size_t in_byt
     if (!sl.d_out) CK(c, cudaMalloc(&sl.d_out, rgba));
     if (!sl.h_out) CK(c, cudaMallocHost(&sl.h_out, rgba));
     if (!sl.h_stat) CK(c, cudaMallocHost(&sl.h_stat, 2 * sizeof(uint64_t)));
-    if (!sl.ev_h2d) CK(c, cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
     if (!sl.ev_done) CK(c, cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    for (auto& e : sl.ev_in) if (!e) CK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : sl.ev_k) if (!e) CK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : sl.ev_out) if (!e) CK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return DIPSB_OK;
 }
 
-// staged frames of 2 MB and more move in up to 4 pieces so that the CPU copy and the PCIe transfer overlap
+// frames of 2 MB and more are worked on in up to 4 row bands so that copies, transfers and kernels overlap
 static uint32_t stage_pieces(uint64_t bytes, uint32_t rows) {
-    const uint64_t p = std::min<uint64_t>(4, bytes >> 20);
+    static const uint64_t max_bands = [] {
+        const char* e = getenv("DIPSB_FRAME_BANDS");           // 1 .. 8, default 4 (measured: profiles/r01_sweeps.md)
+        const long v = e ? strtol(e, nullptr, 10) : 0;
+        return (uint64_t)(v >= 1 && v <= 8 ? v : 4);
+    }();
+    const uint64_t p = std::min<uint64_t>(max_bands, bytes >> 20);
     return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(p, rows));
-}
-static uint64_t piece_offset(uint64_t bytes, int k, int pieces) {
-    return k >= pieces ? bytes : (bytes / pieces * k) & ~uint64_t(4095);
 }
 
 // page-locked host memory (dipsb_host_alloc, cudaHostAlloc/cudaHostRegister, torch pin_memory): the copy engine can
@@ -782,61 +792,50 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     if (rc) return rc;
     rc = ensure_scalars(c, c->stream_index + 1);
     if (rc) return rc;
-    // the input slice is borrowed for the call only (frame_extractor.rs:224-226): it is either staged now or, when it is
-    // page-locked, uploaded straight from the caller's buffer and the upload awaited before this call returns
-    const bool in_direct = stride == row && host_pinned(px);
-    cudaStream_t up = overlap ? c->copy_stream : c->stream;
-    if (in_direct) {
-        CK(c, cudaMemcpyAsync(sl.d_in, px, fb, cudaMemcpyHostToDevice, up));
-    } else {
-        // staged in row bands: the upload of one band runs while the CPU copies the next (synchronous call only: in the
-        // pipelined call transfers already overlap the neighbouring frame's copies and the extra calls only cost)
-        const uint32_t pieces = overlap ? 1 : stage_pieces(fb, height);
-        for (uint32_t k = 0; k < pieces; ++k) {
-            const uint32_t r0 = (uint64_t)height * k / pieces, r1 = (uint64_t)height * (k + 1) / pieces;
-            host_copy2d(sl.h_in + (uint64_t)r0 * row, row, px + (uint64_t)r0 * stride, stride, row, r1 - r0);
-            CK(c, cudaMemcpyAsync(sl.d_in + (uint64_t)r0 * row, sl.h_in + (uint64_t)r0 * row, (uint64_t)(r1 - r0) * row, cudaMemcpyHostToDevice, up));
-        }
-    }
-    if (overlap) {
-        CK(c, cudaEventRecord(sl.ev_h2d, c->copy_stream));
-        CK(c, cudaStreamWaitEvent(c->stream, sl.ev_h2d, 0));
-    }
-    const uint64_t idx = c->stream_index;
-    CK(c, cudaMemsetAsync(c->d_sad + idx, 0, sizeof(uint64_t), c->stream));
-    CK(c, cudaMemsetAsync(c->d_cnt + idx, 0, sizeof(uint64_t), c->stream));
     const uint16_t* i2src = nullptr;
-    if (windowed(c)) {   // N4: spatially filtered intensity of this frame (dips_shader.wgsl:187)
+    if (windowed(c)) {   // N4: spatially filtered intensity of this frame (dips_shader.wgsl:187), computed below
         rc = ensure_i2_scratch(c);
-        if (rc) return rc;
-        rc = filtered_plane(c, sl.d_in, format, c->i2_scratch + g.npx);
         if (rc) return rc;
         i2src = c->i2_scratch + g.npx;
     }
+    // The input slice is borrowed for the call only (frame_extractor.rs:224-226): it is either staged now or, when it is
+    // page-locked, uploaded straight from the caller's buffer and the upload awaited before this call returns.
+    const bool in_direct = stride == row && host_pinned(px);
+    // The synchronous call works in row bands: upload of band k+1 (copy stream), kernels of band k (the context's stream)
+    // and read-back of band k-1 (read-back stream) run concurrently, and so do the CPU staging copies on either side.  In
+    // the pipelined call the neighbouring frames already overlap and the extra launches only cost; a spatial window
+    // needs the whole frame.
+    const uint32_t bands = (overlap || windowed(c)) ? 1u : stage_pieces(std::max<uint64_t>(fb, g.npx * 4), height);
+    const bool banded = bands > 1;
+    const bool side_upload = overlap || banded;
+    cudaStream_t up = side_upload ? c->copy_stream : c->stream;
+    cudaStream_t tail = banded ? c->out_stream : c->stream;
+    const uint64_t idx = c->stream_index;
+    CK(c, cudaMemsetAsync(c->d_sad + idx, 0, sizeof(uint64_t), c->stream));
+    CK(c, cudaMemsetAsync(c->d_cnt + idx, 0, sizeof(uint64_t), c->stream));
+
+    // ---- what this frame does to the state machine (once per frame; the launches below follow per band) ----
     bool establishes;
-    if (c->cfg.flavor == DIPSB_FLAVOR_FRAME0) {
+    const bool ring_flavour = c->cfg.flavor != DIPSB_FLAVOR_FRAME0;
+    FrameArgs f;
+    RingArgs r;
+    if (!ring_flavour) {
         establishes = !c->state_valid || c->snapshot_pending;
-        FrameArgs f;
         f.i2src = i2src;
         f.frame = sl.d_in; f.pitch = row; f.format = format; f.chan_byte = chan_byte_of(format, c->cfg.chroma);
         f.acc_sum = c->acc; f.acc_cnt = c->acc + g.n_elems;
         f.sad = c->d_sad + idx; f.cnt = c->d_cnt + idx;
         f.tau = c->cfg.threshold; f.colorize = c->cfg.colorize; f.filter = c->cfg.filter; f.sig_scalar = c->cfg.sigmoid_scalar;
+        f.state_in = c->state[c->state_cur];
         if (establishes) {
             // this frame becomes the reference: D = 0 for it, output is the input passed through (dips/src/lib.rs:241-245)
-            f.state_in = c->state[c->state_cur]; f.state_out = c->state[c->state_cur]; f.out_rgba = nullptr; f.accumulate = 0;
-            CK(c, launch_frame(g, f, c->stream));
-            if (want_rgba) CK(c, launch_passthrough_rgba(g, sl.d_in, row, format, sl.d_out, c->stream));
-            c->state_valid = true;
+            f.state_out = c->state[c->state_cur]; f.out_rgba = nullptr; f.accumulate = 0;
             c->snapshot_pending = false;
         } else {
-            f.state_in = c->state[c->state_cur];
             f.state_out = c->cfg.mode == DIPSB_MODE_PERFRAME ? c->state[c->state_cur] : nullptr;
             f.out_rgba = want_rgba ? sl.d_out : nullptr; f.accumulate = 1;
-            CK(c, launch_frame(g, f, c->stream));
         }
     } else {
-        RingArgs r;
         r.i2src = i2src;
         r.frame = sl.d_in; r.pitch = row; r.format = format; r.chan_byte = chan_byte_of(format, c->cfg.chroma);
         r.ring = c->ring; r.start = c->state[c->state_cur];
@@ -867,33 +866,62 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
             c->snapshot_pending = false;
             establishes = false;                                       // dips_alt always returns a computed frame
         }
-        CK(c, launch_ring(g, r, c->stream));
-        if (establishes && want_rgba) CK(c, launch_passthrough_rgba(g, sl.d_in, row, format, sl.d_out, c->stream));
-        c->state_valid = true;
     }
+    c->state_valid = true;
     sl.out_direct = want_rgba && out_direct != nullptr;
     sl.out_deferred = want_rgba && !sl.out_direct && defer_out;
     sl.out_pieces = 0;
-    if (sl.out_direct) {
-        CK(c, cudaMemcpyAsync(out_direct, sl.d_out, g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
-    } else if (want_rgba && !sl.out_deferred) {
-        // staged read-back in pieces, each with its own event: collect_frame copies piece k out while piece k+1 is in flight
-        const uint64_t bytes = g.npx * 4;
-        sl.out_pieces = overlap ? 1 : (int)stage_pieces(bytes, g.height);
-        for (int k = 0; k < sl.out_pieces; ++k) {
-            const uint64_t b0 = piece_offset(bytes, k, sl.out_pieces), b1 = piece_offset(bytes, k + 1, sl.out_pieces);
-            CK(c, cudaMemcpyAsync(sl.h_out + b0, sl.d_out + b0, b1 - b0, cudaMemcpyDeviceToHost, c->stream));
-            CK(c, cudaEventRecord(sl.ev_out[k], c->stream));
+    const bool readback = want_rgba && !sl.out_deferred;
+
+    for (uint32_t k = 0; k < bands; ++k) {
+        const uint32_t r0 = (uint32_t)((uint64_t)height * k / bands), r1 = (uint32_t)((uint64_t)height * (k + 1) / bands);
+        const uint64_t p0 = (uint64_t)r0 * width, p1 = (uint64_t)r1 * width;
+        // upload
+        const uint8_t* src = px + (uint64_t)r0 * stride;
+        if (!in_direct) {
+            host_copy2d(sl.h_in + (uint64_t)r0 * row, row, src, stride, row, r1 - r0);
+            src = sl.h_in + (uint64_t)r0 * row;
+        }
+        CK(c, cudaMemcpyAsync(sl.d_in + (uint64_t)r0 * row, src, (uint64_t)(r1 - r0) * row, cudaMemcpyHostToDevice, up));
+        if (side_upload) {
+            CK(c, cudaEventRecord(sl.ev_in[k], c->copy_stream));
+            CK(c, cudaStreamWaitEvent(c->stream, sl.ev_in[k], 0));
+        }
+        // kernels
+        if (windowed(c)) {
+            rc = filtered_plane(c, sl.d_in, format, c->i2_scratch + g.npx);
+            if (rc) return rc;
+        }
+        if (!ring_flavour) {
+            f.p_begin = p0; f.p_end = p1;
+            CK(c, launch_frame(g, f, c->stream));
+        } else {
+            r.p_begin = p0; r.p_end = p1;
+            CK(c, launch_ring(g, r, c->stream));
+        }
+        if (establishes && want_rgba) CK(c, launch_passthrough_rgba(g, sl.d_in, row, format, sl.d_out, c->stream, p0, p1));
+        // read-back
+        if (banded) {
+            CK(c, cudaEventRecord(sl.ev_k[k], c->stream));
+            CK(c, cudaStreamWaitEvent(tail, sl.ev_k[k], 0));
+        }
+        sl.out_off[k] = p0 * 4;
+        if (readback) {
+            uint8_t* dst = sl.out_direct ? out_direct : sl.h_out;
+            CK(c, cudaMemcpyAsync(dst + p0 * 4, sl.d_out + p0 * 4, (p1 - p0) * 4, cudaMemcpyDeviceToHost, tail));
+            if (!sl.out_direct) CK(c, cudaEventRecord(sl.ev_out[k], tail));   // collect_frame copies band k out behind it
         }
     }
-    CK(c, cudaMemcpyAsync(&sl.h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(&sl.h_stat[1], c->d_cnt + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaEventRecord(sl.ev_done, c->stream));
+    sl.out_off[bands] = g.npx * 4;
+    if (readback && !sl.out_direct) sl.out_pieces = (int)bands;
+    CK(c, cudaMemcpyAsync(&sl.h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, tail));
+    CK(c, cudaMemcpyAsync(&sl.h_stat[1], c->d_cnt + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, tail));
+    CK(c, cudaEventRecord(sl.ev_done, tail));
     sl.pending = true; sl.want_rgba = want_rgba; sl.idx = idx; sl.status = establishes ? DIPSB_NOT_READY : DIPSB_OK;
     c->stream_index = idx + 1;
     c->frames_processed += 1;
     c->scal_hi = std::max(c->scal_hi, idx + 1);
-    if (in_direct && overlap) CK(c, cudaEventSynchronize(sl.ev_h2d));   // the caller's buffer is free again on return
+    if (in_direct && overlap) CK(c, cudaEventSynchronize(sl.ev_in[0]));   // the caller's buffer is free again on return
     return DIPSB_OK;
 }
 
@@ -915,9 +943,8 @@ static int32_t collect_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, uint8_t* ou
     if (rb) return rb;
     const bool copy_out = out_rgba && sl.want_rgba && !sl.out_direct && !sl.out_deferred;
     if (copy_out && sl.out_pieces > 1) {
-        const uint64_t bytes = c->g.npx * 4;
         for (int k = 0; k < sl.out_pieces; ++k) {
-            const uint64_t b0 = piece_offset(bytes, k, sl.out_pieces), b1 = piece_offset(bytes, k + 1, sl.out_pieces);
+            const uint64_t b0 = sl.out_off[k], b1 = sl.out_off[k + 1];
             CK(c, cudaEventSynchronize(sl.ev_out[k]));
             host_copy2d(out_rgba + b0, b1 - b0, sl.h_out + b0, b1 - b0, b1 - b0, 1);
         }

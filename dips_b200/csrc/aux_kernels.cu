@@ -183,11 +183,11 @@ struct FrameK {
     const uint16_t* state_in; uint16_t* state_out; uint32_t* acc_sum; uint32_t* acc_cnt;
     unsigned long long* sad; unsigned long long* cnt; uint8_t* out_rgba;
     uint32_t tau, tile_px, threads; int geo_bpp, geo_groups; int accumulate, colorize, filter; float sig;
+    uint64_t p_begin, p_end;     // pixel range of this launch (a row band of the frame, or all of it)
 };
 __global__ void frame_kernel(const FrameK K) {
-    const uint64_t npx = (uint64_t)K.width * K.height;
     unsigned long long s = 0, c = 0;
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t p = K.p_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < K.p_end; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t y = (uint32_t)(p / K.width), x = (uint32_t)(p - (uint64_t)y * K.width);
         const uint32_t cur = K.i2src ? K.i2src[p] : intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
         const uint32_t ref = K.state_in[p];
@@ -228,6 +228,7 @@ struct RingK {
     uint16_t* ring; int n_slots, write_slot, grey_slot, compute_start, snapshot, median_is_max, do_diff;
     uint16_t* start; uint32_t* acc_sum; uint32_t* acc_cnt; unsigned long long* sad; unsigned long long* cnt; uint8_t* out_rgba;
     uint32_t tau, tile_px, threads; int geo_bpp, geo_groups, colorize, filter; float sig;
+    uint64_t p_begin, p_end;     // pixel range of this launch
 };
 __device__ __forceinline__ uint32_t upper_median4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {   // sorted[2]
     const uint32_t lo01 = min(a, b), hi01 = max(a, b), lo23 = min(c, d), hi23 = max(c, d);
@@ -236,7 +237,7 @@ __device__ __forceinline__ uint32_t upper_median4(uint32_t a, uint32_t b, uint32
 __global__ void ring_kernel(const RingK K) {
     const uint64_t npx = (uint64_t)K.width * K.height;
     unsigned long long s = 0, c = 0;
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t p = K.p_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < K.p_end; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t y = (uint32_t)(p / K.width), x = (uint32_t)(p - (uint64_t)y * K.width);
         const uint32_t raw = K.i2src ? K.i2src[p] : intensity2(K.frame + (uint64_t)y * K.pitch + (uint64_t)x * K.bpp, K.chan_byte);
         uint32_t v[4];                                              // compile-time indices only: stays in registers
@@ -330,13 +331,12 @@ __global__ void median4_planes_kernel(const uint16_t* __restrict__ planes, uint6
 }
 
 // warm-up passthrough of frame_callback (dips/src/lib.rs:241-245): input converted to RGBA8, alpha 255
-__global__ void passthrough_kernel(const uint8_t* __restrict__ frame, uint64_t pitch, uint32_t width, uint32_t height,
-                                   int format, uint8_t* __restrict__ out) {
-    const uint64_t npx = (uint64_t)width * height;
+__global__ void passthrough_kernel(const uint8_t* __restrict__ frame, uint64_t pitch, uint32_t width, uint64_t p_begin,
+                                   uint64_t p_end, int format, uint8_t* __restrict__ out) {
     const int bpp = (format == 0 || format == 2) ? 3 : 4;
     int ro, go, bo;
     chan_offsets(format, ro, go, bo);
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t p = p_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < p_end; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t y = (uint32_t)(p / width), x = (uint32_t)(p - (uint64_t)y * width);
         const uint8_t* px = frame + (uint64_t)y * pitch + (uint64_t)x * bpp;
         reinterpret_cast<uchar4*>(out)[p] = make_uchar4(px[ro], px[go], px[bo], bpp == 4 ? px[3] : 255);
@@ -440,7 +440,9 @@ cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) 
     K.sad = reinterpret_cast<unsigned long long*>(a.sad); K.cnt = reinterpret_cast<unsigned long long*>(a.cnt);
     K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp; K.geo_groups = g.groups;
     K.accumulate = a.accumulate; K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
-    frame_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(K);
+    K.p_begin = a.p_begin; K.p_end = a.p_end ? a.p_end : g.npx;
+    if (K.p_end <= K.p_begin) return cudaSuccess;
+    frame_kernel<<<grid_for(K.p_end - K.p_begin, g), kThreads, 0, s>>>(K);
     count_launch();
     return cudaGetLastError();
 }
@@ -469,13 +471,17 @@ cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s) {
     K.sad = reinterpret_cast<unsigned long long*>(a.sad); K.cnt = reinterpret_cast<unsigned long long*>(a.cnt);
     K.out_rgba = a.out_rgba; K.tau = a.tau; K.tile_px = g.tile_px; K.threads = g.threads; K.geo_bpp = g.bpp; K.geo_groups = g.groups;
     K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
-    ring_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(K);
+    K.p_begin = a.p_begin; K.p_end = a.p_end ? a.p_end : g.npx;
+    if (K.p_end <= K.p_begin) return cudaSuccess;
+    ring_kernel<<<grid_for(K.p_end - K.p_begin, g), kThreads, 0, s>>>(K);
     count_launch();
     return cudaGetLastError();
 }
 cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uint64_t pitch, int format, uint8_t* out,
-                                    cudaStream_t s) {
-    passthrough_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(frame, pitch, g.width, g.height, format, out);
+                                    cudaStream_t s, uint64_t p_begin, uint64_t p_end) {
+    if (!p_end) p_end = g.npx;
+    if (p_end <= p_begin) return cudaSuccess;
+    passthrough_kernel<<<grid_for(p_end - p_begin, g), kThreads, 0, s>>>(frame, pitch, g.width, p_begin, p_end, format, out);
     count_launch();
     return cudaGetLastError();
 }

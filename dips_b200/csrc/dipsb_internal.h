@@ -99,6 +99,7 @@ struct FrameArgs {
     int accumulate;              // 0: only prime/visual
     int colorize, filter;
     float sig_scalar;
+    uint64_t p_begin = 0, p_end = 0;   // pixel range of this launch (row band); p_end == 0: the whole frame
 };
 cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s);
 // reference-flavour temporal rings (N1): one frame against a ring of u16 I2 planes
@@ -116,13 +117,14 @@ struct RingArgs {
     uint16_t* start;             // start / snapshot plane (u16, I2 units, even values)
     uint32_t* acc_sum; uint32_t* acc_cnt; uint64_t* sad; uint64_t* cnt; uint8_t* out_rgba;
     uint32_t tau; int colorize, filter; float sig_scalar;
+    uint64_t p_begin = 0, p_end = 0;   // see FrameArgs
 };
 cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s);
 // N4: correct spatial median (window 3/5/7, zero padded) of a u16 intensity plane; upper median of 4 planes
 cudaError_t launch_spatial_median(const Geometry& g, const uint16_t* in, uint16_t* out, int window, cudaStream_t s);
 cudaError_t launch_median4_planes(const Geometry& g, const uint16_t* planes, uint16_t* out, cudaStream_t s);
 cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uint64_t pitch, int format,
-                                    uint8_t* out_rgba, cudaStream_t s);
+                                    uint8_t* out_rgba, cudaStream_t s, uint64_t p_begin = 0, uint64_t p_end = 0);
 cudaError_t launch_synth(uint8_t* dst, uint64_t first_frame, uint64_t n_frames, uint32_t w, uint32_t h, int bpp,
                          uint64_t seed, int profile, cudaStream_t s);
 // accumulator exchange format for the cross-GPU sum (see aux_kernels.cu)
