@@ -288,3 +288,48 @@ def test_pinned_buffer_lifecycle_and_errors():
     assert lib.dipsb_host_alloc(0, 16, None) == -1
     assert lib.dipsb_host_alloc(9999, 16, C.byref(p)) == -2 and not p.value
     assert lib.dipsb_host_free(None) == 0
+
+
+@pytest.mark.parametrize("flavor", [0, 1, 2])
+@pytest.mark.parametrize("w,h,fmt,pad", [(1920, 1080, 1, 0), (1280, 720, 2, 96), (1024, 601, 0, 0)])
+def test_large_frames_take_the_row_band_path_with_identical_results(oracle, flavor, w, h, fmt, pad):
+    """Frames of 2 MB and more go through the synchronous call in row bands (upload / kernels / read-back overlapped).
+    Same bytes as the whole-frame sequence of the pipelined call, with pageable and page-locked buffers, padded rows
+    included; for the frame-0 flavour the integers are also checked against the oracle."""
+    import dips_b200
+    n = 7
+    bpp = 3 if fmt in (0, 2) else 4
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    row, stride = w * bpp, w * bpp + pad
+    padded = np.zeros((n, h, stride), np.uint8)
+    padded[:, :, :row] = clip.reshape(n, h, row)
+    padded = padded.reshape(n, -1)
+    kw = dict(colorize=True, filt=dips_b200.FILTER_SIGMOID, flavor=flavor)
+    with dips_b200.Context(w, h, fmt, 0, 9, **kw) as ctx:                     # whole-frame sequence
+        want = []
+        for t in range(n):
+            rc, rgba, st = ctx.push_frame_pipelined(padded[t], stride=stride)
+            if t:
+                want.append((rc, rgba, st))
+        want.append(ctx.flush_frame())
+        acc_want = ctx.get_accumulators()
+    if flavor == 0:
+        ref = oracle.run_clip(clip, fmt, 0, 9)
+        assert np.array_equal(acc_want[0], ref.acc_sum) and np.array_equal(acc_want[1], ref.acc_cnt)
+        assert [s[2][1] for s in want] == [int(x) for x in ref.sad]
+    with dips_b200.PinnedBuffer(h * stride) as pin, dips_b200.PinnedBuffer(w * h * 4) as pout:
+        for pinned in (False, True):
+            if pinned and pad:
+                continue                                              # the direct path needs tightly packed rows anyway
+            with dips_b200.Context(w, h, fmt, 0, 9, **kw) as ctx:
+                for t in range(n):
+                    if pinned:
+                        pin.array[:] = padded[t]
+                        rc, rgba, st = ctx.push_frame(pin.array, stride=stride, out=pout.array)
+                    else:
+                        rc, rgba, st = ctx.push_frame(padded[t], stride=stride)
+                    assert (2 if rc == dips_b200.NOT_READY else 0) == want[t][0]
+                    assert st == want[t][2], (t, st, want[t][2])
+                    assert np.array_equal(rgba, want[t][1]), t
+                acc = ctx.get_accumulators()
+                assert np.array_equal(acc[0], acc_want[0]) and np.array_equal(acc[1], acc_want[1])
