@@ -69,6 +69,7 @@ struct dipsb_ctx {
     uint8_t* h_chunk[2] = {nullptr, nullptr};
     uint8_t* d_chunk[2] = {nullptr, nullptr};
     size_t chunk_bytes = 0;
+    uint8_t* d_repack = nullptr; size_t repack_bytes = 0;   // aligned, zero-padded copy of an unaligned device clip
     uint32_t tune_stages = 0, tune_tile_px = 0, tune_segments = 0, tune_regs = 0;
     int tune_kernel = -1;                      // -1: automatic (clip_kernel_ws whenever the tuning allows it)
     uint32_t last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -231,7 +232,7 @@ static void free_all(dipsb_ctx* c) {
         if (c->d_chunk[k]) cudaFree(c->d_chunk[k]);
     }
     cudaFree(c->acc); cudaFree(c->planar); cudaFree(c->d_sad); cudaFree(c->d_cnt); cudaFree(c->partials);
-    cudaFree(c->d_frame); cudaFree(c->d_rgba); cudaFree(c->ring); cudaFree(c->i2_scratch); cudaFree(c->xchg);
+    cudaFree(c->d_repack); cudaFree(c->d_frame); cudaFree(c->d_rgba); cudaFree(c->ring); cudaFree(c->i2_scratch); cudaFree(c->xchg);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_stat) cudaFreeHost(c->h_stat);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -576,7 +577,10 @@ static int32_t ensure_scalars(dipsb_ctx* c, uint64_t upto) {
 }
 
 // ---- batch ---------------------------------------------------------------------------------------------------------
-static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first) {
+// `zero_padded`: the rows come from the library's own re-packed buffers -- pitch a multiple of 16 and zero bytes between the
+// end of a frame and its pitch -- so the clip kernel may round its last bulk copy of a frame up to 16 bytes.
+static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first,
+                                  bool zero_padded = false) {
     const Geometry& g = c->g;
     if (n == 0) return DIPSB_OK;
     if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0) return fail(c, DIPSB_ERR_STATE, "run_clip: the ring flavours are streaming-only (dipsb_push_frame)");
@@ -587,6 +591,31 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
     if (stride < g.npx * g.bpp) return fail(c, DIPSB_ERR_INVALID, "run_clip: stride %llu smaller than a frame", (unsigned long long)stride);
     int32_t rc = ensure_scalars(c, first + n);
     if (rc) return rc;
+    // the TMA bulk copies of the clip kernel need 16-byte aligned addresses and sizes
+    // (a spatial window > 1 needs a filtered intensity plane per frame: per-frame kernels, not the clip kernel)
+    const uint64_t fb = g.npx * g.bpp;
+    const bool aligned = !windowed(c) && (((uintptr_t)d_frames | stride) & 15u) == 0 && ((fb & 15u) == 0 || (zero_padded && stride >= ((fb + 15) & ~15ull)));
+    if (!aligned && !windowed(c) && !zero_padded && n >= 2) {
+        // Unaligned base, pitch or frame size: re-pack through an aligned, zero-padded scratch (one extra read + write of
+        // the clip on the device) and stream that, instead of one small kernel per frame.
+        const uint64_t dpitch = (fb + 15) & ~15ull;
+        const uint64_t per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (256ull << 20) / dpitch));
+        if (c->repack_bytes < per_chunk * dpitch) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_repack); c->d_repack = nullptr; c->repack_bytes = 0;
+            CK(c, cudaMalloc(&c->d_repack, per_chunk * dpitch));
+            c->repack_bytes = per_chunk * dpitch;
+            CK(c, cudaMemsetAsync(c->d_repack, 0, c->repack_bytes, c->stream));
+        }
+        for (uint64_t done = 0; done < n;) {
+            const uint64_t m = std::min(per_chunk, n - done);
+            CK(c, cudaMemcpy2DAsync(c->d_repack, dpitch, d_frames + done * stride, stride, fb, m, cudaMemcpyDeviceToDevice, c->stream));
+            rc = run_clip_on_stream(c, c->d_repack, m, dpitch, first + done, true);
+            if (rc) return rc;
+            done += m;
+        }
+        return DIPSB_OK;
+    }
     if (!c->state_valid) {   // frame 0 of the call is the reference (overall) / has no predecessor (per-frame): D = 0
         if (windowed(c)) {
             rc = filtered_plane(c, d_frames, g.format, c->state[c->state_cur]);
@@ -596,9 +625,6 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         }
         c->state_valid = true;
     }
-    // the TMA bulk copies of the clip kernel need 16-byte aligned addresses and sizes
-    // (a spatial window > 1 needs a filtered intensity plane per frame: per-frame kernels, not the clip kernel)
-    const bool aligned = !windowed(c) && (((uintptr_t)d_frames | stride | (g.npx * g.bpp)) & 15u) == 0;
     const uint32_t tau = c->cfg.threshold;
     if (aligned) {
         const uint32_t segs = plan_segments(c, n);
@@ -634,7 +660,7 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         if (c->cfg.mode == DIPSB_MODE_PERFRAME) c->state_cur ^= 1;
         c->last_plan[1] = segs;
         c->last_plan[7] = 1;
-    } else {   // unaligned base/stride: per-frame kernel (TMA bulk copies need 16-byte alignment)
+    } else {   // spatial window, or a single unaligned frame: per-frame kernels
         CK(c, cudaMemsetAsync(c->d_sad + first, 0, n * sizeof(uint64_t), c->stream));
         CK(c, cudaMemsetAsync(c->d_cnt + first, 0, n * sizeof(uint64_t), c->stream));
         for (uint64_t k = 0; k < n; ++k) {
@@ -696,6 +722,8 @@ extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint
         for (int k = 0; k < 2; ++k) {
             CK(c, cudaMalloc(&c->d_chunk[k], cbytes));
             CK(c, cudaMallocHost(&c->h_chunk[k], cbytes));
+            CK(c, cudaMemsetAsync(c->d_chunk[k], 0, cbytes, c->copy_stream));   // row padding stays zero from here on
+            memset(c->h_chunk[k], 0, cbytes);
         }
         c->chunk_bytes = cbytes;
     }
@@ -715,7 +743,7 @@ extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint
         }
         CK(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
         CK(c, cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
-        int32_t rc = run_clip_on_stream(c, c->d_chunk[slot], m, dpitch, first + done);
+        int32_t rc = run_clip_on_stream(c, c->d_chunk[slot], m, dpitch, first + done, true);
         if (rc) return rc;
         CK(c, cudaEventRecord(c->ev_done[slot], c->stream));
         used[slot] = true;

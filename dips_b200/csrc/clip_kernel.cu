@@ -244,7 +244,9 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
     const uint64_t tile_first_px = (uint64_t)tile * P.tile_px;
     const uint64_t remain_px = P.npx - tile_first_px;
     const uint32_t valid_px = remain_px < P.tile_px ? (uint32_t)remain_px : P.tile_px;
-    const uint32_t valid_bytes = valid_px * BPP;
+    // rounded up to the 16-byte granule of a bulk copy: only a frame whose size is not a multiple of 16 is affected, and
+    // the host takes this kernel for such frames only from its own re-packed buffer, whose row padding is zero
+    const uint32_t valid_bytes = (valid_px * BPP + 15u) & ~15u;
 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_base + S * stage_bytes;   // full[S] then empty[S], 8 bytes each
@@ -268,7 +270,7 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
     if (warp >= P.active_warps) return;   // warps without pixels (tile_px small against the block); they never touch a barrier
 
     // ---- producer (thread 0): one TMA bulk copy per frame, re-arming the buffer freed one iteration ago ----------------
-    // (the host only takes this kernel when frame bytes, base and stride are multiples of 16, so valid_bytes is too)
+    // (the host only takes this kernel when base and stride are multiples of 16)
     const uint64_t tile_byte0 = tile_first_px * BPP;
     auto issue = [&](uint32_t it, uint32_t stage) {   // frame `first + it` of the call into buffer `stage`
         const uint8_t* src = P.frames + (uint64_t)(first + it) * P.stride + tile_byte0;
@@ -464,7 +466,7 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
     const uint64_t tile_first_px = (uint64_t)tile * P.tile_px;
     const uint64_t remain_px = P.npx - tile_first_px;
     const uint32_t valid_px = remain_px < P.tile_px ? (uint32_t)remain_px : P.tile_px;
-    const uint32_t valid_bytes = valid_px * BPP;
+    const uint32_t valid_bytes = (valid_px * BPP + 15u) & ~15u;   // see clip_kernel
 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_base + S * stage_bytes;

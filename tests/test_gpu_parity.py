@@ -92,7 +92,7 @@ def test_committed_golden_fixtures(torch_cuda, oracle, case):
     assert sha(clip) == case["clip_sha256"]
     acc_sum, acc_cnt, sad, cnt, state, plan = run_gpu(torch_cuda, clip, case["width"], case["height"], case["fmt"],
                                                       case["mode"], case["tau"], case["chroma"])
-    assert plan["tma_path"] == (clip.shape[1] % 16 == 0)     # unaligned frame pitch -> per-frame fallback kernel
+    assert plan["tma_path"] == (clip.shape[1] % 16 == 0 or case["n_frames"] >= 2)   # unaligned clips are re-packed
     assert [int(v) for v in sad] == case["sad"] and [int(v) for v in cnt] == case["cnt"]
     assert sha(acc_sum) == case["acc_sum_sha256"] and sha(acc_cnt) == case["acc_cnt_sha256"]
     assert sha(state) == case["state_sha256"]
@@ -193,27 +193,39 @@ def test_register_variants(torch_cuda, oracle, regs, fmt, mode):
     check(oracle, got, clip, fmt, mode, 20)
 
 
-def test_padded_stride_and_unaligned_fallback(torch_cuda, oracle):
+def test_padded_stride_and_unaligned_clips(torch_cuda, oracle):
+    """16-byte aligned base and pitch go straight to the clip kernel; anything else (odd pitch, odd base, frame size not a
+    multiple of 16 bytes) is re-packed on the device into an aligned, zero-padded scratch and streamed from there; a single
+    unaligned frame takes the per-frame kernel."""
     w, h, n = 112, 30, 7       # frame bytes are a multiple of 16 for both formats
     for fmt in (0, 1):
         clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
         pad = 48 + (-clip.shape[1]) % 16
-        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, stride_pad=pad)      # 16-byte aligned pitch: TMA path
-        assert got[5]["tma_path"]
-        check(oracle, got, clip, fmt, 1, 8)
-        got = run_gpu(torch_cuda, clip, w, h, fmt, 1, 8, stride_pad=5)        # unaligned pitch: per-frame kernel
+        for mode in (0, 1):
+            got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 8, stride_pad=pad)    # aligned pitch: direct
+            assert got[5]["tma_path"]
+            check(oracle, got, clip, fmt, mode, 8)
+            got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 8, stride_pad=5)      # unaligned pitch: re-packed
+            assert got[5]["tma_path"]
+            check(oracle, got, clip, fmt, mode, 8)
+            got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 8, offset=3)          # unaligned base: re-packed
+            assert got[5]["tma_path"]
+            check(oracle, got, clip, fmt, mode, 8)
+        got = run_gpu(torch_cuda, clip[:1], w, h, fmt, 0, 8, offset=3)             # one unaligned frame: per-frame kernel
         assert not got[5]["tma_path"]
-        check(oracle, got, clip, fmt, 1, 8)
-        got = run_gpu(torch_cuda, clip, w, h, fmt, 0, 8, offset=3)            # unaligned base
-        assert not got[5]["tma_path"]
-        check(oracle, got, clip, fmt, 0, 8)
-    # frame size not a multiple of 16 bytes (even with an aligned pitch): per-frame kernel
-    w, h = 37, 5
-    clip = oracle.synth_clip(n, w, h, 0, profile=oracle.SYNTH_UNIFORM)
-    pad = (-clip.shape[1]) % 16
-    got = run_gpu(torch_cuda, clip, w, h, 0, 0, 8, stride_pad=pad)
-    assert not got[5]["tma_path"]
-    check(oracle, got, clip, 0, 0, 8)
+        check(oracle, got, clip[:1], fmt, 0, 8)
+    # frame size not a multiple of 16 bytes: the last bulk copy of a frame is rounded up into the zero padding
+    for (w, h, fmt) in ((37, 5, 0), (37, 5, 1), (1001, 33, 0), (333, 3, 1), (2047, 129, 0)):
+        clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_UNIFORM)
+        assert clip.shape[1] % 16
+        for mode in (0, 1):
+            for kw in (dict(), dict(stride_pad=(-clip.shape[1]) % 16), dict(offset=1), dict(chunks=[0, 1, 2, 5, 7])):
+                got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 8, **kw)
+                check(oracle, got, clip, fmt, mode, 8)
+            for tuning in (dict(kernel=0), dict(kernel=0, regs=128), dict(segments=2)):
+                got = run_gpu(torch_cuda, clip, w, h, fmt, mode, 8, tuning=tuning)
+                assert got[5]["tma_path"]
+                check(oracle, got, clip, fmt, mode, 8)
 
 
 def test_config1_full_640x480x300(torch_cuda, oracle):
