@@ -139,7 +139,9 @@ int32_t dipsb_get_state_plane(dipsb_ctx *ctx, uint16_t *out);
  * Frames k = 0..n_frames-1 live at d_frames + k*frame_stride_bytes, tightly packed rows.  They are frames
  * first_frame_index .. first_frame_index+n_frames-1 of the logical clip; per-frame scalars are stored under
  * that index.  If the state plane is not valid it is primed from frame 0 of this call (so D of that frame is 0).
- * Asynchronous with respect to the host; ordered on the context's stream.
+ * Asynchronous with respect to the host; ordered on the context's stream.  Fastest when d_frames, frame_stride_bytes and
+ * width*height*bpp are multiples of 16 bytes (the clip is then streamed in place); any other layout is first re-packed on
+ * the device into an aligned scratch of at most 256 MB, chunk by chunk -- same results.
  */
 int32_t dipsb_run_clip_device(dipsb_ctx *ctx, const void *d_frames, uint64_t n_frames,
                               uint64_t frame_stride_bytes, uint64_t first_frame_index);
