@@ -597,7 +597,8 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
     const bool aligned = !windowed(c) && (((uintptr_t)d_frames | stride) & 15u) == 0 && ((fb & 15u) == 0 || (zero_padded && stride >= ((fb + 15) & ~15ull)));
     if (!aligned && !windowed(c) && !zero_padded && n >= 2) {
         // Unaligned base, pitch or frame size: re-pack through an aligned, zero-padded scratch (one extra read + write of
-        // the clip on the device) and stream that, instead of one small kernel per frame.
+        // the clip on the device; repack_kernel -- a 2-D cudaMemcpy with an odd pitch runs at a third of its rate) and
+        // stream that, instead of one small kernel per frame.
         const uint64_t dpitch = (fb + 15) & ~15ull;
         const uint64_t per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (256ull << 20) / dpitch));
         if (c->repack_bytes < per_chunk * dpitch) {
@@ -609,7 +610,7 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         }
         for (uint64_t done = 0; done < n;) {
             const uint64_t m = std::min(per_chunk, n - done);
-            CK(c, cudaMemcpy2DAsync(c->d_repack, dpitch, d_frames + done * stride, stride, fb, m, cudaMemcpyDeviceToDevice, c->stream));
+            CK(c, launch_repack(g, d_frames + done * stride, stride, fb, m, c->d_repack, dpitch, c->stream));
             rc = run_clip_on_stream(c, c->d_repack, m, dpitch, first + done, true);
             if (rc) return rc;
             done += m;

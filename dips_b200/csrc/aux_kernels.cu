@@ -330,6 +330,35 @@ __global__ void median4_planes_kernel(const uint16_t* __restrict__ planes, uint6
         out[p] = (uint16_t)upper_median4(planes[p], planes[npx + p], planes[2 * npx + p], planes[3 * npx + p]);
 }
 
+// Re-pack of an unaligned device clip (odd base, pitch or frame size) into rows of a 16-byte pitch whose padding is zero:
+// one thread per 16-byte output chunk, source read as aligned 32-bit words and realigned with funnel shifts.
+__global__ void repack_kernel(const uint8_t* __restrict__ src, uint64_t stride, uint64_t fb, uint64_t n_frames,
+                              uint8_t* __restrict__ dst, uint64_t dpitch) {
+    const uint64_t chunks = dpitch / 16, total = chunks * n_frames;
+    const uint8_t* end = src + (n_frames - 1) * stride + fb;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = i / chunks, o = (i - k * chunks) * 16;
+        const uintptr_t a = (uintptr_t)(src + k * stride + o);
+        const uint32_t* a4 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+        uint32_t w[5];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) w[t] = (reinterpret_cast<const uint8_t*>(a4 + t) < end) ? __ldg(a4 + t) : 0u;
+        uint32_t v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = __funnelshift_r(w[t], w[t + 1], sh);
+        const uint64_t remain = fb > o ? fb - o : 0;             // bytes of this chunk that belong to the frame
+        if (remain < 16) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint64_t vb = remain > 4u * t ? remain - 4u * t : 0;
+                v[t] &= vb >= 4 ? 0xFFFFFFFFu : (vb == 0 ? 0u : (1u << (8u * (uint32_t)vb)) - 1u);
+            }
+        }
+        *reinterpret_cast<uint4*>(dst + k * dpitch + o) = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 // warm-up passthrough of frame_callback (dips/src/lib.rs:241-245): input converted to RGBA8, alpha 255
 __global__ void passthrough_kernel(const uint8_t* __restrict__ frame, uint64_t pitch, uint32_t width, uint64_t p_begin,
                                    uint64_t p_end, int format, uint8_t* __restrict__ out) {
@@ -482,6 +511,15 @@ cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uin
     if (!p_end) p_end = g.npx;
     if (p_end <= p_begin) return cudaSuccess;
     passthrough_kernel<<<grid_for(p_end - p_begin, g), kThreads, 0, s>>>(frame, pitch, g.width, p_begin, p_end, format, out);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_repack(const Geometry& g, const uint8_t* src, uint64_t stride, uint64_t fb, uint64_t n_frames, uint8_t* dst,
+                          uint64_t dpitch, cudaStream_t s) {
+    if (!n_frames) return cudaSuccess;
+    uint64_t b = (dpitch / 16 * n_frames + kThreads - 1) / kThreads;
+    const uint64_t cap = (uint64_t)(g.num_sms ? g.num_sms : 148) * 32;
+    repack_kernel<<<(int)(b > cap ? cap : b), kThreads, 0, s>>>(src, stride, fb, n_frames, dst, dpitch);
     count_launch();
     return cudaGetLastError();
 }

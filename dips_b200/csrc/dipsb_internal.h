@@ -125,6 +125,8 @@ cudaError_t launch_spatial_median(const Geometry& g, const uint16_t* in, uint16_
 cudaError_t launch_median4_planes(const Geometry& g, const uint16_t* planes, uint16_t* out, cudaStream_t s);
 cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uint64_t pitch, int format,
                                     uint8_t* out_rgba, cudaStream_t s, uint64_t p_begin = 0, uint64_t p_end = 0);
+cudaError_t launch_repack(const Geometry& g, const uint8_t* src, uint64_t stride, uint64_t fb, uint64_t n_frames, uint8_t* dst,
+                          uint64_t dpitch, cudaStream_t s);
 cudaError_t launch_synth(uint8_t* dst, uint64_t first_frame, uint64_t n_frames, uint32_t w, uint32_t h, int bpp,
                          uint64_t seed, int profile, cudaStream_t s);
 // accumulator exchange format for the cross-GPU sum (see aux_kernels.cu)
