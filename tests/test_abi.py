@@ -161,3 +161,13 @@ def test_host_copy_pool_is_exact_and_thread_safe():
     src = np.zeros(64, np.uint8)
     assert lib.dipsb_host_copy2d(src.ctypes.data, 4, src.ctypes.data, 8, 8, 2) == -1       # pitch < row
     assert lib.dipsb_host_copy2d(None, 0, None, 0, 0, 0) == 0                              # empty copy
+
+
+def test_tools_and_entry_points_compile():
+    """Every helper script that travels to the GPU box at least parses (they only run there)."""
+    import glob
+    import py_compile
+    files = glob.glob(os.path.join(ROOT, "tools", "*.py")) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    assert len(files) >= 6
+    for f in files:
+        py_compile.compile(f, doraise=True)
