@@ -103,9 +103,9 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("mode", [sharding.MODE_OVERALL, sharding.MODE_PERFRAME])
-def test_two_rank_sharding_matches_single_rank(mode, tmp_path):
-    world = 2
+def test_multi_rank_sharding_matches_single_rank(mode, world, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), mode, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
 
