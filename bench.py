@@ -47,6 +47,9 @@ def parse_args():
     p.add_argument("--mode", choices=["overall", "per-frame"], default=None)
     p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--exchange", choices=["replicated", "collective"], default="replicated",
+                   help="what a shard needs before its first frame (the clip's frame 0 / the one-frame halo): replicated = "
+                        "each shard carries its own copy, loaded with it; collective = broadcast / send-recv every clip")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--stages", type=int, default=0)
     p.add_argument("--tile-px", type=int, default=0)
@@ -202,6 +205,9 @@ def config_of(wl, args, world, sample_note=None):
     cfg = {"workload": desc, "width": w, "height": h, "format": FMT_NAMES[fmt], "mode": MODE_NAMES[mode],
            "threshold_i2": tau, "frames_per_gpu": frames, "frames_total": frames * world, "seed": hex(SEED),
            "profile": "scene", "parallelism": f"frame-shard x{world}",
+           "exchange": ("none (single GPU)" if world == 1 else
+                        ("reference / halo frame replicated with each shard at load, " if args.exchange == "replicated" else
+                         "reference plane broadcast / halo send-recv per clip, ") + "one packed accumulator all-reduce per clip"),
            "l2": "clip per GPU >> 126 MB L2 (inputs larger than L2)"}
     if sample_note:
         cfg["sample"] = sample_note
@@ -264,7 +270,17 @@ def main():
     if args.stages or args.tile_px or args.segments or args.regs:
         ctx.set_tuning(args.stages, args.tile_px, args.segments, args.regs)
     ctx.set_stream(stream.cuda_stream)
-    engine = sharding.GpuShardEngine(ctx, clip, torch, total_frames=world * frames)
+    reference = None
+    replicated = world > 1 and args.exchange == "replicated"          # the same on every rank
+    if replicated and rank > 0:
+        # the shard's copy of the frame it needs before its first one: the clip's frame 0 (overall) or its predecessor
+        # t0-1 (per-frame); part of the resident input, like the shard itself
+        ref_frame = torch.empty(fb, dtype=torch.uint8, device=dev)
+        dips_b200.synth_fill_device(local_rank, ref_frame.data_ptr(), 0 if mode == sharding.MODE_OVERALL else t0_frame - 1,
+                                    1, w, h, fmt, SEED, dips_b200.SYNTH_SCENE, stream.cuda_stream)
+        torch.cuda.synchronize()
+        reference = {mode: ref_frame}
+    engine = sharding.GpuShardEngine(ctx, clip, torch, total_frames=world * frames, replicated=replicated, reference=reference)
 
     phase_events = []
 
@@ -332,6 +348,12 @@ def main():
         dist.all_reduce(tot)          # per-frame scalars are per shard; the all-reduced maps must add up to all of them
     assert int(acc_sum.astype(np.uint64).sum()) == int(tot[0]) and int(acc_cnt.astype(np.uint64).sum()) == int(tot[1]), \
         "checksum of checksums failed"
+    if world > 1 and mode == sharding.MODE_OVERALL:   # every rank differenced against the same reference plane
+        plane = ctx.get_state_plane().astype(np.int64)
+        sig = torch.tensor([int(plane.sum()), int((plane * (np.arange(plane.size) % 65521 + 1)).sum())], dtype=torch.int64, device=dev)
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        assert all(bool((x == sigs[0]).all()) for x in sigs), "reference planes differ between ranks"
 
     # ---- roofline of the dominant kernel --------------------------------------------------------------------------
     alg_bytes = frames * fb + npx * 2 + npx * 8      # every input byte once + reference plane + accumulators once

@@ -20,6 +20,12 @@ optional:
     after_reduce() -> None       called after the all-reduce (unpacks an exchange format into the accumulators)
     state_tensor() -> tensor     the reference plane itself (as bytes); when present it is broadcast instead of raw frame 0
     mark_primed() -> None        the state plane was filled by the broadcast
+    replicated (attribute) + local_reference(mode) -> tensor | None
+                                 `replicated` is True when the shards carry their own copy of what they need before their
+                                 first frame -- the clip's frame 0 (overall) or frame t0-1 (per-frame halo), loaded with the
+                                 shard.  Then there is no exchange before the pass at all: every rank > 0 primes from
+                                 local_reference(mode) and starts at once (rank 0 needs nothing).  The attribute must have
+                                 the same value on every rank -- it decides whether the ranks meet in a collective.
 """
 from __future__ import annotations
 
@@ -47,6 +53,13 @@ class ShardEngine(Protocol):
 def exchange_reference(engine: ShardEngine, mode: int, rank: int, world: int, dist=None, group=None) -> None:
     """Give every rank what it needs before its first frame (no-op for a single rank)."""
     if world == 1:
+        return
+    if getattr(engine, "replicated", False):      # same on every rank by contract: nobody enters a collective here
+        ref = engine.local_reference(mode)
+        if ref is not None:
+            engine.prime(ref)
+        elif rank != 0:                            # rank 0 starts the clip: its pass primes itself from its first frame
+            raise ValueError("replicated shard of rank %d has no reference / halo frame for mode %d" % (rank, mode))
         return
     if mode == MODE_OVERALL and hasattr(engine, "state_tensor"):
         # rank 0 builds the reference plane and broadcasts it (2 B/px instead of the raw frame's 3-4 B/px)
@@ -95,11 +108,16 @@ class _DeviceBuffer:
 class GpuShardEngine:
     """ShardEngine over a dips_b200.Context and a device-resident shard (a torch uint8 tensor [n, frame_bytes])."""
 
-    def __init__(self, ctx, frames, torch, total_frames=None):
+    def __init__(self, ctx, frames, torch, total_frames=None, replicated=False, reference=None):
         """total_frames: frames of the whole clip over all ranks -- enables the packed accumulator exchange
-        (dipsb_pack_accumulators_device); None exchanges the two u32 planes as they are."""
+        (dipsb_pack_accumulators_device); None exchanges the two u32 planes as they are.
+        replicated: the shards carry their own reference / halo frame (pass the SAME value on every rank); then
+        reference = {mode: device tensor} holds this shard's copy of frame 0 (MODE_OVERALL) / frame t0-1 (MODE_PERFRAME)
+        on every rank but 0.  replicated=False: broadcast / halo exchange per clip."""
         self.ctx, self.frames, self.torch = ctx, frames, torch
         self.total_frames = total_frames
+        self.replicated = bool(replicated)
+        self.reference = reference
         self._buf = None
         self._views = {}
 
@@ -116,6 +134,9 @@ class GpuShardEngine:
 
     def prime(self, frame) -> None:
         self.ctx.prime_device(frame.data_ptr())
+
+    def local_reference(self, mode):
+        return None if not self.reference else self.reference.get(mode)
 
     def run(self, first_frame_index: int) -> None:
         self.ctx.run_clip_device(self.frames.data_ptr(), self.frames.shape[0], self.frames.stride(0), first_frame_index)

@@ -73,7 +73,35 @@ class OracleEngine:
         self.reduced = True
 
 
-def _worker(rank, world, port, mode, tmpdir):
+class ReplicatedEngine(OracleEngine):
+    """The shard carries its own reference / halo frame (replicated at load time): no exchange before the pass."""
+
+    replicated = True
+
+    def __init__(self, O, clip, t0, t1, fmt, mode, tau):
+        super().__init__(O, clip[t0:t1], fmt, mode, tau)
+        self._ref = None if t0 == 0 else torch.from_numpy(clip[0] if mode == sharding.MODE_OVERALL else clip[t0 - 1])
+
+    def local_reference(self, mode):
+        return self._ref
+
+    def state_tensor(self):
+        raise AssertionError("a replicated shard must not take part in a broadcast")
+
+    def frame_buffer(self):
+        raise AssertionError("a replicated shard must not take part in a halo exchange")
+
+
+class NotReplicatedEngine(OracleEngine):
+    """Has the optional method but is not in replicated mode (dips_b200.sharding.GpuShardEngine without a reference, as
+    bench.py's end-to-end leg builds it): every rank, rank 0 included, must take the collective path."""
+    replicated = False
+
+    def local_reference(self, mode):
+        return None
+
+
+def _worker(rank, world, port, mode, tmpdir, replicated=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -82,14 +110,18 @@ def _worker(rank, world, port, mode, tmpdir):
         fmt, tau, n, w, h = O.FMT_RGB8, 12, 11, 24, 10
         clip = O.synth_clip(n, w, h, fmt, profile=O.SYNTH_SCENE)
         t0, t1 = sharding.shard_range(rank, world, n)
-        eng = OracleEngine(O, clip[t0:t1], fmt, mode, tau)
+        if replicated == "off":
+            eng = NotReplicatedEngine(O, clip[t0:t1], fmt, mode, tau)
+            replicated = False
+        else:
+            eng = ReplicatedEngine(O, clip, t0, t1, fmt, mode, tau) if replicated else OracleEngine(O, clip[t0:t1], fmt, mode, tau)
         sharding.run_sharded(eng, mode, t0, rank, world, dist)
         whole = O.run_clip(clip, fmt, mode, tau)
         npx = w * h
         assert np.array_equal(eng.acc[:npx].view(np.uint32), whole.acc_sum), "acc_sum differs after all-reduce"
         assert np.array_equal(eng.acc[npx:].view(np.uint32), whole.acc_cnt), "acc_cnt differs after all-reduce"
         assert np.array_equal(eng.sad, whole.sad[t0:t1]) and np.array_equal(eng.cnt, whole.cnt[t0:t1])
-        assert eng.reduced and eng.primed_by_broadcast == (mode == sharding.MODE_OVERALL and rank > 0)
+        assert eng.reduced and eng.primed_by_broadcast == (mode == sharding.MODE_OVERALL and rank > 0 and not replicated)
         open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -108,6 +140,28 @@ def _free_port():
 def test_multi_rank_sharding_matches_single_rank(mode, world, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), mode, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+@pytest.mark.parametrize("mode", [sharding.MODE_OVERALL, sharding.MODE_PERFRAME])
+def test_replicated_reference_needs_no_exchange_before_the_pass(mode, tmp_path):
+    world = 3
+    mp.spawn(_worker, args=(world, _free_port(), mode, str(tmp_path), True), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+@pytest.mark.parametrize("mode", [sharding.MODE_OVERALL, sharding.MODE_PERFRAME])
+def test_engine_with_the_optional_method_but_not_replicated_still_meets_in_the_collective(mode, tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), mode, str(tmp_path), "off"), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_gpu_shard_engine_defaults_to_the_collective_exchange():
+    """bench.py's end-to-end engine is a GpuShardEngine built without `replicated`: it must not skip the broadcast."""
+    eng = sharding.GpuShardEngine(ctx=None, frames=None, torch=None, total_frames=10)
+    assert eng.replicated is False and eng.local_reference(sharding.MODE_OVERALL) is None
+    eng = sharding.GpuShardEngine(ctx=None, frames=None, torch=None, total_frames=10, replicated=True, reference={0: "x"})
+    assert eng.replicated is True and eng.local_reference(0) == "x" and eng.local_reference(1) is None
 
 
 def test_single_rank_needs_no_dist():
