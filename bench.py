@@ -251,7 +251,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import datetime
+        # a rank that never arrives at a collective should end the run after minutes, not hold the box for the default 10+
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(minutes=4))
     bpp = dips_b200.bytes_per_pixel(fmt)
     npx, fb = w * h, w * h * bpp
     stream = torch.cuda.Stream(device=dev)       # one explicit stream for our kernels, torch copies and NCCL ordering
