@@ -1,0 +1,40 @@
+"""CPU tests of bench.py's reference arm (the only arm that runs without a GPU): one JSON line on stdout with the contract's
+keys, under plain python and under torchrun with two ranks (rank 0 prints, the other exits 0 without work)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
+
+
+def _check(line, n_gpus):
+    d = json.loads(line)
+    assert KEYS <= set(d), KEYS - set(d)
+    assert d["impl"] == "reference" and d["metric"] == "frames/sec" and d["unit"] == "frames/s" and d["n_gpus"] == n_gpus
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["dtype"] == "u8" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.strip()]
+    assert len(lines) == 1, r.stdout
+    _check(lines[0], 1)
+
+
+def test_reference_arm_under_torchrun_two_ranks():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", "bench.py", "--impl", "reference", "--gpus", "2", "--workload", "c1", "--steps", "1",
+           "--warmup", "1"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout
+    _check(lines[0], 2)
