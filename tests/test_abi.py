@@ -171,3 +171,41 @@ def test_tools_and_entry_points_compile():
     assert len(files) >= 6
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_planner_invariants_on_random_geometries():
+    """Host-only planner, 400 random frame sizes and SM counts: the plan always covers the frame, fits a block, fits the
+    SM's registers and shared memory, and the tile-order index (host restatement below) is a bijection onto the
+    accumulator elements for a sample of them."""
+    import numpy as np
+    from dips_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(20261018)
+    for i in range(400):
+        w = int(rng.integers(1, 8193)) if i % 3 else int(rng.integers(1, 513)) * 16
+        h = int(rng.integers(1, 4321)) if i % 5 else int(rng.integers(1, 65))
+        fmt = int(rng.integers(0, 4))
+        sms = int(rng.choice([148, 148, 148, 132, 74, 8]))
+        out = (ctypes.c_uint32 * 8)()
+        assert L.dipsb_plan_query(w, h, fmt, sms, ctypes.byref(out)) == 0, (w, h, fmt, sms)
+        tiles, threads, stages, occ, tile_px = out[0], out[2], out[3] & 0xFFFF, out[4], out[5]
+        block = threads + 32 * (out[3] >> 16)
+        smem, regs = out[6] & 0xFFFFFF, out[6] >> 24
+        npx = w * h
+        assert tile_px % 16 == 0 and tile_px >= 16 and tiles * tile_px >= npx > (tiles - 1) * tile_px
+        assert threads % 32 == 0 and 32 <= block <= 1024 and tile_px <= 16 * threads
+        assert 2 <= stages <= 8 and occ >= 1 and regs in (64, 72)
+        assert occ * block * regs <= 65536 and occ * (smem + 1024) <= 227 * 1024
+        assert out[7] >= 1 and out[7] * 32 <= threads          # active warps
+        if i % 20 == 0 and npx <= 1 << 18:                      # the accumulator order is a bijection
+            bpp = 3 if fmt in (0, 2) else 4
+            p = np.arange(npx, dtype=np.int64)
+            tile, q = p // tile_px, p % tile_px
+            if bpp == 3:
+                grp = q // 16
+                thread, k = grp % threads, (grp // threads) * 16 + q % 16
+            else:
+                quad = q // 4
+                thread, k = quad % threads, 4 * (quad // threads) + q % 4
+            idx = tile * (threads * 16) + k * threads + thread
+            assert k.max() < 16 and idx.max() < tiles * threads * 16 and np.unique(idx).size == npx
