@@ -155,6 +155,9 @@ int32_t dipsb_run_clip_host(dipsb_ctx *ctx, const uint8_t *frames, uint64_t n_fr
  * px: host frame, `stride` bytes per row.  out_rgba (nullable): width*height*4 bytes, receives the reference's
  * visual frame for this input (RGBA8, alpha 255).  stats (nullable).  Returns DIPSB_NOT_READY and copies the
  * input through (converted to RGBA8) while there is no reference yet, as frame_callback does during warm-up.
+ * Both buffers are borrowed for the call only.  Ordinary host memory is staged through page-locked buffers by the threaded
+ * host copy; page-locked buffers (dipsb_host_alloc) are read and written by the copy engine directly.  Frames of 2 MB and
+ * more are processed in up to 4 row bands (DIPSB_FRAME_BANDS) so that upload, kernels and read-back overlap.
  */
 int32_t dipsb_push_frame(dipsb_ctx *ctx, const uint8_t *px, uint32_t width, uint32_t height, uint32_t stride,
                          int32_t format, uint8_t *out_rgba, dipsb_frame_stats *stats);
