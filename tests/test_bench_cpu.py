@@ -29,9 +29,16 @@ def test_reference_arm_prints_one_json_line():
     _check(lines[0], 1)
 
 
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_reference_arm_under_torchrun_two_ranks():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29577", "bench.py", "--impl", "reference", "--gpus", "2", "--workload", "c1", "--steps", "1",
+           "--master-port", str(_free_port()), "bench.py", "--impl", "reference", "--gpus", "2", "--workload", "c1", "--steps", "1",
            "--warmup", "1"]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
