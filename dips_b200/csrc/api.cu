@@ -69,6 +69,8 @@ struct dipsb_ctx {
     uint8_t* h_chunk[2] = {nullptr, nullptr};
     uint8_t* d_chunk[2] = {nullptr, nullptr};
     size_t chunk_bytes = 0;
+    bool chunk_used[2] = {false, false};       // ev_copy / ev_done of the slot were recorded (possibly by an earlier call)
+    int chunk_slot = 0;                        // slot the next chunk goes to
     uint8_t* d_repack = nullptr; size_t repack_bytes = 0;   // aligned, zero-padded copy of an unaligned device clip
     uint32_t tune_stages = 0, tune_tile_px = 0, tune_segments = 0, tune_regs = 0;
     int tune_kernel = -1;                      // -1: automatic (clip_kernel_ws whenever the tuning allows it)
@@ -718,6 +720,7 @@ extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint
             if (c->h_chunk[k]) cudaFreeHost(c->h_chunk[k]);
             if (c->d_chunk[k]) cudaFree(c->d_chunk[k]);
             c->h_chunk[k] = nullptr; c->d_chunk[k] = nullptr;
+            c->chunk_used[k] = false;
         }
         c->chunk_bytes = 0;
         for (int k = 0; k < 2; ++k) {
@@ -728,17 +731,19 @@ extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint
         }
         c->chunk_bytes = cbytes;
     }
-    bool used[2] = {false, false};
+    // The slot flags live in the context: a second call without a synchronisation in between (reset + run loops, a long
+    // video fed in several calls) must still wait for the kernels and copies of the previous call that use the same slot.
     uint64_t done = 0;
-    int slot = 0;
+    int slot = c->chunk_slot;
+    int last_slot = -1;
     while (done < n) {
         const uint64_t m = std::min(per_chunk, n - done);
         const uint8_t* src = frames + done * stride;
-        if (used[slot]) CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));   // kernels finished with d_chunk[slot]
+        if (c->chunk_used[slot]) CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));   // kernels finished with d_chunk[slot]
         if (pinned) {
             CK(c, cudaMemcpy2DAsync(c->d_chunk[slot], dpitch, src, stride, fb, m, cudaMemcpyHostToDevice, c->copy_stream));
         } else {
-            if (used[slot]) CK(c, cudaEventSynchronize(c->ev_copy[slot]));                 // previous H2D from h_chunk[slot] done
+            if (c->chunk_used[slot]) CK(c, cudaEventSynchronize(c->ev_copy[slot]));        // previous H2D from h_chunk[slot] done
             host_copy2d(c->h_chunk[slot], dpitch, src, stride, fb, m);
             CK(c, cudaMemcpyAsync(c->d_chunk[slot], c->h_chunk[slot], m * dpitch, cudaMemcpyHostToDevice, c->copy_stream));
         }
@@ -747,10 +752,15 @@ extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint
         int32_t rc = run_clip_on_stream(c, c->d_chunk[slot], m, dpitch, first + done, true);
         if (rc) return rc;
         CK(c, cudaEventRecord(c->ev_done[slot], c->stream));
-        used[slot] = true;
+        c->chunk_used[slot] = true;
+        last_slot = slot;
         slot ^= 1;
         done += m;
     }
+    c->chunk_slot = slot;
+    // the caller's frames are borrowed for the call only: a page-locked clip is read by the copy engine directly, so wait
+    // for the last upload (the earlier ones precede it on the copy stream); the kernels of the last chunk stay asynchronous
+    if (pinned && last_slot >= 0) CK(c, cudaEventSynchronize(c->ev_copy[last_slot]));
     return DIPSB_OK;
 }
 
@@ -1076,6 +1086,10 @@ extern "C" int32_t dipsb_pack_accumulators_device(dipsb_ctx* c, uint64_t total_f
     if (!c || !d_packed || !n_words || total_frames == 0) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     const Geometry& g = c->g;
+    if (total_frames < c->frames_processed)
+        return fail(c, DIPSB_ERR_INVALID, "pack_accumulators: total_frames %llu < the %llu frames this context accumulated since its last reset "
+                    "(it must bound every frame accumulated on ALL ranks, or the packed fields carry into each other)",
+                    (unsigned long long)total_frames, (unsigned long long)c->frames_processed);
     // after the sum over all ranks: acc_sum <= 510*total_frames, acc_cnt <= total_frames (every frame counts at most once)
     const int sum_bits = bit_length(510ull * total_frames), cnt_bits = bit_length(total_frames);
     int layout;

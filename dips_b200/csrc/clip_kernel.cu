@@ -641,7 +641,7 @@ __global__ void stream_probe_kernel(const __grid_constant__ KParams P, int bpp) 
     const uint32_t S = P.stages, stage_bytes = P.stage_bytes, nwarps = blockDim.x >> 5;
     const uint64_t tile_first_px = (uint64_t)blockIdx.x * P.tile_px;
     const uint64_t remain_px = P.npx - tile_first_px;
-    const uint32_t valid_bytes = (remain_px < P.tile_px ? (uint32_t)remain_px : P.tile_px) * (uint32_t)bpp;
+    const uint32_t valid_bytes = ((remain_px < P.tile_px ? (uint32_t)remain_px : P.tile_px) * (uint32_t)bpp + 15u) & ~15u;   // as the clip kernels
     const uint32_t smem_base = smem_u32(smem), full_bar = smem_base + S * stage_bytes, empty_bar = full_bar + 8u * S;
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) { mbar_init(full_bar + 8u * s, 1); mbar_init(empty_bar + 8u * s, nwarps); }

@@ -115,6 +115,11 @@ class GpuShardEngine:
         reference = {mode: device tensor} holds this shard's copy of frame 0 (MODE_OVERALL) / frame t0-1 (MODE_PERFRAME)
         on every rank but 0.  replicated=False: broadcast / halo exchange per clip."""
         self.ctx, self.frames, self.torch = ctx, frames, torch
+        # torch.distributed issues its collectives on torch's current stream; a Context launches on a private stream by
+        # default.  Put the context on the stream that is current now, so that prime / clip kernel / pack precede the
+        # collective and unpack / the next reset follow it.  Callers that switch streams later must call ctx.set_stream too.
+        if getattr(frames, "is_cuda", False):
+            ctx.set_stream(torch.cuda.current_stream(frames.device).cuda_stream)
         self.total_frames = total_frames
         self.replicated = bool(replicated)
         self.reference = reference

@@ -146,7 +146,9 @@ int32_t dipsb_get_state_plane(dipsb_ctx *ctx, uint16_t *out);
 int32_t dipsb_run_clip_device(dipsb_ctx *ctx, const void *d_frames, uint64_t n_frames,
                               uint64_t frame_stride_bytes, uint64_t first_frame_index);
 /* Same from pageable or pinned HOST memory: chunks are staged through pinned buffers and uploaded on a copy
- * stream overlapped with the kernels of the previous chunk.  Returns after the last kernel was issued. */
+ * stream overlapped with the kernels of the previous chunk.  Returns after the last kernel was issued; `frames` is borrowed
+ * for the call only (ordinary memory has been staged, a page-locked clip has been uploaded when the call returns).  Calls
+ * may follow each other without a synchronisation in between: the staging slots are guarded across calls. */
 int32_t dipsb_run_clip_host(dipsb_ctx *ctx, const uint8_t *frames, uint64_t n_frames,
                             uint64_t frame_stride_bytes, uint64_t first_frame_index);
 
