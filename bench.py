@@ -4,16 +4,23 @@
     python bench.py --gpus N --steps K --warmup W            our arm (N>1 under torch.distributed.run)
     python bench.py --impl reference --gpus N ...            CPU arm: the oracle port on the host cores (rank 0 only)
 
-A step = one pass of the hot path over one synthetic clip (default workload: BASELINE.json configs[1], 1920x1080 RGB8,
-1800 frames per GPU, overall difference + threshold).  `value` = frames/s over all GPUs with the clip resident in HBM;
-`e2e` = the same through dipsb_run_clip_host from pinned HOST memory (H2D inside the timed region, results read back).
-Weak scaling: every rank owns an 1800-frame shard of an N*1800-frame clip; frame 0 is broadcast (overall mode) or the
-one-frame halo is sent to the next rank (per-frame mode) and the accumulators are all-reduced once per step (NCCL).
+Headline workload (BASELINE.json configs[3], the configuration the target sentence is quoted on): ONE synthetic
+3840x2160 RGBx8 clip of 3600 frames, overall difference + threshold, frame-sharded over the N GPUs -- strong scaling: rank r
+owns frames dipsb_shard_range(3600, N, r); at N=1 the whole 119.4 GB clip is resident on the one GPU.  A step = one pass
+over the clip: dipsb_reset + dipsb_run_clip_sharded_device, i.e. inside the library and inside the timed region: rank 0
+builds the reference plane from frame 0 and ncclBroadcast's it, every rank runs its shard through the clip kernel, and the
+per-pixel accumulators are combined by the library's reduce-scatter over peer memory (NVLink).  `value` = frames/s of the
+whole job with the clip resident in HBM; `e2e` = the same through dipsb_run_clip_sharded_host from pinned HOST memory (H2D
+inside the timed region, maps and scalars read back).  `configs` carries one row per other BASELINE configuration (C2, C3,
+C5 overall, C5 per-frame with the halo exchange), each with its own roofline, phases and a sustained (>= 1 s) figure.
+torch is used for device memory, streams and (gloo) for handing the NCCL unique id around and taking the max over ranks;
+every collective of the data path is issued by libdips_b200.so.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -25,13 +32,15 @@ if ROOT not in sys.path:
 
 SEED = 0x44695073
 WORKLOADS = {
-    # name: (description, width, height, fmt, mode, tau, frames per GPU)
+    # name: (description, width, height, fmt, mode, tau, frames of the whole clip)
     "c1": ("C1: synthetic 640x480 RGB8 300-frame clip, overall-difference vs first frame", 640, 480, 0, 0, 32, 300),
     "c2": ("C2: synthetic 1920x1080 RGB8 1800-frame clip, overall-difference + threshold", 1920, 1080, 0, 0, 32, 1800),
     "c3": ("C3: synthetic 1920x1080 RGB8 1800-frame clip, per-frame difference + per-frame scalars", 1920, 1080, 0, 1, 32, 1800),
-    "c4": ("C4-shard: synthetic 3840x2160 RGBx8 450-frame shard (3600-frame clip over 8 GPUs), overall-difference", 3840, 2160, 1, 0, 32, 450),
-    "c5": ("C5-shard: synthetic 7680x4320 RGB8 150-frame shard (1200-frame clip over 8 GPUs)", 7680, 4320, 0, 0, 32, 150),
+    "c4": ("C4: synthetic 3840x2160 RGBx8 3600-frame clip, overall-difference, frame-sharded with accumulator reduction", 3840, 2160, 1, 0, 32, 3600),
+    "c5o": ("C5: synthetic 7680x4320 RGB8 1200-frame clip, overall-difference, frame-sharded", 7680, 4320, 0, 0, 32, 1200),
+    "c5p": ("C5: synthetic 7680x4320 RGB8 1200-frame clip, per-frame difference, halo exchange at shard boundaries", 7680, 4320, 0, 1, 32, 1200),
 }
+ROWS = ["c2", "c3", "c5o", "c5p"]
 MODE_NAMES = {0: "overall", 1: "per-frame"}
 FMT_NAMES = {0: "RGB8", 1: "RGBx8", 2: "BGR8", 3: "BGRx8"}
 
@@ -39,18 +48,20 @@ FMT_NAMES = {0: "RGB8", 1: "RGBx8", 2: "BGR8", 3: "BGRx8"}
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=100)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    p.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
-    p.add_argument("--frames", type=int, default=0, help="override frames per GPU")
-    p.add_argument("--mode", choices=["overall", "per-frame"], default=None)
+    p.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
+    p.add_argument("--frames", type=int, default=0, help="override the frames of the whole clip")
+    p.add_argument("--rows", default=",".join(ROWS), help="comma-separated extra workloads reported under `configs` ('' = none)")
+    p.add_argument("--sustained-s", type=float, default=1.0, help="length of the back-to-back sustained measurement per workload")
     p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--exchange", choices=["replicated", "collective"], default="replicated",
-                   help="what a shard needs before its first frame (the clip's frame 0 / the one-frame halo): replicated = "
-                        "each shard carries its own copy, loaded with it; collective = broadcast / send-recv every clip")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-stream", action="store_true")
+    p.add_argument("--no-preflight", action="store_true")
+    p.add_argument("--reduce", choices=["auto", "p2p", "nccl"], default="auto",
+                   help="accumulator exchange: the library's peer-memory kernels or pack + ncclAllReduce + unpack")
     p.add_argument("--stages", type=int, default=0)
     p.add_argument("--tile-px", type=int, default=0)
     p.add_argument("--segments", type=int, default=0)
@@ -141,25 +152,51 @@ def host_cores() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_port_throughput(wl, sample_frames: int, clip_host=None, budget_s: float = 20.0):
+def shard_of(total: int, world: int, rank: int):
+    """first frame and frame count of `rank` (the same arithmetic as dipsb_shard_range, without loading the library)"""
+    t0 = (rank * total) // world
+    return t0, ((rank + 1) * total) // world - t0
+
+
+def cpu_sample_frames(wl) -> int:
+    """frames of the bounded sample the CPU port is timed on (C1/C2/C3 in full, 4K/8K on a >= 64-frame
+    prefix)"""
+    _, w, h, fmt, _, _, total = wl
+    fb = w * h * (3 if fmt in (0, 2) else 4)
+    return total if total * fb <= 12e9 else min(total, max(64, int(2.2e9 // fb)))
+
+
+def cpu_port_throughput(wl, clip_host, budget_s: float = 12.0):
     """The oracle (C port of the reference's shader arithmetic) on the host cores: frames/s on a bounded sample."""
-    import numpy as np
     from oracle import oracle as O
-    desc, w, h, fmt, mode, tau, _ = wl
+    _, w, h, fmt, mode, tau, _ = wl
     cores = host_cores()
-    if clip_host is None:
-        clip_host = O.synth_clip(sample_frames, w, h, fmt, seed=SEED, profile=O.SYNTH_SCENE)
-    clip_host = np.ascontiguousarray(clip_host[:sample_frames])
-    O.run_clip(clip_host[: min(8, sample_frames)], fmt, mode, tau, nthreads=cores)        # warm the threads and caches
+    n = clip_host.shape[0]
+    O.run_clip(clip_host[: min(8, n)], fmt, mode, tau, nthreads=cores)        # warm the threads and caches
     t = time.perf_counter()
     reps = 0
     while True:
         O.run_clip(clip_host, fmt, mode, tau, nthreads=cores)
         reps += 1
         dt = time.perf_counter() - t
-        if dt > budget_s / 2 or reps >= 20:
+        if dt > budget_s or reps >= 20:
             break
-    return reps * sample_frames / dt, cores, f"{sample_frames}-frame prefix of the workload x{reps} passes, {cores} OpenMP threads, oracle/dips_oracle.c"
+    return reps * n / dt, cores, f"{n}-frame prefix of the workload x{reps} passes, {cores} OpenMP threads, oracle/dips_oracle.c"
+
+
+def config_of(wl, world):
+    """the `config` object of the JSON line -- identical for both arms"""
+    desc, w, h, fmt, mode, tau, total = wl
+    shards = [shard_of(total, world, r)[1] for r in range(world)]
+    return {"workload": desc, "width": w, "height": h, "format": FMT_NAMES[fmt], "mode": MODE_NAMES[mode],
+            "threshold_i2": tau, "frames_total": total, "frames_per_gpu": shards[0] if len(set(shards)) == 1 else shards,
+            "seed": hex(SEED), "profile": "scene", "parallelism": f"frame-shard x{world} (strong scaling: one clip, {world} contiguous frame ranges)",
+            "exchange": ("none (single GPU)" if world == 1 else
+                         "per clip, issued by libdips_b200.so: " +
+                         ("reference plane of frame 0 ncclBroadcast from rank 0" if mode == 0 else
+                          "one-frame halo pushed over NVLink by the copy engine during the pass") +
+                         " + accumulator reduce-scatter over peer memory (totals stay sharded by pixel range; gathered on read-out)"),
+            "l2": "clip shard per GPU >> 126 MB L2 (inputs larger than L2)"}
 
 
 def reference_arm(args, wl, rank, out):
@@ -167,11 +204,9 @@ def reference_arm(args, wl, rank, out):
     this arm times the oracle port on the host cores, all threads, on a bounded sample of the same workload."""
     if rank != 0:
         return 0
-    import numpy as np
     from oracle import oracle as O
-    desc, w, h, fmt, mode, tau, frames = wl
-    fb = w * h * O.bpp(fmt)
-    sample = max(8, min(frames, int(1.5e9 // fb)))          # ~1.5 GB of frames per step
+    desc, w, h, fmt, mode, tau, total = wl
+    sample = cpu_sample_frames(wl)
     cores = host_cores()
     clip = O.synth_clip(sample, w, h, fmt, seed=SEED, profile=O.SYNTH_SCENE, nthreads=cores)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -182,36 +217,23 @@ def reference_arm(args, wl, rank, out):
     for _ in range(steps):
         O.run_clip(clip, fmt, mode, tau, nthreads=cores)
         done += 1
-        if time.perf_counter() - t0 > 120 and done >= 3:      # keep the whole run within a few minutes
+        if time.perf_counter() - t0 > 150 and done >= 3:      # keep the whole run within a few minutes
             break
     dt = time.perf_counter() - t0
     fps = done * sample / dt
+    what = (f"each step = the first {sample} of the clip's {total} frames" if sample < total else f"each step = all {total} frames of the clip")
     line = {
         "impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": config_of(wl, args, 1, sample_note=f"each step = {sample}-frame prefix of the workload"),
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_of(wl, args.gpus),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample}-frame prefix x{done} steps, {cores} OpenMP threads (oracle/dips_oracle.c; the reference has no CPU implementation)"},
+                         "sample": f"{what}, x{done} steps, {cores} OpenMP threads (oracle/dips_oracle.c; the reference has no CPU implementation)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=out, flush=True)
     return 0
-
-
-def config_of(wl, args, world, sample_note=None):
-    desc, w, h, fmt, mode, tau, frames = wl
-    cfg = {"workload": desc, "width": w, "height": h, "format": FMT_NAMES[fmt], "mode": MODE_NAMES[mode],
-           "threshold_i2": tau, "frames_per_gpu": frames, "frames_total": frames * world, "seed": hex(SEED),
-           "profile": "scene", "parallelism": f"frame-shard x{world}",
-           "exchange": ("none (single GPU)" if world == 1 else
-                        ("reference / halo frame replicated with each shard at load, " if args.exchange == "replicated" else
-                         "reference plane broadcast / halo send-recv per clip, ") + "one packed accumulator all-reduce per clip"),
-           "l2": "clip per GPU >> 126 MB L2 (inputs larger than L2)"}
-    if sample_note:
-        cfg["sample"] = sample_note
-    return cfg
 
 
 def _claim_stdout():
@@ -223,207 +245,317 @@ def _claim_stdout():
     return os.fdopen(real, "w")
 
 
-def main():
-    args = parse_args()
-    out = _claim_stdout()
-    wl = list(WORKLOADS[args.workload])
-    if args.frames:
-        wl[6] = args.frames
-    if args.mode:
-        wl[4] = 0 if args.mode == "overall" else 1
-    wl = tuple(wl)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        return reference_arm(args, wl, rank, out)
+def log(rank, *a):
+    if rank == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
 
-    import dips_b200
-    from dips_b200 import sharding
+# --------------------------------------------------------------------------------------------------------------------
+class Bench:
+    """One process = one GPU = one rank.  Holds the device buffer the synthetic shards are generated into."""
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; dips_b200 has no CPU fallback")
-    desc, w, h, fmt, mode, tau, frames = wl
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import datetime
-        # a rank that never arrives at a collective should end the run after minutes, not hold the box for the default 10+
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(minutes=4))
-    bpp = dips_b200.bytes_per_pixel(fmt)
-    npx, fb = w * h, w * h * bpp
-    stream = torch.cuda.Stream(device=dev)       # one explicit stream for our kernels, torch copies and NCCL ordering
-    torch.cuda.set_stream(stream)
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
 
-    # ---- synthetic shard, generated on the device (outside every timed region) ------------------------------------
-    t0_frame = rank * frames
-    clip = torch.empty((frames, fb), dtype=torch.uint8, device=dev)
-    dips_b200.synth_fill_device(local_rank, clip.data_ptr(), t0_frame, frames, w, h, fmt, SEED, dips_b200.SYNTH_SCENE,
-                                stream.cuda_stream)
-    torch.cuda.synchronize()
-
-    ctx = dips_b200.Context(w, h, fmt, mode, tau, device=local_rank)
-    if args.kernel >= 0:
-        ctx.set_kernel(args.kernel)
-    if args.stages or args.tile_px or args.segments or args.regs:
-        ctx.set_tuning(args.stages, args.tile_px, args.segments, args.regs)
-    ctx.set_stream(stream.cuda_stream)
-    reference = None
-    replicated = world > 1 and args.exchange == "replicated"          # the same on every rank
-    if replicated and rank > 0:
-        # the shard's copy of the frame it needs before its first one: the clip's frame 0 (overall) or its predecessor
-        # t0-1 (per-frame); part of the resident input, like the shard itself
-        ref_frame = torch.empty(fb, dtype=torch.uint8, device=dev)
-        dips_b200.synth_fill_device(local_rank, ref_frame.data_ptr(), 0 if mode == sharding.MODE_OVERALL else t0_frame - 1,
-                                    1, w, h, fmt, SEED, dips_b200.SYNTH_SCENE, stream.cuda_stream)
-        torch.cuda.synchronize()
-        reference = {mode: ref_frame}
-    engine = sharding.GpuShardEngine(ctx, clip, torch, total_frames=world * frames, replicated=replicated, reference=reference)
-
-    phase_events = []
-
-    def step(record=False):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
-        if ev: ev[0].record(stream)
-        ctx.reset()
-        sharding.exchange_reference(engine, mode, rank, world, dist if world > 1 else None)
-        if ev: ev[1].record(stream)
-        engine.run(t0_frame)
-        if ev: ev[2].record(stream)
+        import dips_b200
+        self.torch, self.dist, self.lib = torch, dist, dips_b200
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
         if world > 1:
-            dist.all_reduce(engine.acc_tensor(), op=dist.ReduceOp.SUM)
-            engine.after_reduce()
-        if ev:
-            ev[3].record(stream)
-            phase_events.append(ev)
+            import datetime
+            # gloo only carries the NCCL unique id, barriers and max-over-ranks of the timings; every collective of the data
+            # path is issued by libdips_b200.so on its own NCCL communicator / peer-memory kernels
+            dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(minutes=4))
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.buf = None
+        self.reduce_path = {"auto": dips_b200.REDUCE_AUTO, "p2p": dips_b200.REDUCE_P2P, "nccl": dips_b200.REDUCE_NCCL}[args.reduce]
 
-    def fence():
+    # ---- plumbing -------------------------------------------------------------------------------------------------
+    def fence(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, xs):
+        if self.world == 1:
+            return list(xs)
+        t = self.torch.tensor(list(xs), dtype=self.torch.int64)
+        self.dist.all_reduce(t)
+        return [int(v) for v in t]
+
+    def gather_floats(self, x: float):
+        if self.world == 1:
+            return [x]
+        outs = [None] * self.world
+        self.dist.all_gather_object(outs, x)
+        return [float(v) for v in outs]
+
+    def unique_id(self) -> bytes:
+        box = [self.lib.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def ensure_buf(self, nbytes: int):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.torch.cuda.empty_cache()
+            self.buf = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.dev)
+        return self.buf
+
+    def make_context(self, wl, tune=True):
+        _, w, h, fmt, mode, tau, _ = wl
+        a = self.args
+        ctx = self.lib.Context(w, h, fmt, mode, tau, device=self.local_rank)
+        if tune and a.kernel >= 0:
+            ctx.set_kernel(a.kernel)
+        if tune and (a.stages or a.tile_px or a.segments or a.regs):
+            ctx.set_tuning(a.stages, a.tile_px, a.segments, a.regs)
+        ctx.set_stream(self.stream.cuda_stream)
+        if self.world > 1:
+            ctx.comm_init_rank(self.world, self.rank, self.unique_id())
+            if self.reduce_path != self.lib.REDUCE_AUTO:
+                ctx.comm_set_reduce(self.reduce_path)
+        return ctx
+
+    # ---- one workload: device-resident shard, K timed steps, sustained run, roofline --------------------------------
+    def measure(self, name, wl, steps, warmup, with_probe=False, keep=False):
+        torch, lib = self.torch, self.lib
+        desc, w, h, fmt, mode, tau, total = wl
+        bpp = lib.bytes_per_pixel(fmt)
+        npx, fb = w * h, w * h * bpp
+        t0_frame, n_local = shard_of(total, self.world, self.rank)
+        clip = self.ensure_buf(n_local * fb)[: n_local * fb].view(n_local, fb)
+        lib.synth_fill_device(self.local_rank, clip.data_ptr(), t0_frame, n_local, w, h, fmt, SEED, lib.SYNTH_SCENE,
+                              self.stream.cuda_stream)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        ctx = self.make_context(wl)
+        sharded = self.world > 1
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    fence()
-    ctx.enable_timing(True)
-    ctx.clip_kernel_time()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = dips_b200.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fence()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step(record=True)
-    e1.record(stream)
-    fence()
-    clocks = sampler.stop()
-    launches = dips_b200.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    kern_ms, kern_n = ctx.clip_kernel_time()
-    ctx.enable_timing(False)
-    plan = ctx.last_plan()
-    phases = {"reset+exchange_ms": sum(e[0].elapsed_time(e[1]) for e in phase_events) / len(phase_events),
-              "prime+clip+finalize_ms": sum(e[1].elapsed_time(e[2]) for e in phase_events) / len(phase_events),
-              "allreduce_ms": sum(e[2].elapsed_time(e[3]) for e in phase_events) / len(phase_events)}
-    t_all = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    ms_total = float(t_all.item())
-    value = world * frames * args.steps / (ms_total / 1e3)
-    per_rank = [kern_ms / max(kern_n, 1)]
-    if world > 1:                                   # the slowest GPU sets the step time: report every rank's kernel time
-        g_all = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
-        dist.all_gather(g_all, torch.tensor([per_rank[0]], dtype=torch.float64, device=dev))
-        per_rank = [float(x.item()) for x in g_all]
+        def step():
+            ctx.reset()
+            if sharded:
+                ctx.run_clip_sharded_device(clip.data_ptr(), n_local, t0_frame, total, fb)
+            else:
+                ctx.run_clip_device(clip.data_ptr(), n_local, fb, 0)
 
-    # sanity of the last step's results (cheap integer identity; parity proper lives in tests/)
-    sad, cnt = ctx.get_scalars(t0_frame, frames)
-    acc_sum, acc_cnt = ctx.get_accumulators()
-    tot = torch.tensor([int(sad.sum()), int(cnt.sum())], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot)          # per-frame scalars are per shard; the all-reduced maps must add up to all of them
-    assert int(acc_sum.astype(np.uint64).sum()) == int(tot[0]) and int(acc_cnt.astype(np.uint64).sum()) == int(tot[1]), \
-        "checksum of checksums failed"
-    if world > 1 and mode == sharding.MODE_OVERALL:   # every rank differenced against the same reference plane
-        plane = ctx.get_state_plane().astype(np.int64)
-        sig = torch.tensor([int(plane.sum()), int((plane * (np.arange(plane.size) % 65521 + 1)).sum())], dtype=torch.int64, device=dev)
-        sigs = [torch.zeros_like(sig) for _ in range(world)]
-        dist.all_gather(sigs, sig)
-        assert all(bool((x == sigs[0]).all()) for x in sigs), "reference planes differ between ranks"
+        for _ in range(max(warmup, 3)):
+            step()
+        self.fence()
+        ctx.enable_timing(True)
+        ctx.clip_kernel_time()
+        if sharded:
+            ctx.comm_phase_times()
+        sampler = ClockSampler(self.local_rank)
+        sampler.start()
+        launches0 = lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.fence()
+        e0.record(self.stream)
+        for _ in range(steps):
+            step()
+        e1.record(self.stream)
+        self.fence()
+        clocks = sampler.stop()
+        launches = lib.launch_count() - launches0
+        ms_total = self.max_over_ranks(e0.elapsed_time(e1))
+        kern_ms, kern_n = ctx.clip_kernel_time()
+        kern_avg_ms = kern_ms / max(kern_n, 1)
+        phases = {"step_ms": ms_total / steps, "clip_kernel_ms": kern_avg_ms}
+        if sharded:
+            (ex_ms, run_ms, red_ms), n_pass = ctx.comm_phase_times()
+            n_pass = max(n_pass, 1)
+            phases.update({"exchange_before_pass_ms": ex_ms / n_pass, "prime+clip+finalize_ms": run_ms / n_pass,
+                           "accumulator_exchange_ms": red_ms / n_pass,
+                           "note": "event pairs on this rank's stream (rank 0); a phase that waits for a slower rank contains the wait"})
+            ctx.comm_check()
+        ctx.enable_timing(False)
+        per_rank = self.gather_floats(kern_avg_ms)
+        value = total * steps / (ms_total / 1e3)
 
-    # ---- roofline of the dominant kernel --------------------------------------------------------------------------
-    alg_bytes = frames * fb + npx * 2 + npx * 8      # every input byte once + reference plane + accumulators once
-    kern_avg_ms = kern_ms / max(kern_n, 1)
-    achieved = alg_bytes / (kern_avg_ms / 1e3) / 1e9
-    peak, peak_src = measured_peak()
-    probe_ms = ctx.stream_probe(clip.data_ptr(), frames, clip.stride(0), 5)      # compute-free TMA stream, same tiles
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload),
-                "kernel": "clip_kernel_ws" if plan.get("kernel") == 1 else "clip_kernel", "kernel_ms": kern_avg_ms,
-                "kernel_share_of_step": kern_avg_ms / (ms_total / args.steps), "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms_per_rank": per_rank, "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0,
-                "stream_probe_GBps": frames * fb / (probe_ms / 1e3) / 1e9,
-                "frac_of_stream_probe": (frames * fb / (kern_avg_ms / 1e3) / 1e9) / (frames * fb / (probe_ms / 1e3) / 1e9)}
+        # ---- sanity of the last step's results (cheap integer identity; parity proper lives in tests/ and the preflight) ----
+        import numpy as np
+        sad, cnt = ctx.get_scalars(t0_frame, n_local)
+        if sharded:
+            t_g = time.perf_counter()
+            ctx.gather_accumulators()
+            ctx.synchronize()
+            gather_ms = 1e3 * (time.perf_counter() - t_g)
+            ctx.comm_check()
+        acc_sum, acc_cnt = ctx.get_accumulators()
+        tot = self.sum_over_ranks([int(sad.sum()), int(cnt.sum())])
+        assert int(acc_sum.astype(np.uint64).sum()) == tot[0] and int(acc_cnt.astype(np.uint64).sum()) == tot[1], \
+            f"{name}: checksum of checksums failed"
+        if sharded:   # every rank must hold the same gathered maps
+            sig = [int(acc_sum[::97].astype(np.uint64).sum()), int(acc_cnt[::89].astype(np.uint64).sum())]
+            allsig = self.sum_over_ranks(sig)
+            assert allsig[0] == sig[0] * self.world and allsig[1] == sig[1] * self.world, f"{name}: gathered maps differ between ranks"
+            phases["gather_on_readout_ms"] = gather_ms
 
-    # ---- end to end: pinned host clip -> dipsb_run_clip_host -> results back on the host ---------------------------
-    e2e = None
-    if not args.no_e2e:
+        # ---- sustained: back-to-back steps for >= sustained_s (the power-capped regime; short runs measure burst clocks) ----
+        sustained = None
+        if self.args.sustained_s > 0:
+            n_sus = max(steps, int(math.ceil(self.args.sustained_s * 1e3 / (ms_total / steps))))
+            ctx.enable_timing(True)
+            ctx.clip_kernel_time()
+            s2 = ClockSampler(self.local_rank)
+            s2.start()
+            self.fence()
+            e0.record(self.stream)
+            for _ in range(n_sus):
+                step()
+            e1.record(self.stream)
+            self.fence()
+            c2 = s2.stop()
+            ms_sus = self.max_over_ranks(e0.elapsed_time(e1))
+            k_ms, k_n = ctx.clip_kernel_time()
+            ctx.enable_timing(False)
+            if sharded:
+                ctx.comm_phase_times()
+                ctx.comm_check()
+            k_avg = k_ms / max(k_n, 1)
+            sustained = {"steps": n_sus, "seconds": ms_sus / 1e3, "value": total * n_sus / (ms_sus / 1e3), "unit": "frames/s",
+                         "ms_per_step": ms_sus / n_sus, "clip_kernel_ms": k_avg,
+                         "kernel_GBps": (n_local * fb + npx * 10) / (k_avg / 1e3) / 1e9, "clocks": c2}
+
+        # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+        alg_bytes = n_local * fb + npx * 2 + npx * 8      # every input byte once + reference plane + accumulators once
+        achieved = alg_bytes / (kern_avg_ms / 1e3) / 1e9
+        peak, peak_src = measured_peak()
+        plan = ctx.last_plan()
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(name),
+                    "kernel": "clip_kernel_ws" if plan.get("kernel") == 1 else "clip_kernel", "kernel_ms": kern_avg_ms,
+                    "kernel_share_of_step": kern_avg_ms / (ms_total / steps), "algorithmic_bytes_per_launch": alg_bytes,
+                    "kernel_ms_per_rank": per_rank, "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0}
+        if sustained:
+            roofline["sustained"] = {"achieved": sustained["kernel_GBps"], "frac": sustained["kernel_GBps"] / peak,
+                                     "seconds": sustained["seconds"], "sm_mhz": sustained["clocks"]["sm_mhz"],
+                                     "reasons": sustained["clocks"]["reasons"]}
+        if with_probe:
+            probe_ms = ctx.stream_probe(clip.data_ptr(), n_local, fb, 3)      # compute-free TMA stream, same tiles
+            roofline["stream_probe_GBps"] = n_local * fb / (probe_ms / 1e3) / 1e9
+            roofline["frac_of_stream_probe"] = probe_ms / kern_avg_ms
+        res = {"name": name, "value": value, "unit": "frames/s", "ms_per_step": ms_total / steps, "steps": steps,
+               "hbm_GBps_per_gpu_whole_step": n_local * fb * steps / (ms_total / 1e3) / 1e9,
+               "phases": phases, "roofline": roofline, "sustained": sustained, "clocks": clocks, "plan": plan,
+               "gpu_launches": int(launches) * self.world, "comm": ctx.comm_info() if sharded else None}
+        if keep:
+            return res, ctx, clip
+        ctx.close()
+        return res, None, None
+
+    # ---- multi-GPU parity against the oracle (outside every timed region) -------------------------------------------
+    def preflight(self):
+        """A small clip through the real sharded path on the real GPUs -- both modes, both accumulator paths -- compared bit
+        for bit with the CPU oracle run over the whole clip."""
+        import numpy as np
+        from oracle import oracle as O      # the checker; nothing it computes is measured or shipped
+        lib, torch = self.lib, self.torch
+        w, h, fmt, tau = 640, 360, 1, 24
+        total = 6 * self.world + 3
+        fb = w * h * 4
+        cases = []
+        for mode in (0, 1):
+            for path, pname in ((lib.REDUCE_P2P, "p2p"), (lib.REDUCE_NCCL, "nccl")):
+                t0, n = shard_of(total, self.world, self.rank)
+                clip = self.ensure_buf(n * fb)[: n * fb].view(n, fb)
+                lib.synth_fill_device(self.local_rank, clip.data_ptr(), t0, n, w, h, fmt, SEED, lib.SYNTH_SCENE, self.stream.cuda_stream)
+                torch.cuda.synchronize()
+                ctx = lib.Context(w, h, fmt, mode, tau, device=self.local_rank)
+                ctx.set_stream(self.stream.cuda_stream)
+                ctx.comm_init_rank(self.world, self.rank, self.unique_id())
+                info = ctx.comm_info()
+                if path == lib.REDUCE_P2P and not info["peer_memory"]:
+                    ctx.close()
+                    cases.append({"mode": MODE_NAMES[mode], "reduce": pname, "skipped": "peer memory not mapped"})
+                    continue
+                ctx.comm_set_reduce(path)
+                for _ in range(2):                      # twice: the second pass runs on the other window parity
+                    ctx.reset()
+                    ctx.run_clip_sharded_device(clip.data_ptr(), n, t0, total, fb)
+                ctx.gather_accumulators()
+                ctx.synchronize()
+                ctx.comm_check()
+                acc_sum, acc_cnt = ctx.get_accumulators()
+                sad, cnt = ctx.get_scalars(t0, n)
+                ctx.close()
+                whole = O.synth_clip(total, w, h, fmt, seed=SEED, profile=O.SYNTH_SCENE)
+                want = O.run_clip(whole, fmt, mode, tau)
+                ok = (np.array_equal(acc_sum, want.acc_sum) and np.array_equal(acc_cnt, want.acc_cnt) and
+                      np.array_equal(sad, want.sad[t0:t0 + n]) and np.array_equal(cnt, want.cnt[t0:t0 + n]))
+                n_ok = self.sum_over_ranks([1 if ok else 0])[0]
+                cases.append({"mode": MODE_NAMES[mode], "reduce": pname, "ranks_bit_exact": n_ok, "ranks": self.world})
+                assert n_ok == self.world, f"multi-GPU parity failed: {cases[-1]}"
+        return {"checked": True, "clip": f"{w}x{h} RGBx8 x{total} frames over {self.world} ranks, 2 passes", "against": "oracle/dips_oracle.c over the whole clip",
+                "cases": cases, "bit_exact": True}
+
+    # ---- end to end: pinned host shard -> dipsb_run_clip_sharded_host -> maps and scalars back on the host -----------
+    def e2e(self, wl, ctx):
         import psutil
-        e2e_frames = frames
+        torch, lib = self.torch, self.lib
+        desc, w, h, fmt, mode, tau, total = wl
+        fb, npx = w * h * lib.bytes_per_pixel(fmt), w * h
+        t0_frame, n_local = shard_of(total, self.world, self.rank)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(self.world)))
         avail = psutil.virtual_memory().available
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        while e2e_frames > 32 and e2e_frames * fb * local_world * 1.5 > avail:
-            e2e_frames //= 2
-        host = torch.empty((e2e_frames, fb), dtype=torch.uint8, pin_memory=True)
-        host.copy_(clip[:e2e_frames])
+        frames = min(n_local, int(16e9 // fb))                       # at most 16 GB of page-locked memory per process
+        while frames > 16 and frames * fb * local_world * 1.5 > avail:
+            frames //= 2
+        frames = int(self.sum_over_ranks([frames])[0] // self.world) if self.world > 1 else frames   # same on every rank
+        frames = min(frames, n_local)
+        e_total, e_first = frames * self.world, frames * self.rank
+        host = torch.empty((frames, fb), dtype=torch.uint8, pin_memory=True)
+        lib.synth_fill_device(self.local_rank, self.buf.data_ptr(), e_first, frames, w, h, fmt, SEED, lib.SYNTH_SCENE, self.stream.cuda_stream)
+        host.copy_(self.buf[: frames * fb].view(frames, fb))
         torch.cuda.synchronize()
         h_sum = torch.empty(npx, dtype=torch.int32, pin_memory=True)
         h_cnt = torch.empty(npx, dtype=torch.int32, pin_memory=True)
 
-        class HostEngine(sharding.GpuShardEngine):
-            def first_frame(self):
-                return host[0].to(dev, non_blocking=True)
-
-            def last_frame(self):
-                return host[e2e_frames - 1].to(dev, non_blocking=True)
-
-            def run(self, first_frame_index):
-                ctx.run_clip_host(host.data_ptr(), e2e_frames, fb, first_frame_index)
-
-        hengine = HostEngine(ctx, clip, torch, total_frames=world * e2e_frames)
-
-        def e2e_step():
+        def step():
             ctx.reset()
-            sharding.run_sharded(hengine, mode, t0_frame, rank, world, dist if world > 1 else None)
-            ctx.get_accumulators_into(h_sum.data_ptr(), h_cnt.data_ptr())                           # D2H of the maps
-            return ctx.get_scalars(t0_frame, e2e_frames)                                            # D2H of the scalars
+            if self.world > 1:
+                ctx.run_clip_sharded_host(host.data_ptr(), frames, e_first, e_total, fb)
+                ctx.gather_accumulators()
+            else:
+                ctx.run_clip_host(host.data_ptr(), frames, fb, 0)
+            ctx.get_accumulators_into(h_sum.data_ptr(), h_cnt.data_ptr())            # D2H of the maps
+            return ctx.get_scalars(e_first, frames)                                  # D2H of the scalars
 
-        e2e_step()
-        fence()
+        step()
+        self.fence()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        fence()
-        dt = time.perf_counter() - t0
-        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        dt = float(t_e.item())
-        e2e = {"value": world * e2e_frames * args.e2e_steps / dt, "unit": "frames/s",
-               "h2d_bytes_per_step": e2e_frames * fb, "d2h_bytes_per_step": npx * 8 + e2e_frames * 16,
-               "frames_per_gpu": e2e_frames, "steps": args.e2e_steps,
-               "api": "dipsb_run_clip_host (pinned host clip, chunked H2D overlapped with the clip kernel) + dipsb_get_accumulators + dipsb_get_scalars",
-               "h2d_GBps_per_gpu": e2e_frames * fb * args.e2e_steps / dt / 1e9}
-        if world == 1:
+        for _ in range(self.args.e2e_steps):
+            step()
+        self.fence()
+        dt = self.max_over_ranks(time.perf_counter() - t0)
+        if self.world > 1:
+            ctx.comm_check()
+        res = {"value": e_total * self.args.e2e_steps / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": frames * fb * self.world, "d2h_bytes_per_step": (npx * 8 + frames * 16) * self.world,
+               "frames_per_gpu": frames, "frames_total": e_total, "steps": self.args.e2e_steps,
+               "clip": f"a {e_total}-frame clip of the workload's geometry ({frames} frames per GPU: what fits page-locked host memory), same call path",
+               "api": ("dipsb_run_clip_sharded_host + dipsb_gather_accumulators" if self.world > 1 else "dipsb_run_clip_host") +
+                      " (pinned host clip, chunked H2D overlapped with the clip kernel) + dipsb_get_accumulators + dipsb_get_scalars",
+               "h2d_GBps_per_gpu": frames * fb * self.args.e2e_steps / dt / 1e9,
+               "h2d_GBps_aggregate": frames * fb * self.world * self.args.e2e_steps / dt / 1e9,
+               "limit": "host side: PCIe Gen5 x16 per GPU (~55 GB/s measured at N<=2); the aggregate over 4-8 GPUs is bounded by the host's "
+                        "root complexes / memory, not by the GPUs (SCALE_r01: 115 GB/s at N=4, 186 GB/s at N=8)"}
+        if self.world == 1:
+            import numpy as np
             # the same call from ORDINARY host memory (what a caller without page-locked buffers has): every chunk is first
             # staged into a page-locked bounce buffer by the library's threaded host copy
-            pn = min(e2e_frames, max(32, int(2.5e9 // fb)))
+            pn = min(frames, max(16, int(2.5e9 // fb)))
             pageable = np.empty((pn, fb), np.uint8)
             pageable[:] = host[:pn].numpy()
             ctx.reset(); ctx.run_clip_host(pageable.ctypes.data, pn, fb, 0); ctx.synchronize()
@@ -433,34 +565,35 @@ def main():
                 ctx.run_clip_host(pageable.ctypes.data, pn, fb, 0)
                 ctx.get_accumulators_into(h_sum.data_ptr(), h_cnt.data_ptr())
                 ctx.get_scalars(0, pn)
-            e2e["pageable_host_fps"] = 2 * pn / (time.perf_counter() - t0)
-            e2e["pageable_host_frames"] = pn
+            res["pageable_host_fps"] = 2 * pn / (time.perf_counter() - t0)
+            res["pageable_host_frames"] = pn
             del pageable
         del host
+        return res
 
     # ---- streaming boundary (the reference's per-frame callback shape): RGBA8 frame in -> RGBA8 difference frame out ----
-    stream_info = None
-    if not args.no_e2e and world == 1:
+    def stream_boundary(self, tau=32):
+        import numpy as np
+        torch, lib = self.torch, self.lib
         sw, sh, sn = 1920, 1080, 120
         frames_rgba = np.empty((8, sw * sh * 4), np.uint8)
-        tmp = torch.empty(8 * sw * sh * 4, dtype=torch.uint8, device=dev)
-        dips_b200.synth_fill_device(local_rank, tmp.data_ptr(), 0, 8, sw, sh, dips_b200.FMT_RGBX8, SEED,
-                                    dips_b200.SYNTH_SCENE, stream.cuda_stream)
+        tmp = torch.empty(8 * sw * sh * 4, dtype=torch.uint8, device=self.dev)
+        lib.synth_fill_device(self.local_rank, tmp.data_ptr(), 0, 8, sw, sh, lib.FMT_RGBX8, SEED, lib.SYNTH_SCENE, self.stream.cuda_stream)
         torch.cuda.synchronize()
         frames_rgba[:] = tmp.cpu().numpy().reshape(8, -1)
         del tmp
-        stream_info = {"geometry": "1920x1080 RGBx8 in, RGBA8 difference frame out, per-frame call", "frames": sn,
-                       "buffers": "pageable = ordinary host memory (staged by the library's threaded host copy each way); pinned = "
-                                  "dipsb_host_alloc buffers (copy engine reads/writes them directly)"}
-        pin_in = dips_b200.PinnedBuffer(8 * sw * sh * 4, device=local_rank)
-        pin_out = dips_b200.PinnedBuffer(2 * sw * sh * 4, device=local_rank)
+        info = {"geometry": "1920x1080 RGBx8 in, RGBA8 difference frame out, per-frame call", "frames": sn,
+                "buffers": "pageable = ordinary host memory (staged by the library's threaded host copy each way); pinned = "
+                           "dipsb_host_alloc buffers (copy engine reads/writes them directly)"}
+        pin_in = lib.PinnedBuffer(8 * sw * sh * 4, device=self.local_rank)
+        pin_out = lib.PinnedBuffer(2 * sw * sh * 4, device=self.local_rank)
         pin_in.array[:] = frames_rgba.reshape(-1)
         for kind in ("pageable", "pinned"):
             src = frames_rgba if kind == "pageable" else pin_in.array.reshape(8, -1)
             dst = (np.empty((2, sw * sh * 4), np.uint8) if kind == "pageable" else pin_out.array.reshape(2, -1))
             dst[:] = 0
             for name in ("dipsb_push_frame", "dipsb_push_frame_pipelined"):
-                with dips_b200.Context(sw, sh, dips_b200.FMT_RGBX8, 0, tau, device=local_rank) as sctx:
+                with lib.Context(sw, sh, lib.FMT_RGBX8, 0, tau, device=self.local_rank) as sctx:
                     fn = sctx.push_frame if name == "dipsb_push_frame" else sctx.push_frame_pipelined
                     for k in range(4):
                         fn(src[k % 8], out=dst[k & 1])
@@ -469,36 +602,86 @@ def main():
                         fn(src[k % 8], out=dst[k & 1])
                     if name != "dipsb_push_frame":
                         sctx.flush_frame(out=dst[sn & 1])
-                    key = name + ("_fps" if kind == "pageable" else "_pinned_fps")
-                    stream_info[key] = sn / (time.perf_counter() - t0)
+                    info[name + ("_fps" if kind == "pageable" else "_pinned_fps")] = sn / (time.perf_counter() - t0)
         pin_in.close()
         pin_out.close()
+        return info
 
-    # ---- CPU baseline (rank 0, N == 1 only) -----------------------------------------------------------------------
+
+def main():
+    args = parse_args()
+    out = _claim_stdout()
+    wl = list(WORKLOADS[args.workload])
+    if args.frames:
+        wl[6] = args.frames
+    wl = tuple(wl)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, wl, rank, out)
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; dips_b200 has no CPU fallback")
+    B = Bench(args, rank, world, local_rank)
+    t_start = time.perf_counter()
+
+    parity = None
+    if world > 1 and not args.no_preflight:
+        parity = B.preflight()
+        log(rank, "preflight parity ok", json.dumps(parity["cases"]))
+
+    # ---- headline workload ----------------------------------------------------------------------------------------
+    head, ctx, clip = B.measure(args.workload, wl, args.steps, args.warmup, with_probe=True, keep=True)
+    log(rank, f"{args.workload}: {head['value']:.0f} frames/s, {head['ms_per_step']:.3f} ms/step, kernel {head['roofline']['achieved']:.0f} GB/s "
+              f"({time.perf_counter() - t_start:.0f} s)")
+    e2e = None
+    if not args.no_e2e:
+        e2e = B.e2e(wl, ctx)
+        log(rank, f"e2e: {e2e['value']:.0f} frames/s ({time.perf_counter() - t_start:.0f} s)")
     cpu = None
     if not args.no_cpu and world == 1:
-        sample = max(8, min(frames, int(1.0e9 // fb)))
-        host_sample = clip[:sample].cpu().numpy()
-        v, cores, what = cpu_port_throughput(wl, sample, host_sample)
+        desc, w, h, fmt, mode, tau, total = wl
+        n_s = min(cpu_sample_frames(wl), max(16, int(1.1e9 // clip.shape[1])))
+        host_sample = clip[:n_s].cpu().numpy()
+        v, cores, what = cpu_port_throughput(wl, host_sample)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": what}
+        del host_sample
+    ctx.close()
+    del clip
+
+    # ---- the other BASELINE configurations, one row each ------------------------------------------------------------
+    rows = []
+    for name in [r for r in args.rows.split(",") if r and r != args.workload]:
+        if name in ("c2", "c3") and world > 1:
+            continue                    # C2 / C3 are BASELINE's one-GPU configurations; their rows belong to the N=1 line
+        rwl = WORKLOADS[name]
+        rsteps = max(5, min(args.steps, 40))
+        r, _, _ = B.measure(name, rwl, rsteps, args.warmup)
+        r["config"] = config_of(rwl, world)
+        rows.append(r)
+        log(rank, f"{name}: {r['value']:.0f} frames/s, {r['ms_per_step']:.3f} ms/step, kernel {r['roofline']['achieved']:.0f} GB/s "
+                  f"({time.perf_counter() - t_start:.0f} s)")
+
+    stream_info = None
+    if not args.no_stream and not args.no_e2e and world == 1:
+        stream_info = B.stream_boundary()
 
     if rank == 0:
-        cfg = config_of(wl, args, world)
-        cfg["plan"] = plan
         line = {
-            "metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
-            "hbm_GBps_per_gpu_whole_step": frames * fb * args.steps / (ms_total / 1e3) / 1e9,
-            "phases": phases, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "stream": stream_info,
-            "gpu_launches": int(launches) * world,
-            "clocks": clocks,
+            "metric": "frames/sec", "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_of(wl, world),
+            "plan": head["plan"], "hbm_GBps_per_gpu_whole_step": head["hbm_GBps_per_gpu_whole_step"],
+            "phases": head["phases"], "roofline": head["roofline"], "sustained": head["sustained"], "cpu_baseline": cpu, "e2e": e2e,
+            "configs": rows, "multi_gpu_parity": parity, "comm": head["comm"], "stream": stream_info,
+            "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
         }
         print(json.dumps(line), file=out, flush=True)
-    ctx.close()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        B.dist.barrier()
+        B.dist.destroy_process_group()
     return 0
 
 

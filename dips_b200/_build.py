@@ -11,12 +11,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libdips_b200.so")
-SOURCES = ["clip_kernel.cu", "aux_kernels.cu", "api.cu", "host_copy.cu"]
-HEADERS = [os.path.join(CSRC, "dipsb_internal.h"), os.path.join(ROOT, "include", "dips_b200.h")]
+SOURCES = ["clip_kernel.cu", "aux_kernels.cu", "api.cu", "comm.cu", "host_copy.cu"]
+HEADERS = [os.path.join(CSRC, "dipsb_internal.h"), os.path.join(CSRC, "dipsb_ctx.h"), os.path.join(ROOT, "include", "dips_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-pthread", "-shared", "-cudart", "static",
 ]
+LINK_FLAGS = ["-ldl"]    # NCCL is loaded with dlopen when a communicator is made: no link-time dependency
 
 
 def nvcc() -> str:
@@ -37,7 +38,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + LINK_FLAGS
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -70,6 +70,30 @@ SYMBOLS = {
     "dipsb_set_kernel": (_i32, [_vp, _i32]),
     "dipsb_plan_query": (_i32, [_u32, _u32, _i32, _u32, C.POINTER(_u32 * 8)]),
     "dipsb_set_tuning": (_i32, [_vp, _u32, _u32, _u32, _u32]),
+    # several GPUs
+    "dipsb_shard_range": (None, [_u64, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64)]),
+    "dipsb_xchg_plan_query": (_i32, [_u64, _u32, _u64, C.POINTER(_u64 * 4)]),
+    "dipsb_comm_unique_id": (_i32, [_vp]),
+    "dipsb_comm_init_rank": (_i32, [_vp, _u32, _u32, _vp]),
+    "dipsb_comm_destroy": (_i32, [_vp]),
+    "dipsb_comm_info": (_i32, [_vp, C.POINTER(_u32 * 8)]),
+    "dipsb_comm_set_reduce": (_i32, [_vp, _i32]),
+    "dipsb_comm_check": (_i32, [_vp]),
+    "dipsb_run_clip_sharded_device": (_i32, [_vp, _vp, _u64, _u64, _u64, _u64]),
+    "dipsb_run_clip_sharded_host": (_i32, [_vp, _vp, _u64, _u64, _u64, _u64]),
+    "dipsb_comm_phase_times": (_i32, [_vp, C.POINTER(C.c_double * 3), C.POINTER(_u64)]),
+    "dipsb_gather_accumulators": (_i32, [_vp]),
+    "dipsb_create_group": (_i32, [C.POINTER(Config), _u32, C.POINTER(_i32), C.POINTER(_vp)]),
+    "dipsb_destroy_group": (None, [_vp]),
+    "dipsb_group_size": (_u32, [_vp]),
+    "dipsb_group_ctx": (_vp, [_vp, _u32]),
+    "dipsb_group_last_error": (C.c_char_p, [_vp]),
+    "dipsb_group_reset": (_i32, [_vp]),
+    "dipsb_group_run_clip_device": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_u64), _u64]),
+    "dipsb_group_gather_accumulators": (_i32, [_vp]),
+    "dipsb_group_synchronize": (_i32, [_vp]),
+    "dipsb_group_get_accumulators": (_i32, [_vp, _vp, _vp]),
+    "dipsb_group_get_scalars": (_i32, [_vp, _u64, _u64, _vp, _vp]),
 }
 
 _lib = None

@@ -42,6 +42,37 @@ def synth_fill_device(device: int, d_dst: int, first_frame: int, n_frames: int, 
         raise DipsError(rc, _lib.load().dipsb_last_error(None).decode())
 
 
+REDUCE_AUTO, REDUCE_P2P, REDUCE_NCCL = 0, 1, 2
+UNIQUE_ID_BYTES = 128
+
+
+def shard_range(total_frames: int, nranks: int, rank: int):
+    """(first, count): the contiguous frames of a total_frames clip that `rank` of `nranks` owns (dipsb_shard_range)."""
+    if not (0 <= rank < nranks):
+        raise ValueError("rank outside the communicator")
+    first, count = C.c_uint64(), C.c_uint64()
+    _lib.load().dipsb_shard_range(total_frames, nranks, rank, C.byref(first), C.byref(count))
+    return int(first.value), int(count.value)
+
+
+def xchg_plan_query(total_frames: int, nranks: int, n_elems: int = 0) -> dict:
+    """host-only: the exchange format of the peer-memory accumulator reduce for such a clip"""
+    out = (C.c_uint64 * 4)()
+    rc = _lib.load().dipsb_xchg_plan_query(total_frames, nranks, n_elems, C.byref(out))
+    if rc != 0:
+        raise DipsError(rc, "xchg_plan_query: invalid arguments")
+    return dict(bytes_per_element=int(out[0]), sum_bits=int(out[1]), frames_per_rank_bound=int(out[2]), owned_elements=int(out[3]))
+
+
+def comm_unique_id() -> bytes:
+    """128 bytes rank 0 hands to every rank of a new communicator (ncclGetUniqueId inside the library)"""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    rc = _lib.load().dipsb_comm_unique_id(buf)
+    if rc != 0:
+        raise DipsError(rc, _lib.load().dipsb_last_error(None).decode())
+    return bytes(buf.raw)
+
+
 FRAME_COUNT = 2      # dips_alt/src/lib.rs:36
 
 
@@ -118,6 +149,16 @@ class PinnedBuffer:
             pass
 
 
+def _make_config(lib, width, height, fmt, mode, threshold, chroma, device, colorize, filt, sigmoid_scalar, spatial_window,
+                 flavor):
+    cfg = _lib.Config()
+    lib.dipsb_default_config(C.byref(cfg))
+    cfg.device, cfg.width, cfg.height, cfg.format, cfg.mode = device, width, height, fmt, mode
+    cfg.chroma, cfg.threshold, cfg.colorize, cfg.filter = chroma, threshold, int(colorize), filt
+    cfg.sigmoid_scalar, cfg.spatial_window, cfg.flavor = sigmoid_scalar, spatial_window, flavor
+    return cfg
+
+
 def _host_ptr(a: np.ndarray) -> int:
     if not a.flags["C_CONTIGUOUS"]:
         raise ValueError("array must be C-contiguous")
@@ -130,17 +171,18 @@ class Context:
 
     def __init__(self, width: int, height: int, fmt: int = FMT_RGBX8, mode: int = MODE_OVERALL, threshold: int = 0,
                  chroma: int = CHROMA_NONE, device: int = 0, colorize: bool = False, filt: int = FILTER_NONE,
-                 sigmoid_scalar: float = 5.0, spatial_window: int = 1, flavor: int = FLAVOR_FRAME0):
+                 sigmoid_scalar: float = 5.0, spatial_window: int = 1, flavor: int = FLAVOR_FRAME0, _borrowed=None):
         self._lib = _lib.load()
-        cfg = _lib.Config()
-        self._lib.dipsb_default_config(C.byref(cfg))
-        cfg.device, cfg.width, cfg.height, cfg.format, cfg.mode = device, width, height, fmt, mode
-        cfg.chroma, cfg.threshold, cfg.colorize, cfg.filter = chroma, threshold, int(colorize), filt
-        cfg.sigmoid_scalar, cfg.spatial_window, cfg.flavor = sigmoid_scalar, spatial_window, flavor
-        h = C.c_void_p()
-        rc = self._lib.dipsb_create(C.byref(cfg), C.byref(h))
-        if rc != 0:
-            raise DipsError(rc, self._lib.dipsb_last_error(None).decode())
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            cfg = _make_config(self._lib, width, height, fmt, mode, threshold, chroma, device, colorize, filt,
+                               sigmoid_scalar, spatial_window, flavor)
+            h = C.c_void_p()
+            rc = self._lib.dipsb_create(C.byref(cfg), C.byref(h))
+            if rc != 0:
+                raise DipsError(rc, self._lib.dipsb_last_error(None).decode())
+        else:
+            h = C.c_void_p(_borrowed)      # a rank of a Group: the group owns the handle
         self._h = h
         self.width, self.height, self.fmt, self.mode = width, height, fmt, mode
         self.npx = width * height
@@ -155,7 +197,8 @@ class Context:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
-            self._lib.dipsb_destroy(self._h)
+            if self._owned:
+                self._lib.dipsb_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -255,6 +298,50 @@ class Context:
         else:
             ptr, n, st = int(frames), int(n_frames), stride or self.frame_bytes
         self._ck(self._lib.dipsb_run_clip_host(self._h, ptr, n, st, first_frame))
+
+    # -- several GPUs: this context as one rank of a communicator ----------------------------------------------
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes) -> None:
+        """collective over all ranks (ncclCommInitRank + mapping of the peers' windows)"""
+        if len(unique_id) != UNIQUE_ID_BYTES:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        self._ck(self._lib.dipsb_comm_init_rank(self._h, nranks, rank, C.create_string_buffer(unique_id, UNIQUE_ID_BYTES)))
+
+    def comm_destroy(self) -> None:
+        self._ck(self._lib.dipsb_comm_destroy(self._h))
+
+    def comm_info(self) -> dict:
+        out = (C.c_uint32 * 8)()
+        self._ck(self._lib.dipsb_comm_info(self._h, C.byref(out)))
+        return dict(nranks=out[0], rank=out[1], peer_memory=bool(out[2]), nccl_version=out[3],
+                    reduce_path={REDUCE_P2P: "p2p", REDUCE_NCCL: "nccl"}.get(out[4], "none"), single_process=bool(out[5]),
+                    acc_sharded=bool(out[6]), nccl=bool(out[7]))
+
+    def comm_set_reduce(self, path: int) -> None:
+        self._ck(self._lib.dipsb_comm_set_reduce(self._h, path))
+
+    def comm_check(self) -> None:
+        self._ck(self._lib.dipsb_comm_check(self._h))
+
+    def run_clip_sharded_device(self, d_frames: int, n_frames: int, first_frame: int, total_frames: int,
+                                stride: int | None = None) -> None:
+        self._ck(self._lib.dipsb_run_clip_sharded_device(self._h, d_frames, n_frames, stride or self.frame_bytes,
+                                                         first_frame, total_frames))
+
+    def run_clip_sharded_host(self, frames, n_frames: int, first_frame: int, total_frames: int,
+                              stride: int | None = None) -> None:
+        ptr = _host_ptr(frames) if isinstance(frames, np.ndarray) else int(frames)
+        self._ck(self._lib.dipsb_run_clip_sharded_host(self._h, ptr, n_frames, stride or self.frame_bytes, first_frame,
+                                                       total_frames))
+
+    def comm_phase_times(self):
+        """((exchange_ms, pass_ms, reduce_ms) summed, passes) of the sharded passes since the last call (enable_timing)"""
+        ms, n = (C.c_double * 3)(), C.c_uint64()
+        self._ck(self._lib.dipsb_comm_phase_times(self._h, C.byref(ms), C.byref(n)))
+        return (float(ms[0]), float(ms[1]), float(ms[2])), int(n.value)
+
+    def gather_accumulators(self) -> None:
+        """collective: complete the accumulator planes on every rank after a sharded pass"""
+        self._ck(self._lib.dipsb_gather_accumulators(self._h))
 
     # -- streaming --------------------------------------------------------------------------------------------
     def _out_buffer(self, out):
@@ -357,3 +444,76 @@ class Context:
         out = np.empty(n, np.float32)
         self._ck(self._lib.dipsb_get_frame_means(self._h, first, n, _host_ptr(out)))
         return out
+
+
+class Group:
+    """All GPUs of one process as the ranks of one clip (dipsb_create_group): one context per device, ncclCommInitAll and
+    peer access inside the library.  devices=[0, 0, ...] gives a loopback group on one GPU (tests)."""
+
+    def __init__(self, devices, width: int, height: int, fmt: int = FMT_RGBX8, mode: int = MODE_OVERALL, threshold: int = 0,
+                 chroma: int = CHROMA_NONE):
+        self._lib = _lib.load()
+        devices = list(devices)
+        cfg = _make_config(self._lib, width, height, fmt, mode, threshold, chroma, 0, False, FILTER_NONE, 5.0, 1, FLAVOR_FRAME0)
+        arr = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._lib.dipsb_create_group(C.byref(cfg), len(devices), arr, C.byref(h))
+        if rc != 0:
+            raise DipsError(rc, self._lib.dipsb_group_last_error(None).decode())
+        self._h = h
+        self.devices, self.npx = devices, width * height
+        self.frame_bytes = self.npx * bytes_per_pixel(fmt)
+        self.ranks = [Context(width, height, fmt, mode, threshold, chroma, device=d,
+                              _borrowed=self._lib.dipsb_group_ctx(h, i)) for i, d in enumerate(devices)]
+
+    def _ck(self, rc: int) -> int:
+        if rc < 0:
+            raise DipsError(rc, self._lib.dipsb_group_last_error(self._h).decode())
+        return rc
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            for r in self.ranks:
+                r.close()
+            self._lib.dipsb_destroy_group(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self) -> None:
+        self._ck(self._lib.dipsb_group_reset(self._h))
+
+    def run_clip_device(self, d_frames, n_frames, stride: int | None = None) -> None:
+        """d_frames[i] / n_frames[i]: device address and frame count of shard i (resident on device i), in clip order"""
+        n = len(self.ranks)
+        ptrs = (C.c_void_p * n)(*[int(p) for p in d_frames])
+        cnts = (C.c_uint64 * n)(*[int(k) for k in n_frames])
+        self._ck(self._lib.dipsb_group_run_clip_device(self._h, ptrs, cnts, stride or self.frame_bytes))
+
+    def gather_accumulators(self) -> None:
+        self._ck(self._lib.dipsb_group_gather_accumulators(self._h))
+
+    def synchronize(self) -> None:
+        self._ck(self._lib.dipsb_group_synchronize(self._h))
+
+    def get_accumulators(self):
+        s = np.empty(self.npx, np.uint32)
+        c = np.empty(self.npx, np.uint32)
+        self._ck(self._lib.dipsb_group_get_accumulators(self._h, _host_ptr(s), _host_ptr(c)))
+        return s, c
+
+    def get_scalars(self, first: int, n: int):
+        sad = np.empty(n, np.uint64)
+        cnt = np.empty(n, np.uint64)
+        self._ck(self._lib.dipsb_group_get_scalars(self._h, first, n, _host_ptr(sad), _host_ptr(cnt)))
+        return sad, cnt

@@ -12,95 +12,14 @@
 #include <string>
 #include <vector>
 
-#include "../../include/dips_b200.h"
-#include "dipsb_internal.h"
+#include "dipsb_ctx.h"
 
 namespace dipsb {
 uint64_t launch_count_value();
 }
 using namespace dipsb;
 
-struct dipsb_ctx {
-    dipsb_config cfg;
-    Geometry g;
-    int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, out_stream = nullptr;
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_switch = nullptr;
-    uint16_t* state[2] = {nullptr, nullptr};   // u16[n_elems] each, zero padded past npx
-    int state_cur = 0;
-    bool state_valid = false;
-    bool snapshot_pending = false;
-    uint32_t* acc = nullptr;                   // u32[2*n_elems]: sum plane then count plane, internal order
-    uint32_t* planar = nullptr;                // u32[2*npx] scratch for get/set in pixel order
-    uint64_t* d_sad = nullptr;                 // per logical frame index
-    uint64_t* d_cnt = nullptr;
-    uint64_t scal_cap = 0, scal_hi = 0;
-    uint32_t* partials = nullptr;
-    uint64_t partial_cap = 0;                  // in u32 words
-    uint64_t frames_processed = 0;
-    uint64_t stream_index = 0;                 // logical index of the next pushed frame
-    uint32_t* xchg = nullptr;                  // packed accumulators for the cross-GPU sum (dipsb_pack_accumulators_device)
-    int xchg_layout = 0, xchg_sum_bits = 0;
-    uint16_t* i2_scratch = nullptr;            // spatial window > 1: 5 planes of npx u16 (raw + up to 4 filtered)
-    uint16_t* ring = nullptr;                  // ring flavours: 4 (dips) or 2 (dips_alt) u16 I2 planes of npx
-    uint32_t ring_seen = 0, ring_index = 0;    // frames pushed since the last (re)start, next slot to overwrite
-    // streaming staging
-    uint8_t* d_frame = nullptr; size_t d_frame_bytes = 0;
-    uint8_t* d_rgba = nullptr;
-    uint8_t* h_pin = nullptr; size_t h_pin_bytes = 0;   // pinned bounce buffer (frame in / rgba out)
-    uint64_t* h_stat = nullptr;                          // pinned [2]
-    // frame slots of the streaming path (slot 0 only for the synchronous call, both for the pipelined one)
-    struct FrameSlot {
-        uint8_t* h_in = nullptr; uint8_t* d_in = nullptr; size_t in_bytes = 0;
-        uint8_t* d_out = nullptr; uint8_t* h_out = nullptr; uint64_t* h_stat = nullptr;
-        cudaEvent_t ev_done = nullptr;
-        cudaEvent_t ev_in[8] = {};    // per row band: uploaded
-        cudaEvent_t ev_k[8] = {};     //               kernels done
-        cudaEvent_t ev_out[8] = {};   //               read back into the staging buffer
-        uint64_t out_off[9] = {};                          // byte offsets of the bands in the RGBA frame
-        int out_pieces = 0;
-        bool pending = false, want_rgba = false; int32_t status = 0; uint64_t idx = 0;
-        bool out_direct = false;               // the read-back already targets the caller's (pinned) buffer
-        bool out_deferred = false;             // the read-back is enqueued at collection time (pipelined, pinned caller)
-    } slot[2];
-    int next_slot = 0;
-    bool out_pinned_hint = false;              // the pipelined caller's output buffers are page-locked
-    // host clip staging
-    uint8_t* h_chunk[2] = {nullptr, nullptr};
-    uint8_t* d_chunk[2] = {nullptr, nullptr};
-    size_t chunk_bytes = 0;
-    bool chunk_used[2] = {false, false};       // ev_copy / ev_done of the slot were recorded (possibly by an earlier call)
-    int chunk_slot = 0;                        // slot the next chunk goes to
-    uint8_t* d_repack = nullptr; size_t repack_bytes = 0;   // aligned, zero-padded copy of an unaligned device clip
-    uint32_t tune_stages = 0, tune_tile_px = 0, tune_segments = 0, tune_regs = 0;
-    int tune_kernel = -1;                      // -1: automatic (clip_kernel_ws whenever the tuning allows it)
-    uint32_t last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool timing = false;
-    std::vector<cudaEvent_t> tev;              // start/stop pairs around clip kernel launches
-    size_t tev_used = 0;
-    std::string err;
-};
-
-static thread_local std::string g_create_err;
-
-static int32_t fail(dipsb_ctx* c, int32_t code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (c) c->err = buf; else g_create_err = buf;
-    return code;
-}
-
-#define CK(c, call)                                                                                     \
-    do {                                                                                                \
-        cudaError_t e__ = (call);                                                                       \
-        if (e__ != cudaSuccess)                                                                         \
-            return fail((c), DIPSB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-
-static int bpp_of(int format) { return (format == DIPSB_FMT_RGB8 || format == DIPSB_FMT_BGR8) ? 3 : 4; }
+int dipsb::bpp_of(int format) { return (format == DIPSB_FMT_RGB8 || format == DIPSB_FMT_BGR8) ? 3 : 4; }
 
 static int chan_byte_of(int format, int chroma) {
     if (chroma == DIPSB_CHROMA_NONE) return -1;
@@ -238,6 +157,7 @@ static void free_all(dipsb_ctx* c) {
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_stat) cudaFreeHost(c->h_stat);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     if (c->ev_switch) cudaEventDestroy(c->ev_switch);
     for (auto& sl : c->slot) {
         if (sl.h_in) cudaFreeHost(sl.h_in);
@@ -339,6 +259,7 @@ extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
 
 extern "C" void dipsb_destroy(dipsb_ctx* c) {
     if (!c) return;
+    comm_detach(c);
     free_all(c);
     delete c;
 }
@@ -362,6 +283,7 @@ extern "C" int32_t dipsb_reset(dipsb_ctx* c) {
     }
     c->state_valid = false; c->snapshot_pending = false; c->state_cur = 0;
     c->frames_processed = 0; c->stream_index = 0; c->scal_hi = 0;
+    c->acc_sharded = false;
     return DIPSB_OK;
 }
 
@@ -416,6 +338,7 @@ extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile
     c->tune_segments = segments;
     if (!regeo) return DIPSB_OK;
     if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_tuning: geometry can only change on a fresh or reset context");
+    if (c->comm) return fail(c, DIPSB_ERR_STATE, "set_tuning: the geometry is fixed once the context has a communicator (its planes are mapped by the peers)");
     CK(c, cudaStreamSynchronize(c->stream));
     Geometry g = c->g;
     if (!plan_geometry(g, stages, tile_px, regs, pick_kernel(c->tune_kernel, stages, regs))) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u / regs %u do not fit", tile_px, stages, regs);
@@ -449,6 +372,7 @@ extern "C" int32_t dipsb_set_kernel(dipsb_ctx* c, int32_t kernel) {
     kernel = pick_kernel(requested, c->tune_stages, c->tune_regs);
     if (kernel == c->g.kernel) { c->tune_kernel = requested; return DIPSB_OK; }
     if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_kernel: only on a fresh or reset context");
+    if (c->comm) return fail(c, DIPSB_ERR_STATE, "set_kernel: the geometry is fixed once the context has a communicator");
     CK(c, cudaStreamSynchronize(c->stream));
     Geometry g = c->g;
     if (!plan_geometry(g, c->tune_stages, c->tune_tile_px, c->tune_regs, kernel))
@@ -559,7 +483,7 @@ extern "C" int32_t dipsb_get_state_plane(dipsb_ctx* c, uint16_t* out) {
 }
 
 // ---- scalars storage -----------------------------------------------------------------------------------------------
-static int32_t ensure_scalars(dipsb_ctx* c, uint64_t upto) {
+int32_t dipsb::ensure_scalars(dipsb_ctx* c, uint64_t upto) {
     if (upto <= c->scal_cap) return DIPSB_OK;
     uint64_t cap = std::max<uint64_t>(1024, c->scal_cap);
     while (cap < upto) cap *= 2;
@@ -579,19 +503,28 @@ static int32_t ensure_scalars(dipsb_ctx* c, uint64_t upto) {
 }
 
 // ---- batch ---------------------------------------------------------------------------------------------------------
+// The extra trailing frame of a per-frame shard on a layout the clip kernel cannot stream in place: wait for its arrival
+// with a one-thread kernel, then difference it as an ordinary one-frame call (the state plane chains it to frame n-1).
+static int32_t run_extra_frame(dipsb_ctx* c, const ShardExtra& x, uint64_t index) {
+    if (x.flag) CK(c, launch_wait_flag(x.flag, x.epoch, x.timeout_ns, x.status, c->stream));
+    return run_clip_on_stream(c, x.frame, 1, (c->g.npx * c->g.bpp + 15) & ~15ull, index, true, nullptr);
+}
+
 // `zero_padded`: the rows come from the library's own re-packed buffers -- pitch a multiple of 16 and zero bytes between the
 // end of a frame and its pitch -- so the clip kernel may round its last bulk copy of a frame up to 16 bytes.
-static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first,
-                                  bool zero_padded = false) {
+int32_t dipsb::run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first,
+                                  bool zero_padded, const ShardExtra* extra) {
     const Geometry& g = c->g;
     if (n == 0) return DIPSB_OK;
+    if (extra && (!extra->frame || c->cfg.mode != DIPSB_MODE_PERFRAME)) extra = nullptr;
+    const uint64_t n_scal = n + (extra ? 1 : 0);   // scalar rows this call produces
     if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0) return fail(c, DIPSB_ERR_STATE, "run_clip: the ring flavours are streaming-only (dipsb_push_frame)");
     if (n > 0x7FFFFFFFull) return fail(c, DIPSB_ERR_INVALID, "run_clip: too many frames in one call");
     if (c->frames_processed + n > DIPSB_MAX_ACCUMULATED_FRAMES)
         return fail(c, DIPSB_ERR_STATE, "run_clip: %llu frames accumulated, %llu more would overflow the u32 sums; read the results and dipsb_reset",
                     (unsigned long long)c->frames_processed, (unsigned long long)n);
     if (stride < g.npx * g.bpp) return fail(c, DIPSB_ERR_INVALID, "run_clip: stride %llu smaller than a frame", (unsigned long long)stride);
-    int32_t rc = ensure_scalars(c, first + n);
+    int32_t rc = ensure_scalars(c, first + n_scal);
     if (rc) return rc;
     // the TMA bulk copies of the clip kernel need 16-byte aligned addresses and sizes
     // (a spatial window > 1 needs a filtered intensity plane per frame: per-frame kernels, not the clip kernel)
@@ -613,11 +546,11 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         for (uint64_t done = 0; done < n;) {
             const uint64_t m = std::min(per_chunk, n - done);
             CK(c, launch_repack(g, d_frames + done * stride, stride, fb, m, c->d_repack, dpitch, c->stream));
-            rc = run_clip_on_stream(c, c->d_repack, m, dpitch, first + done, true);
+            rc = run_clip_on_stream(c, c->d_repack, m, dpitch, first + done, true, nullptr);
             if (rc) return rc;
             done += m;
         }
-        return DIPSB_OK;
+        return extra ? run_extra_frame(c, *extra, first + n) : DIPSB_OK;
     }
     if (!c->state_valid) {   // frame 0 of the call is the reference (overall) / has no predecessor (per-frame): D = 0
         if (windowed(c)) {
@@ -632,7 +565,7 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
     if (aligned) {
         const uint32_t segs = plan_segments(c, n);
         const uint32_t words = g.n_tiles * clip_active_warps(g);
-        const uint64_t need = n * (uint64_t)((words + 3u) & ~3u);   // rows pitched to 4 words (16-byte aligned)
+        const uint64_t need = n_scal * (uint64_t)((words + 3u) & ~3u);   // rows pitched to 4 words (16-byte aligned)
         if (need >= (1ull << 32)) return fail(c, DIPSB_ERR_INVALID, "run_clip: %llu frames x %u warps exceed the per-call scalar scratch; split the call", (unsigned long long)n, words);
         if (need > c->partial_cap) {
             CK(c, cudaStreamSynchronize(c->stream));
@@ -645,6 +578,10 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         a.state_in = c->state[c->state_cur]; a.state_out = c->state[c->state_cur ^ 1];
         a.acc_sum = c->acc; a.acc_cnt = c->acc + g.n_elems; a.partials = c->partials;
         a.tau = tau; a.mode = c->cfg.mode;
+        if (extra) {
+            a.extra_frame = extra->frame; a.halo_flag = extra->flag; a.halo_epoch = extra->epoch;
+            a.wait_timeout_ns = extra->timeout_ns; a.status = extra->status;
+        }
         if (c->timing) {
             if (c->tev_used + 2 > c->tev.size()) {
                 cudaEvent_t e0, e1;
@@ -659,7 +596,7 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
             CK(c, cudaEventRecord(c->tev[c->tev_used + 1], c->stream));
             c->tev_used += 2;
         }
-        CK(c, launch_finalize_scalars(g, c->partials, (uint32_t)n, words, c->d_sad + first, c->d_cnt + first, c->stream));
+        CK(c, launch_finalize_scalars(g, c->partials, (uint32_t)n_scal, words, c->d_sad + first, c->d_cnt + first, c->stream));
         if (c->cfg.mode == DIPSB_MODE_PERFRAME) c->state_cur ^= 1;
         c->last_plan[1] = segs;
         c->last_plan[7] = 1;
@@ -685,22 +622,31 @@ static int32_t run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         }
         c->last_plan[1] = 0;
         c->last_plan[7] = 0;
+        c->frames_processed += n;
+        c->scal_hi = std::max(c->scal_hi, first + n);
+        c->stream_index = first + n;
+        return extra ? run_extra_frame(c, *extra, first + n) : DIPSB_OK;
     }
-    c->frames_processed += n;
-    c->scal_hi = std::max(c->scal_hi, first + n);
-    c->stream_index = first + n;
+    c->frames_processed += n_scal;
+    c->scal_hi = std::max(c->scal_hi, first + n_scal);
+    c->stream_index = first + n_scal;
     return DIPSB_OK;
 }
 
 extern "C" int32_t dipsb_run_clip_device(dipsb_ctx* c, const void* d_frames, uint64_t n_frames, uint64_t stride, uint64_t first) {
     if (!c || (!d_frames && n_frames)) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
-    return run_clip_on_stream(c, (const uint8_t*)d_frames, n_frames, stride, first);
+    return run_clip_on_stream(c, (const uint8_t*)d_frames, n_frames, stride, first, false, nullptr);
 }
 
 extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint64_t n, uint64_t stride, uint64_t first) {
     if (!c || (!frames && n)) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    return run_clip_host_impl(c, frames, n, stride, first, nullptr);
+}
+
+int32_t dipsb::run_clip_host_impl(dipsb_ctx* c, const uint8_t* frames, uint64_t n, uint64_t stride, uint64_t first,
+                                  const HostClipHooks* hooks) {
     const Geometry& g = c->g;
     const uint64_t fb = g.npx * g.bpp;
     if (n == 0) return DIPSB_OK;
@@ -749,7 +695,12 @@ extern "C" int32_t dipsb_run_clip_host(dipsb_ctx* c, const uint8_t* frames, uint
         }
         CK(c, cudaEventRecord(c->ev_copy[slot], c->copy_stream));
         CK(c, cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
-        int32_t rc = run_clip_on_stream(c, c->d_chunk[slot], m, dpitch, first + done, true);
+        if (done == 0 && hooks && hooks->after_first_upload) {
+            int32_t hrc = hooks->after_first_upload(c, c->d_chunk[slot], hooks->user);
+            if (hrc) return hrc;
+        }
+        const ShardExtra* extra = (hooks && done + m == n) ? hooks->extra : nullptr;
+        int32_t rc = run_clip_on_stream(c, c->d_chunk[slot], m, dpitch, first + done, true, extra);
         if (rc) return rc;
         CK(c, cudaEventRecord(c->ev_done[slot], c->stream));
         c->chunk_used[slot] = true;
@@ -1044,6 +995,7 @@ extern "C" uint64_t dipsb_frames_processed(const dipsb_ctx* c) { return c ? c->f
 extern "C" int32_t dipsb_get_accumulators(dipsb_ctx* c, uint32_t* acc_sum, uint32_t* acc_cnt) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    if (c->acc_sharded) return fail(c, DIPSB_ERR_STATE, "%s: the totals are sharded by pixel range over the ranks; call dipsb_gather_accumulators (collective) first", __func__);
     const Geometry& g = c->g;
     if (acc_sum) {
         CK(c, launch_unpermute(g, c->acc, c->planar, c->stream));
@@ -1060,6 +1012,7 @@ extern "C" int32_t dipsb_get_accumulators(dipsb_ctx* c, uint32_t* acc_sum, uint3
 extern "C" int32_t dipsb_set_accumulators(dipsb_ctx* c, const uint32_t* acc_sum, const uint32_t* acc_cnt) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    if (c->acc_sharded) return fail(c, DIPSB_ERR_STATE, "%s: the totals are sharded by pixel range over the ranks; call dipsb_gather_accumulators (collective) first", __func__);
     const Geometry& g = c->g;
     if (acc_sum) {
         CK(c, cudaMemcpyAsync(c->planar, acc_sum, g.npx * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
@@ -1080,7 +1033,7 @@ extern "C" int32_t dipsb_accumulators_device(dipsb_ctx* c, void** d_acc, uint64_
     return DIPSB_OK;
 }
 
-static int bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+int dipsb::bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
 
 extern "C" int32_t dipsb_pack_accumulators_device(dipsb_ctx* c, uint64_t total_frames, void** d_packed, uint64_t* n_words) {
     if (!c || !d_packed || !n_words || total_frames == 0) return DIPSB_ERR_INVALID;
@@ -1132,6 +1085,7 @@ extern "C" int32_t dipsb_get_scalars(dipsb_ctx* c, uint64_t first, uint64_t n, u
 extern "C" int32_t dipsb_get_intensity_map(dipsb_ctx* c, uint64_t n_eff, float* out) {
     if (!c || !out) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    if (c->acc_sharded) return fail(c, DIPSB_ERR_STATE, "%s: the totals are sharded by pixel range over the ranks; call dipsb_gather_accumulators (collective) first", __func__);
     float* d = reinterpret_cast<float*>(c->planar);
     CK(c, launch_intensity_map(c->g, c->acc, n_eff, d, c->stream));
     CK(c, cudaMemcpyAsync(out, d, c->g.npx * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

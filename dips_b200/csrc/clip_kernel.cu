@@ -70,6 +70,23 @@ __device__ __forceinline__ void mbar_wait_after(uint32_t bar, uint32_t parity, u
         "r"(parity), "r"(token), "r"(hint_ns)
         : "memory");
 }
+// the same without a suspend-time hint (one register less in the warp-specialised kernel's loop)
+__device__ __forceinline__ void mbar_wait_after(uint32_t bar, uint32_t parity, uint32_t token) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        ".reg .b32 T;\n"
+        "and.b32 T, %2, 0;\n"
+        "add.u32 T, T, %0;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [T], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity), "r"(token)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -92,6 +109,23 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+// Wait until a peer GPU (its copy engine, over NVLink) has raised *flag to `want`; the data it guards was written before
+// the flag.  Bounded: a rank that never arrives must not hang this GPU (status := 1 and the pass carries on with garbage).
+__device__ __forceinline__ void wait_peer_flag(const unsigned long long* flag, unsigned long long want, unsigned long long timeout_ns,
+                                            uint32_t* status) {
+    unsigned long long v, t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (uint32_t n = 1; flag != nullptr; ++n) {   // no flag: the frame is already there
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= want) break;
+        __nanosleep(200);
+        if ((n & 255u) == 0u) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) { if (status) atomicExch(status, 1u); break; }
+        }
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");   // the frame is read through the async proxy (TMA)
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -159,6 +193,28 @@ __device__ __forceinline__ void intensity16(const uint32_t* w, uint32_t* I) {
     }
 }
 
+// 4 B/px: one 128-bit piece = 4 pixels -> two packed registers (pixels 0,1 and 2,3)
+template <int CH>
+__device__ __forceinline__ void intensity4_x(const uint4 x, uint32_t& i01, uint32_t& i23) {
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const uint32_t a = w[2 * j], b = w[2 * j + 1];
+        uint32_t r;
+        if constexpr (CH < 0) {
+            const uint32_t t = __byte_perm(a, b, 0x5410);  // a0 a1 b0 b1
+            const uint32_t p = __byte_perm(t, 0u, 0x4240);
+            const uint32_t q = __byte_perm(t, 0u, 0x4341);
+            const uint32_t z = __byte_perm(a, b, 0x0602) & kLoMask;  // (a2, b2)
+            r = __vimax3_u16x2(p, q, z) + __vimin3_u16x2(p, q, z);
+        } else {
+            const uint32_t p = __byte_perm(a, b, sel_cross(CH, CH)) & kLoMask;
+            r = p + p;
+        }
+        if (j == 0) i01 = r; else i23 = r;
+    }
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------------------
 struct KParams {
     const uint8_t* frames;
@@ -180,6 +236,14 @@ struct KParams {
     uint32_t l2_evict_first; // 1: frames are fetched with an L2 evict-first policy (they are read exactly once)
     uint32_t wait_hint_ns;   // suspend-time hint of the consumers' mbarrier.try_wait
     uint32_t one;            // the constant 1 (an IMAD multiplier the compiler cannot fold away, see add_fma)
+    // per-frame mode across GPUs: one extra trailing frame (the next shard's first frame, pushed into this rank's window by
+    // its owner while this kernel runs) is differenced after frame n_frames-1 under scalar row n_frames; the producer waits
+    // until *halo_flag >= halo_epoch before it fetches it
+    const uint8_t* extra_frame;
+    const unsigned long long* halo_flag;
+    unsigned long long halo_epoch;
+    unsigned long long wait_timeout_ns;
+    uint32_t* status;        // set to 1 when that wait timed out (the results of this pass are then invalid)
 };
 
 // a + b on the FMA pipe (IMAD with a multiplier the compiler cannot fold): the integer ALU pipe is the busier one here
@@ -239,7 +303,8 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
     const uint32_t t1 = (uint32_t)(((uint64_t)P.n_frames * (seg + 1)) / P.n_segments);
     const bool prime_first = (MODE == 1) && (seg > 0);
     const uint32_t first = t0 - (prime_first ? 1u : 0u);
-    const uint32_t count = t1 - first;
+    const bool has_extra = (MODE == 1) && P.extra_frame != nullptr && seg == P.n_segments - 1;
+    const uint32_t count = t1 - first + (has_extra ? 1u : 0u);
 
     const uint64_t tile_first_px = (uint64_t)tile * P.tile_px;
     const uint64_t remain_px = P.npx - tile_first_px;
@@ -274,6 +339,10 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
     const uint64_t tile_byte0 = tile_first_px * BPP;
     auto issue = [&](uint32_t it, uint32_t stage) {   // frame `first + it` of the call into buffer `stage`
         const uint8_t* src = P.frames + (uint64_t)(first + it) * P.stride + tile_byte0;
+        if (has_extra && it + 1 == count) {
+            wait_peer_flag(P.halo_flag, P.halo_epoch, P.wait_timeout_ns, P.status);
+            src = P.extra_frame + tile_byte0;
+        }
         mbar_arrive_expect_tx(full_bar + 8u * stage, valid_bytes);
         if (P.l2_evict_first) bulk_g2s(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage, policy_evict_first());
         else bulk_g2s_nohint(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage);
@@ -461,7 +530,8 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
     const uint32_t t1 = (uint32_t)(((uint64_t)P.n_frames * (seg + 1)) / P.n_segments);
     const bool prime_first = (MODE == 1) && (seg > 0);
     const uint32_t first = t0 - (prime_first ? 1u : 0u);
-    const uint32_t count = t1 - first;
+    const bool has_extra = (MODE == 1) && P.extra_frame != nullptr && seg == P.n_segments - 1;   // see KParams
+    const uint32_t count = t1 - first + (has_extra ? 1u : 0u);
 
     const uint64_t tile_first_px = (uint64_t)tile * P.tile_px;
     const uint64_t remain_px = P.npx - tile_first_px;
@@ -492,6 +562,10 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
             uint32_t stage = 0, par = 1;   // the wait on a never-used buffer falls through (parity of the preceding phase)
             for (uint32_t it = 0; it < count; ++it) {
                 mbar_wait(empty_bar + 8u * stage, par);
+                if (has_extra && it + 1 == count) {   // the next shard's first frame, delivered into this rank's window
+                    wait_peer_flag(P.halo_flag, P.halo_epoch, P.wait_timeout_ns, P.status);
+                    src = P.extra_frame + tile_first_px * BPP;
+                }
                 mbar_arrive_expect_tx(full_bar + 8u * stage, valid_bytes);
                 if (P.l2_evict_first) bulk_g2s(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage, policy_evict_first());
                 else bulk_g2s_nohint(smem_base + stage * stage_bytes, src, valid_bytes, full_bar + 8u * stage);
@@ -532,7 +606,6 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
     const uint32_t my_smem = smem_base + (BPP == 3 ? tid * 48u : tid * 16u);
     const uint32_t my_step = (BPP == 3) ? 16u : nthr * 16u;
     const uint32_t one = P.one;
-    const uint32_t hint = P.wait_hint_ns;
 
     auto flush = [&]() {
         uint32_t* const acc_sum = P.acc_sum + (uint64_t)tile * slots + tid;
@@ -548,16 +621,27 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
     };
     // bytes -> packed intensities of one frame sitting in buffer `stage` (compile-time or run-time index)
     auto fetch = [&](uint32_t stage, uint32_t par, uint32_t* cur, uint32_t token) {
-        mbar_wait_after(full_bar + 8u * stage, par, token, hint);
-        uint32_t w[kWords];
+        mbar_wait_after(full_bar + 8u * stage, par, token);
+        if constexpr (BPP == 4) {
+            // convert piece by piece: only 4 raw words are live next to the 32 state / accumulator registers
 #pragma unroll
-        for (int v = 0; v < BPP; ++v) {
-            const uint4 x = lds128(my_smem + stage * stage_bytes + my_step * v);
-            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            for (int v = 0; v < 4; ++v) {
+                const uint4 x = lds128(my_smem + stage * stage_bytes + my_step * v);
+                intensity4_x<CH>(x, cur[2 * v], cur[2 * v + 1]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
+        } else {
+            uint32_t w[kWords];
+#pragma unroll
+            for (int v = 0; v < BPP; ++v) {
+                const uint4 x = lds128(my_smem + stage * stage_bytes + my_step * v);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
+            intensity16<BPP, CH>(w, cur);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
-        intensity16<BPP, CH>(w, cur);
     };
     auto emit = [&](uint32_t packed) {
         const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, packed);
@@ -567,21 +651,23 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
     };
 
     uint32_t iter = 0, token = 0, since_flush = 0;
+    uint32_t rs = 0, par = 0;   // run-time stage index / parity of the lead-in and tail (the main loop starts every trip at stage 0)
     // ---- lead-in with run-time stage index: the halo frame of a per-frame segment, then up to the next trip boundary
     if (prime_first) {
         fetch(0u, 0u, ra, token);
         part += P.words_per_frame;
-        iter = 1;
+        iter = 1; rs = 1;
+        if (rs == (uint32_t)S) { rs = 0; par ^= 1u; }
         while (iter % U != 0 && iter < count) {
-            fetch(iter % S, (iter / S) & 1u, rb, token);
+            fetch(rs, par, rb, token);
             token = emit(diff_px_ws<R>(rb, ra, accD, accM, negtau2, one));
 #pragma unroll
             for (int j = 0; j < R; ++j) ra[j] = rb[j];
             ++iter; ++since_flush;
+            if (++rs == (uint32_t)S) { rs = 0; par ^= 1u; }
         }
     }
-    // ---- main loop: U frames per trip, compile-time stages; iter is a multiple of U here
-    uint32_t par = (iter / S) & 1u;
+    // ---- main loop: U frames per trip, compile-time stages; iter is a multiple of U (hence rs == 0) here
     while (iter + U <= count) {
 #pragma unroll
         for (int u = 0; u < U; u += 2) {
@@ -600,15 +686,16 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
         since_flush += U;
         if (since_flush + U > (uint32_t)kFlushFrames) { flush(); since_flush = 0; }
     }
-    // ---- tail with run-time stage index
+    // ---- tail with run-time stage index (starts at stage 0)
     while (iter < count) {
-        fetch(iter % S, (iter / S) & 1u, rb, token);
+        fetch(rs, par, rb, token);
         token = emit(diff_px_ws<R>(rb, ra, accD, accM, negtau2, one));
         if constexpr (MODE == 1) {
 #pragma unroll
             for (int j = 0; j < R; ++j) ra[j] = rb[j];
         }
         ++iter;
+        if (++rs == (uint32_t)S) { rs = 0; par ^= 1u; }
         if (++since_flush >= (uint32_t)kFlushFrames) { flush(); since_flush = 0; }
     }
     flush();
@@ -784,6 +871,8 @@ cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
     static const int wait_hint = [] { const char* e = getenv("DIPSB_WAIT_HINT_NS"); return e ? atoi(e) : 0; }();
     kp.wait_hint_ns = (uint32_t)wait_hint;
     kp.one = 1u;
+    kp.extra_frame = a.extra_frame; kp.halo_flag = a.halo_flag; kp.halo_epoch = a.halo_epoch;
+    kp.wait_timeout_ns = a.wait_timeout_ns; kp.status = a.status;
     const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages, g.regs);
     return g.bpp == 3 ? launch_c<3>(g, a, kp, smem, s) : launch_c<4>(g, a, kp, smem, s);
 }

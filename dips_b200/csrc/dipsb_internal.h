@@ -42,6 +42,12 @@ struct ClipArgs {
     uint32_t* partials;          // u32[n_frames][n_tiles*warps]: sad | cnt<<20 per warp per frame
     uint32_t tau;                // clamped to <= 511
     int mode;                    // dipsb_mode
+    // frame-range shards, per-frame mode (comm.cu): an extra trailing frame -- the next shard's first frame -- differenced
+    // after frame n_frames-1 (scalar row n_frames); the kernel waits for *halo_flag >= halo_epoch before reading it
+    const uint8_t* extra_frame = nullptr;
+    const unsigned long long* halo_flag = nullptr;
+    unsigned long long halo_epoch = 0, wait_timeout_ns = 0;
+    uint32_t* status = nullptr;
 };
 
 // Which pixel of its tile does register slot k (0 .. 16*groups-1) of thread `thread` hold?
@@ -134,6 +140,10 @@ cudaError_t launch_pack_acc(const Geometry& g, const uint32_t* acc, uint32_t* ou
 cudaError_t launch_unpack_acc(const Geometry& g, const uint32_t* in, uint32_t* acc, int layout, int sum_bits, cudaStream_t s);
 cudaError_t launch_intensity_map(const Geometry& g, const uint32_t* acc_internal, uint64_t n_eff, float* out,
                                  cudaStream_t s);
+
+// comm.cu: one-thread kernel that waits (bounded) until *flag >= want
+cudaError_t launch_wait_flag(const unsigned long long* flag, unsigned long long want, unsigned long long timeout_ns,
+                             uint32_t* status, cudaStream_t s);
 
 void count_launch(uint64_t n = 1);
 

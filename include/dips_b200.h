@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define DIPSB_ABI_VERSION 1
+#define DIPSB_ABI_VERSION 2
 /* frames one context may accumulate between resets: 510 * this still fits the u32 per-pixel sums (~39 h of 60 fps video);
  * a call that would exceed it fails with DIPSB_ERR_STATE instead of wrapping */
 #define DIPSB_MAX_ACCUMULATED_FRAMES 8421504ull
@@ -202,6 +202,87 @@ int32_t dipsb_get_scalars(dipsb_ctx *ctx, uint64_t first, uint64_t n, uint64_t *
 /* X6 float outputs: acc_sum/(510*n_eff) per pixel, sad[t]/(510*W*H) per frame */
 int32_t dipsb_get_intensity_map(dipsb_ctx *ctx, uint64_t n_eff, float *out);
 int32_t dipsb_get_frame_means(dipsb_ctx *ctx, uint64_t first, uint64_t n, float *out);
+
+/* ---- several GPUs: frame-range shards of one clip ------------------------------------------- */
+/*
+ * The reference drives one adapter (dips/src/gpu/mod.rs:71-78); long clips shard naturally by frame range over the GPUs of
+ * a box.  Rank r of R owns the contiguous frames dipsb_shard_range gives it and runs them through its own
+ * context; per clip the library exchanges
+ *   overall mode    the u16 reference plane of frame 0, ncclBroadcast from rank 0 before the pass;
+ *   per-frame mode  the one-frame halo: every rank starts at once from its own first frame while its copy engine pushes
+ *                   that frame over NVLink to the previous rank, whose clip kernel differences it as one extra trailing
+ *                   frame (nothing is exchanged before the pass; the boundary frame's scalars are handed to the rank
+ *                   that owns the frame with the accumulator exchange);
+ *   at the end      the per-pixel accumulators: a reduce-scatter written by the library's own kernels over peer memory
+ *                   (packed partial sums stored straight into the owner's window over NVLink), after which every rank
+ *                   holds the totals of the pixel range it owns until dipsb_gather_accumulators (a collective all-gather
+ *                   over the same peer memory) completes the planes everywhere.  Without peer memory, or on request
+ *                   (DIPSB_REDUCE_NCCL): pack -> ncclAllReduce -> unpack, totals replicated at once.
+ * Per-frame scalars stay on the rank that owns the frame.  Integer sums: the result is bit-identical to one GPU.
+ *
+ * Two ways to form the ranks:
+ *   one process per GPU   rank 0 calls dipsb_comm_unique_id and hands the 128 bytes to the others by any means (a file,
+ *                         MPI, torchrun's store); every rank calls dipsb_comm_init_rank on its context (collective:
+ *                         ncclCommInitRank + mapping of the peers' windows with cudaIpc*), then, per clip,
+ *                         dipsb_reset + dipsb_run_clip_sharded_device/_host.
+ *   one process, all GPUs dipsb_create_group makes one context per device, ncclCommInitAll and peer access; the
+ *                         dipsb_group_* calls drive all ranks from the calling thread.
+ * NCCL is loaded at run time (dlopen libnccl.so.2) by these calls only.
+ */
+#define DIPSB_UNIQUE_ID_BYTES 128
+enum dipsb_reduce_path { DIPSB_REDUCE_AUTO = 0, DIPSB_REDUCE_P2P = 1, DIPSB_REDUCE_NCCL = 2 };
+typedef struct dipsb_group dipsb_group;
+
+/* frames [*first, *first + *count) of a total_frames clip owned by `rank` of `nranks` (contiguous, disjoint, covering) */
+void dipsb_shard_range(uint64_t total_frames, uint32_t nranks, uint32_t rank, uint64_t *first, uint64_t *count);
+/* host-only: exchange format of the peer-memory reduce for such a clip: out[0] bytes per accumulator element (4: sum |
+ * count << out[1] in one u32, 8: two u32), out[1] sum bits, out[2] frames a rank may difference (ceil(total/nranks) + 1),
+ * out[3] accumulator elements owned per rank for planes of n_elems elements */
+int32_t dipsb_xchg_plan_query(uint64_t total_frames, uint32_t nranks, uint64_t n_elems, uint64_t out[4]);
+int32_t dipsb_comm_unique_id(void *id128);
+int32_t dipsb_comm_init_rank(dipsb_ctx *ctx, uint32_t nranks, uint32_t rank, const void *id128);
+int32_t dipsb_comm_destroy(dipsb_ctx *ctx);
+/* out: [0] ranks, [1] rank, [2] 1 = peers' windows mapped (peer-memory kernels available), [3] NCCL version, [4] the
+ * dipsb_reduce_path in effect, [5] 1 = single-process group, [6] 1 = the accumulators currently hold totals only in this
+ * rank's owned range, [7] 1 = NCCL communicator present */
+int32_t dipsb_comm_info(const dipsb_ctx *ctx, uint32_t out[8]);
+int32_t dipsb_comm_set_reduce(dipsb_ctx *ctx, int32_t path);
+/* DIPSB_ERR_STATE if a bounded wait for a peer GPU timed out since the last check (DIPSB_COMM_TIMEOUT_MS, default 5000):
+ * a rank never arrived and the results are invalid.  Synchronises the stream. */
+int32_t dipsb_comm_check(dipsb_ctx *ctx);
+/*
+ * One pass over this rank's shard of a total_frames clip: the n_frames frames starting at logical index
+ * first_frame_index (at most ceil(total_frames / ranks)); collective -- every rank of the communicator calls it once per
+ * dipsb_reset.  Asynchronous; ordered on the context's stream (the halo push uses the context's copy stream).
+ */
+int32_t dipsb_run_clip_sharded_device(dipsb_ctx *ctx, const void *d_frames, uint64_t n_frames, uint64_t frame_stride_bytes,
+                                      uint64_t first_frame_index, uint64_t total_frames);
+int32_t dipsb_run_clip_sharded_host(dipsb_ctx *ctx, const uint8_t *frames, uint64_t n_frames, uint64_t frame_stride_bytes,
+                                    uint64_t first_frame_index, uint64_t total_frames);
+/* with dipsb_enable_timing: summed milliseconds of the three phases of the sharded passes since the last call -- [0] reference
+ * / halo exchange before the pass, [1] the pass (prime, clip kernel, scalars), [2] accumulator exchange -- and their number.
+ * Event pairs on the context's stream; a phase that waits for a slower rank contains that wait.  Synchronises. */
+int32_t dipsb_comm_phase_times(dipsb_ctx *ctx, double out_ms[3], uint64_t *passes);
+/* collective: complete the accumulator planes on every rank (no-op when they already are); then dipsb_get_accumulators,
+ * dipsb_get_intensity_map ... work as on one GPU.  Those calls fail with DIPSB_ERR_STATE while the totals are sharded. */
+int32_t dipsb_gather_accumulators(dipsb_ctx *ctx);
+
+/* single process: ndev contexts of the same configuration on devices[0..ndev-1] (NULL: 0..ndev-1; cfg->device is ignored).
+ * Listing one device several times gives a loopback group (no NCCL, ranks share the device) for tests on one GPU. */
+int32_t dipsb_create_group(const dipsb_config *cfg, uint32_t ndev, const int32_t *devices, dipsb_group **out);
+void dipsb_destroy_group(dipsb_group *grp);
+uint32_t dipsb_group_size(const dipsb_group *grp);
+dipsb_ctx *dipsb_group_ctx(dipsb_group *grp, uint32_t rank);    /* borrowed: per-rank setters, scalars, tuning queries */
+const char *dipsb_group_last_error(const dipsb_group *grp);      /* grp may be NULL: last error of dipsb_create_group */
+int32_t dipsb_group_reset(dipsb_group *grp);
+/* shard i = n_frames[i] frames at d_frames[i] (resident on device i), in clip order; total = their sum */
+int32_t dipsb_group_run_clip_device(dipsb_group *grp, const void *const *d_frames, const uint64_t *n_frames,
+                                    uint64_t frame_stride_bytes);
+int32_t dipsb_group_gather_accumulators(dipsb_group *grp);
+int32_t dipsb_group_synchronize(dipsb_group *grp);
+/* the clip's combined maps (gathers first when needed) and the scalars of its frames, each from the rank that owns them */
+int32_t dipsb_group_get_accumulators(dipsb_group *grp, uint32_t *acc_sum, uint32_t *acc_cnt);
+int32_t dipsb_group_get_scalars(dipsb_group *grp, uint64_t first, uint64_t n, uint64_t *sad, uint64_t *cnt);
 
 /* ---- utilities ------------------------------------------------------------------------------ */
 /* deterministic synthetic clip generated on the device (same bytes as the oracle's generator) */

@@ -10,6 +10,16 @@ pub struct dipsb_ctx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct dipsb_group {
+    _private: [u8; 0],
+}
+
+pub const DIPSB_UNIQUE_ID_BYTES: usize = 128;
+pub const DIPSB_REDUCE_AUTO: i32 = 0;
+pub const DIPSB_REDUCE_P2P: i32 = 1;
+pub const DIPSB_REDUCE_NCCL: i32 = 2;
+
 pub const DIPSB_OK: i32 = 0;
 pub const DIPSB_NOT_READY: i32 = 1;
 pub const DIPSB_ERR_INVALID: i32 = -1;
@@ -104,4 +114,28 @@ extern "C" {
     pub fn dipsb_set_kernel(ctx: *mut dipsb_ctx, kernel: i32) -> i32;
     pub fn dipsb_plan_query(width: u32, height: u32, format: i32, num_sms: u32, out: *mut u32) -> i32;
     pub fn dipsb_set_tuning(ctx: *mut dipsb_ctx, stages: u32, tile_px: u32, segments: u32, regs: u32) -> i32;
+    // several GPUs: frame-range shards of one clip (include/dips_b200.h, "several GPUs")
+    pub fn dipsb_shard_range(total_frames: u64, nranks: u32, rank: u32, first: *mut u64, count: *mut u64);
+    pub fn dipsb_xchg_plan_query(total_frames: u64, nranks: u32, n_elems: u64, out: *mut u64) -> i32;
+    pub fn dipsb_comm_unique_id(id128: *mut c_void) -> i32;
+    pub fn dipsb_comm_init_rank(ctx: *mut dipsb_ctx, nranks: u32, rank: u32, id128: *const c_void) -> i32;
+    pub fn dipsb_comm_destroy(ctx: *mut dipsb_ctx) -> i32;
+    pub fn dipsb_comm_info(ctx: *const dipsb_ctx, out: *mut u32) -> i32;
+    pub fn dipsb_comm_set_reduce(ctx: *mut dipsb_ctx, path: i32) -> i32;
+    pub fn dipsb_comm_check(ctx: *mut dipsb_ctx) -> i32;
+    pub fn dipsb_run_clip_sharded_device(ctx: *mut dipsb_ctx, d_frames: *const c_void, n_frames: u64, frame_stride_bytes: u64, first_frame_index: u64, total_frames: u64) -> i32;
+    pub fn dipsb_run_clip_sharded_host(ctx: *mut dipsb_ctx, frames: *const u8, n_frames: u64, frame_stride_bytes: u64, first_frame_index: u64, total_frames: u64) -> i32;
+    pub fn dipsb_comm_phase_times(ctx: *mut dipsb_ctx, out_ms: *mut f64, passes: *mut u64) -> i32;
+    pub fn dipsb_gather_accumulators(ctx: *mut dipsb_ctx) -> i32;
+    pub fn dipsb_create_group(cfg: *const dipsb_config, ndev: u32, devices: *const i32, out: *mut *mut dipsb_group) -> i32;
+    pub fn dipsb_destroy_group(grp: *mut dipsb_group);
+    pub fn dipsb_group_size(grp: *const dipsb_group) -> u32;
+    pub fn dipsb_group_ctx(grp: *mut dipsb_group, rank: u32) -> *mut dipsb_ctx;
+    pub fn dipsb_group_last_error(grp: *const dipsb_group) -> *const c_char;
+    pub fn dipsb_group_reset(grp: *mut dipsb_group) -> i32;
+    pub fn dipsb_group_run_clip_device(grp: *mut dipsb_group, d_frames: *const *const c_void, n_frames: *const u64, frame_stride_bytes: u64) -> i32;
+    pub fn dipsb_group_gather_accumulators(grp: *mut dipsb_group) -> i32;
+    pub fn dipsb_group_synchronize(grp: *mut dipsb_group) -> i32;
+    pub fn dipsb_group_get_accumulators(grp: *mut dipsb_group, acc_sum: *mut u32, acc_cnt: *mut u32) -> i32;
+    pub fn dipsb_group_get_scalars(grp: *mut dipsb_group, first: u64, n: u64, sad: *mut u64, cnt: *mut u64) -> i32;
 }

@@ -26,7 +26,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dips_b200.h but not exported"
     assert set(names) == set(_lib.SYMBOLS), set(names) ^ set(_lib.SYMBOLS)
-    assert _lib.load().dipsb_abi_version() == 1
+    assert _lib.load().dipsb_abi_version() == 2
 
 
 def test_config_struct_layout():
