@@ -60,6 +60,7 @@ def parse_args():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-stream", action="store_true")
     p.add_argument("--no-preflight", action="store_true")
+    p.add_argument("--no-comm-probes", dest="comm_probes", action="store_false")
     p.add_argument("--reduce", choices=["auto", "p2p", "nccl"], default="auto",
                    help="accumulator exchange: the library's peer-memory kernels or pack + ncclAllReduce + unpack")
     p.add_argument("--stages", type=int, default=0)
@@ -193,7 +194,7 @@ def config_of(wl, world):
             "seed": hex(SEED), "profile": "scene", "parallelism": f"frame-shard x{world} (strong scaling: one clip, {world} contiguous frame ranges)",
             "exchange": ("none (single GPU)" if world == 1 else
                          "per clip, issued by libdips_b200.so: " +
-                         ("reference plane of frame 0 ncclBroadcast from rank 0" if mode == 0 else
+                         ("reference plane of frame 0 scattered by rank 0's prime kernel and all-gathered over peer memory" if mode == 0 else
                           "one-frame halo pushed over NVLink by the copy engine during the pass") +
                          " + accumulator reduce-scatter over peer memory (totals stay sharded by pixel range; gathered on read-out)"),
             "l2": "clip shard per GPU >> 126 MB L2 (inputs larger than L2)"}
@@ -375,9 +376,13 @@ class Bench:
         if sharded:
             (ex_ms, run_ms, red_ms), n_pass = ctx.comm_phase_times()
             n_pass = max(n_pass, 1)
-            phases.update({"exchange_before_pass_ms": ex_ms / n_pass, "prime+clip+finalize_ms": run_ms / n_pass,
-                           "accumulator_exchange_ms": red_ms / n_pass,
-                           "note": "event pairs on this rank's stream (rank 0); a phase that waits for a slower rank contains the wait"})
+            mine = {"exchange_before_pass_ms": ex_ms / n_pass, "prime+clip+finalize_ms": run_ms / n_pass,
+                    "accumulator_exchange_ms": red_ms / n_pass}
+            phases.update(mine)
+            phases["note"] = "event pairs on this rank's stream (rank 0); a phase that waits for a slower rank contains the wait"
+            allp = [None] * self.world
+            self.dist.all_gather_object(allp, mine)
+            phases["per_rank"] = {k: [round(p[k], 4) for p in allp] for k in mine}
             ctx.comm_check()
         ctx.enable_timing(False)
         per_rank = self.gather_floats(kern_avg_ms)
@@ -446,6 +451,19 @@ class Bench:
             probe_ms = ctx.stream_probe(clip.data_ptr(), n_local, fb, 3)      # compute-free TMA stream, same tiles
             roofline["stream_probe_GBps"] = n_local * fb / (probe_ms / 1e3) / 1e9
             roofline["frac_of_stream_probe"] = probe_ms / kern_avg_ms
+        if sharded and self.args.comm_probes:
+            # the exchanges alone, back to back after a barrier (no pass in between, so no waiting for a slower rank's kernel)
+            info = ctx.comm_info()
+            probes = {}
+            for key, what, need in (("reduce_scatter_p2p_ms", 0, info["peer_memory"]), ("reference_broadcast_nccl_ms", 1, info["nccl"]),
+                                    ("allgather_p2p_ms", 2, info["peer_memory"]), ("pack_allreduce_unpack_nccl_ms", 3, info["nccl"]),
+                                    ("reference_broadcast_p2p_ms", 4, info["peer_memory"] and mode == 0)):
+                if need:
+                    self.fence()
+                    probes[key] = self.max_over_ranks(ctx.comm_probe(what, total, 10))
+            ctx.reset()
+            ctx.comm_check()
+            phases["exchange_probes"] = probes
         res = {"name": name, "value": value, "unit": "frames/s", "ms_per_step": ms_total / steps, "steps": steps,
                "hbm_GBps_per_gpu_whole_step": n_local * fb * steps / (ms_total / 1e3) / 1e9,
                "phases": phases, "roofline": roofline, "sustained": sustained, "clocks": clocks, "plan": plan,

@@ -82,6 +82,7 @@ SYMBOLS = {
     "dipsb_run_clip_sharded_device": (_i32, [_vp, _vp, _u64, _u64, _u64, _u64]),
     "dipsb_run_clip_sharded_host": (_i32, [_vp, _vp, _u64, _u64, _u64, _u64]),
     "dipsb_comm_phase_times": (_i32, [_vp, C.POINTER(C.c_double * 3), C.POINTER(_u64)]),
+    "dipsb_comm_probe": (_i32, [_vp, _i32, _u64, _u32, C.POINTER(C.c_float)]),
     "dipsb_gather_accumulators": (_i32, [_vp]),
     "dipsb_create_group": (_i32, [C.POINTER(Config), _u32, C.POINTER(_i32), C.POINTER(_vp)]),
     "dipsb_destroy_group": (None, [_vp]),

@@ -339,6 +339,13 @@ class Context:
         self._ck(self._lib.dipsb_comm_phase_times(self._h, C.byref(ms), C.byref(n)))
         return (float(ms[0]), float(ms[1]), float(ms[2])), int(n.value)
 
+    def comm_probe(self, what: int, total_frames: int, reps: int = 10) -> float:
+        """collective measurement aid: mean ms of back-to-back exchanges (0 reduce-scatter, 1 broadcast, 2 all-gather,
+        3 NCCL all-reduce path); leaves the accumulators undefined"""
+        ms = C.c_float()
+        self._ck(self._lib.dipsb_comm_probe(self._h, what, total_frames, reps, C.byref(ms)))
+        return float(ms.value)
+
     def gather_accumulators(self) -> None:
         """collective: complete the accumulator planes on every rank after a sharded pass"""
         self._ck(self._lib.dipsb_gather_accumulators(self._h))

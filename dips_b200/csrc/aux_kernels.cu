@@ -4,9 +4,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "dipsb_internal.h"
+#include "intensity.cuh"
+#include "peer_sync.cuh"
 
 namespace dipsb {
 
@@ -35,6 +38,37 @@ __global__ void prime_kernel(const uint8_t* __restrict__ frame, uint64_t npx, in
                              uint16_t* __restrict__ state) {
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
         state[p] = (uint16_t)intensity2(frame + p * bpp, chan_byte);
+}
+
+// K1, vectorised: 16 pixels per thread -- 3 or 4 128-bit loads, packed intensity, two 128-bit stores (base 16-byte aligned,
+// npx a multiple of 16).  With a PlaneScatter (rank 0 of a sharded overall-mode pass) slice j of the plane is stored into
+// rank j's state plane as well, and the last block stamps the peers: the scatter half of the reference-plane broadcast.
+template <int BPP, int CH>
+__global__ void __launch_bounds__(256) prime16_kernel(const uint8_t* __restrict__ frame, uint64_t npx, uint16_t* __restrict__ state,
+                                                      const PlaneScatter sc) {
+    const uint64_t groups = npx / 16;
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(frame + g * (16 * BPP));
+        uint32_t w[BPP * 4];
+#pragma unroll
+        for (int v = 0; v < BPP; ++v) {
+            const uint4 x = __ldg(src + v);
+            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        }
+        uint32_t I[8];
+        intensity16<BPP, CH>(w, I);
+        const uint4 lo = make_uint4(I[0], I[1], I[2], I[3]), hi = make_uint4(I[4], I[5], I[6], I[7]);
+        uint4* dst = reinterpret_cast<uint4*>(state + g * 16);
+        dst[0] = lo; dst[1] = hi;
+        if (sc.nranks) {
+            const uint32_t owner = (uint32_t)((g * 16) / sc.slice_px);
+            if (owner != 0u) {
+                uint4* rdst = reinterpret_cast<uint4*>(sc.plane_peer[owner] + g * 16);
+                rdst[0] = lo; rdst[1] = hi;
+            }
+        }
+    }
+    if (sc.nranks) stamp_when_last(sc.blocks_done, sc.stamp_peer, sc.nranks, sc.epoch);
 }
 
 // K1': upper median of 4 start frames, pre_compute_shader.wgsl:103-131 (element [2] of the ascending sort)
@@ -417,8 +451,31 @@ inline int grid_for(uint64_t n, const Geometry& g) {
 
 }  // namespace
 
-cudaError_t launch_prime(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s) {
-    prime_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(frame, g.npx, g.bpp, g.chan_byte, state);
+bool prime_fast_path(const Geometry& g, const uint8_t* frame) { return ((uintptr_t)frame & 15u) == 0 && (g.npx & 15u) == 0; }
+
+template <int BPP>
+static void launch_prime16(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s, const PlaneScatter& sc) {
+    const uint64_t groups = g.npx / 16;
+    const uint64_t cap = (uint64_t)(g.num_sms ? g.num_sms : 148) * 8;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((groups + 255) / 256, cap));
+    switch (g.chan_byte) {
+        case 0: prime16_kernel<BPP, 0><<<grid, 256, 0, s>>>(frame, g.npx, state, sc); break;
+        case 1: prime16_kernel<BPP, 1><<<grid, 256, 0, s>>>(frame, g.npx, state, sc); break;
+        case 2: prime16_kernel<BPP, 2><<<grid, 256, 0, s>>>(frame, g.npx, state, sc); break;
+        default: prime16_kernel<BPP, -1><<<grid, 256, 0, s>>>(frame, g.npx, state, sc); break;
+    }
+}
+
+// scatter != nullptr requires prime_fast_path (the caller falls back to prime + a separate push otherwise)
+cudaError_t launch_prime(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s, const PlaneScatter* scatter) {
+    if (prime_fast_path(g, frame)) {
+        const PlaneScatter none;
+        if (g.bpp == 3) launch_prime16<3>(g, frame, state, s, scatter ? *scatter : none);
+        else launch_prime16<4>(g, frame, state, s, scatter ? *scatter : none);
+    } else {
+        if (scatter) return cudaErrorInvalidValue;
+        prime_kernel<<<grid_for(g.npx, g), kThreads, 0, s>>>(frame, g.npx, g.bpp, g.chan_byte, state);
+    }
     count_launch();
     return cudaGetLastError();
 }

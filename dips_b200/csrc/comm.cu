@@ -36,13 +36,13 @@
 #include <vector>
 
 #include "dipsb_ctx.h"
+#include "peer_sync.cuh"
 
 using namespace dipsb;
 
 namespace dipsb {
 
-constexpr int kMaxRanks = 16;
-constexpr uint32_t kXchgBlocks = 592;      // the same on every rank: the arrival counters count blocks
+constexpr uint32_t kXchgBlocks = 592;      // 4 blocks of 256 threads per SM
 constexpr uint32_t kXchgThreads = 256;
 constexpr size_t kCtrlBytes = 4096;
 
@@ -116,13 +116,15 @@ static NcclApi* nccl_api(std::string* why) {
 //   [4096, + 2*halo_bytes)         halo frame buffers, one per epoch parity (per-frame mode; zero padded to 16 bytes)
 //   then 2 * nranks * slot_bytes   receive slots of the accumulator exchange: [parity][source rank][chunk * 8 bytes]
 struct Control {
-    unsigned long long xchg_arrived[kMaxRanks];     // per source rank: its blocks that finished pushing partial sums (monotonic)
+    unsigned long long xchg_arrived[kMaxRanks];     // per source rank: the last pass whose partial sums it has pushed here (monotonic)
     unsigned long long gather_arrived[kMaxRanks];   // same for the all-gather of the totals
     unsigned long long halo_stamp[2];     // epoch whose halo frame sits in halo buffer [parity]
-    unsigned long long plane_stamp;       // epoch whose reference plane was pushed into my state plane (no-NCCL broadcast)
+    unsigned long long plane_stamp;       // epoch whose reference plane (my slice of it) rank 0 has pushed into my state plane
+    unsigned long long plane_stamp2[kMaxRanks];   // per source rank: epoch whose slice of the reference plane it forwarded here
     unsigned long long my_stamp[2];       // source words of the stamp copies this rank sends (written by stamp_kernel)
     unsigned long long mbox[2][2];        // [parity]{sad, cnt} of my first frame, computed by the previous rank
     uint32_t status;                      // != 0: a bounded wait timed out
+    uint32_t blocks_done[4];              // local: finished blocks of the running exchange / gather / plane scatter / plane forward kernel
 };
 static_assert(sizeof(Control) <= kCtrlBytes, "control block");
 
@@ -162,41 +164,11 @@ struct dipsb_group {
 
 namespace {
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// bounded spin of one thread until *p >= want; false (and *status = 1) on timeout
-__device__ bool spin_until(const unsigned long long* p, unsigned long long want, unsigned long long timeout_ns, uint32_t* status) {
-    const unsigned long long t0 = global_timer();
-    for (uint32_t n = 1;; ++n) {
-        if (ld_acquire_sys(p) >= want) return true;
-        __nanosleep(100);
-        if ((n & 255u) == 0u && global_timer() - t0 > timeout_ns) {
-            if (status) atomicExch(status, 1u);
-            return false;
-        }
-    }
-}
-
 __global__ void wait_flag_kernel(const unsigned long long* flag, unsigned long long want, unsigned long long timeout_ns,
                                  uint32_t* status) {
     spin_until(flag, want, timeout_ns, status);
 }
 __global__ void stamp_kernel(unsigned long long* word, unsigned long long value) { *word = value; }
-// raise a stamp in every peer's control block (system-scope release after whatever preceded it on the stream)
-struct StampTargets { unsigned long long* p[kMaxRanks]; int n; };
-__global__ void stamp_peers_kernel(StampTargets t, unsigned long long value) {
-    __threadfence_system();
-    if ((int)threadIdx.x < t.n) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.p[threadIdx.x]), "l"(value) : "memory");
-}
-
 // ---- the accumulator exchange ----------------------------------------------------------------------------------------
 struct XchgParams {
     uint32_t* acc;                // local planes: sum[n_elems] then cnt[n_elems], internal tile order
@@ -207,10 +179,11 @@ struct XchgParams {
     uint64_t slot_bytes;          // bytes between two source ranks' slots in a receive area
     const uint8_t* recv_local;    // my receive area of this parity
     uint8_t* recv_peer[kMaxRanks];
-    unsigned long long* arrived_local;
-    unsigned long long* arrived_peer[kMaxRanks];
+    unsigned long long* arrived_local;        // my xchg_arrived[]: one stamp per source rank
+    unsigned long long* stamp_peer[kMaxRanks]; // peer r's xchg_arrived[my rank] (null for myself)
     unsigned long long target, timeout_ns;
     uint32_t* status;
+    uint32_t* blocks_done;
     // per-frame boundary scalars: mine for the next rank's first frame go into its mailbox; my own first frame's come in
     const unsigned long long* sad_src; const unsigned long long* cnt_src; unsigned long long* mbox_next;
     const unsigned long long* mbox_local; unsigned long long* sad_dst; unsigned long long* cnt_dst;
@@ -222,38 +195,44 @@ __device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x 
 
 // Reduce-scatter over peer memory, two launches.
 // xchg_push_kernel: every element this rank does not own is packed and stored into its owner's receive slot (remote stores
-// over NVLink, 16 bytes per thread, 512 contiguous bytes per warp); each block then raises this rank's arrival counter in
-// every peer's window.  It never waits, so it always completes -- whatever else is resident on the GPU.
-// xchg_reduce_kernel: waits until all blocks of every peer have arrived (one counter per source rank, monotonic over the
-// passes: a fast peer's next pass cannot stand in for a slow peer's current one), then adds the N-1 received partials of
-// the owned range to the local ones, in place.
+// over NVLink, 16 bytes per thread, 512 contiguous bytes per warp); its last block then stamps this rank's slot in every
+// peer's window with the pass number.  It never waits, so it always completes -- whatever else is resident on the GPU.
+// xchg_reduce_kernel: waits until every peer's stamp has reached this pass (one stamp per source rank, monotonic over
+// the passes: a fast peer's next pass cannot stand in for a slow peer's current one), then adds the N-1 received partials
+// of the owned range to the local ones, in place.
 __global__ void __launch_bounds__(kXchgThreads) xchg_push_kernel(const XchgParams P) {
-    const uint64_t units = P.n_elems / 4;
-    const uint64_t own_lo = (uint64_t)P.rank * P.chunk, own_hi = min(own_lo + P.chunk, P.n_elems);
     const uint32_t* sum = P.acc;
     const uint32_t* cnt = P.acc + P.n_elems;
     if (blockIdx.x == 0 && threadIdx.x == 0 && P.mbox_next) {
         P.mbox_next[0] = *P.sad_src;
         P.mbox_next[1] = *P.cnt_src;
     }
-    for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < units; u += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = 4 * u;
-        if (i >= own_lo && i < own_hi) continue;
-        const uint32_t owner = (uint32_t)(i / P.chunk);
-        const uint4 s = ld4(sum + i), c = ld4(cnt + i);
-        uint8_t* slot = P.recv_peer[owner] + (uint64_t)P.rank * P.slot_bytes;
-        const uint64_t k = i - (uint64_t)owner * P.chunk;
-        if (P.fmt == 1) {
-            st4(reinterpret_cast<uint32_t*>(slot) + k,
-                make_uint4(s.x | (c.x << P.sum_bits), s.y | (c.y << P.sum_bits), s.z | (c.z << P.sum_bits), s.w | (c.w << P.sum_bits)));
-        } else {
-            st4(reinterpret_cast<uint32_t*>(slot) + k, s);
-            st4(reinterpret_cast<uint32_t*>(slot) + P.chunk + k, c);
+    // Owners are visited in the order rank+1, rank+2, ...: at any moment every rank sends to a different owner, so no GPU's
+    // NVLink ingress takes the traffic of all the others at once.  Two 16-byte pieces per thread and step are in flight.
+    const uint64_t chunk_units = P.chunk / 4, total_units = P.n_elems / 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint32_t k = 1; k < P.nranks; ++k) {
+        const uint32_t owner = (P.rank + k) % P.nranks;
+        const uint64_t lo = (uint64_t)owner * chunk_units, hi = min(lo + chunk_units, total_units);
+        uint32_t* slot = reinterpret_cast<uint32_t*>(P.recv_peer[owner] + (uint64_t)P.rank * P.slot_bytes);
+        for (uint64_t u = lo + t0; u < hi; u += 2 * stride) {
+            const uint64_t u2 = u + stride;
+            const bool two = u2 < hi;
+            const uint4 s0 = ld4(sum + 4 * u), c0 = ld4(cnt + 4 * u);
+            uint4 s1 = s0, c1 = c0;
+            if (two) { s1 = ld4(sum + 4 * u2); c1 = ld4(cnt + 4 * u2); }
+            const uint64_t k0 = 4 * (u - lo), k1 = 4 * (u2 - lo);
+            if (P.fmt == 1) {
+                st4(slot + k0, make_uint4(s0.x | (c0.x << P.sum_bits), s0.y | (c0.y << P.sum_bits), s0.z | (c0.z << P.sum_bits), s0.w | (c0.w << P.sum_bits)));
+                if (two) st4(slot + k1, make_uint4(s1.x | (c1.x << P.sum_bits), s1.y | (c1.y << P.sum_bits), s1.z | (c1.z << P.sum_bits), s1.w | (c1.w << P.sum_bits)));
+            } else {
+                st4(slot + k0, s0);
+                st4(slot + P.chunk + k0, c0);
+                if (two) { st4(slot + k1, s1); st4(slot + P.chunk + k1, c1); }
+            }
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < P.nranks && threadIdx.x != P.rank) atomicAdd_system(P.arrived_peer[threadIdx.x] + P.rank, 1ull);
+    stamp_when_last(P.blocks_done, P.stamp_peer, P.nranks, P.target);
 }
 
 __global__ void __launch_bounds__(kXchgThreads) xchg_reduce_kernel(const XchgParams P) {
@@ -294,27 +273,53 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_reduce_kernel(const XchgPar
 struct GatherParams {
     uint32_t* acc; uint64_t n_elems, chunk; uint32_t nranks, rank;
     uint32_t* acc_peer[kMaxRanks];
-    unsigned long long* arrived_local; unsigned long long* arrived_peer[kMaxRanks];
-    unsigned long long target, timeout_ns; uint32_t* status;
+    unsigned long long* arrived_local; unsigned long long* stamp_peer[kMaxRanks];
+    unsigned long long target, timeout_ns; uint32_t* status; uint32_t* blocks_done;
 };
 __global__ void __launch_bounds__(kXchgThreads) gather_push_kernel(const GatherParams P) {
     const uint64_t own_lo = (uint64_t)P.rank * P.chunk, own_hi = min(own_lo + P.chunk, P.n_elems);
     for (uint64_t u = own_lo / 4 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < own_hi / 4; u += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = 4 * u;
         const uint4 s = ld4(P.acc + i), c = ld4(P.acc + P.n_elems + i);
-        for (uint32_t r = 0; r < P.nranks; ++r) {
-            if (r == P.rank) continue;
+        for (uint32_t k = 1; k < P.nranks; ++k) {
+            const uint32_t r = (P.rank + k) % P.nranks;
             st4(P.acc_peer[r] + i, s);
             st4(P.acc_peer[r] + P.n_elems + i, c);
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < P.nranks && threadIdx.x != P.rank) atomicAdd_system(P.arrived_peer[threadIdx.x] + P.rank, 1ull);
+    stamp_when_last(P.blocks_done, P.stamp_peer, P.nranks, P.target);
 }
-__global__ void wait_sources_kernel(const unsigned long long* arrived, uint32_t nranks, uint32_t rank, unsigned long long target,
+
+// Reference-plane broadcast over peer memory: ranges of the local u16 plane go to peers' planes.  Scatter (rank 0 without the
+// fused prime kernel): slice d -> rank d.  Forward (ranks > 0): wait for rank 0's stamp, then my slice -> every rank but 0 and
+// me.  Then the last block stamps the receivers.
+struct PlanePush {
+    const uint16_t* plane; uint16_t* dst[kMaxRanks];
+    uint64_t lo[kMaxRanks], hi[kMaxRanks];      // per destination: range in 16-byte units (lo == hi: nothing)
+    uint32_t nranks, rank;
+    const unsigned long long* wait_flag; unsigned long long wait_value, timeout_ns; uint32_t* status;
+    unsigned long long* stamp_peer[kMaxRanks]; unsigned long long stamp; uint32_t* blocks_done;
+};
+__global__ void __launch_bounds__(kXchgThreads) plane_push_kernel(const PlanePush P) {
+    if (P.wait_flag) {
+        __shared__ int ok;
+        if (threadIdx.x == 0) ok = spin_until(P.wait_flag, P.wait_value, P.timeout_ns, P.status) ? 1 : 0;
+        __syncthreads();
+        if (!ok) return;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(P.plane);
+    for (uint32_t k = 1; k < P.nranks; ++k) {
+        const uint32_t d = (P.rank + k) % P.nranks;
+        uint4* dst = reinterpret_cast<uint4*>(P.dst[d]);
+        for (uint64_t u = P.lo[d] + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < P.hi[d]; u += (uint64_t)gridDim.x * blockDim.x)
+            dst[u] = src[u];
+    }
+    stamp_when_last(P.blocks_done, P.stamp_peer, P.nranks, P.stamp);
+}
+// one warp holds the stream until the stamps of the source ranks in `mask` have reached `target`
+__global__ void wait_sources_kernel(const unsigned long long* arrived, uint32_t mask, unsigned long long target,
                                     unsigned long long timeout_ns, uint32_t* status) {
-    if (threadIdx.x < nranks && threadIdx.x != rank) spin_until(arrived + threadIdx.x, target, timeout_ns, status);
+    if ((mask >> threadIdx.x) & 1u) spin_until(arrived + threadIdx.x, target, timeout_ns, status);
 }
 
 Control* ctrl_of(uint8_t* win) { return reinterpret_cast<Control*>(win); }
@@ -564,7 +569,27 @@ extern "C" int32_t dipsb_comm_check(dipsb_ctx* c) {
 // ---- one sharded pass, in three phases (the group runner interleaves them over its devices) ----------------------------
 namespace {
 
-bool use_p2p_reduce(const Comm* m) { return m->p2p && m->reduce_path != DIPSB_REDUCE_NCCL; }
+bool use_p2p_reduce(const Comm* m) { return m->p2p && m->reduce_path != DIPSB_REDUCE_NCCL; }   // both exchanges follow it
+
+// slices of the reference plane for its broadcast over peer memory: slice j (pixels [j*slice_px, (j+1)*slice_px)) is
+// rank j's to forward
+uint64_t plane_slice_px(const Geometry& g, int nranks) {
+    const uint64_t groups = (g.npx + 15) / 16;
+    return 16 * ((groups + (uint64_t)nranks - 1) / (uint64_t)nranks);
+}
+PlaneScatter make_scatter(dipsb_ctx* c) {
+    Comm* m = c->comm;
+    PlaneScatter sc;
+    sc.nranks = (uint32_t)m->nranks;
+    sc.slice_px = plane_slice_px(c->g, m->nranks);
+    for (int r = 1; r < m->nranks; ++r) {
+        sc.plane_peer[r] = m->state_peer[r][0];
+        sc.stamp_peer[r] = &ctrl_of(m->win_peer[r])->plane_stamp;
+    }
+    sc.epoch = m->epoch;
+    sc.blocks_done = &ctrl_of(m->win)->blocks_done[2];
+    return sc;
+}
 
 struct Pass {
     const uint8_t* d_frames = nullptr;     // device clip (or nullptr for a host clip)
@@ -572,6 +597,7 @@ struct Pass {
     uint64_t n = 0, stride = 0, first = 0, total = 0;
     ShardExtra extra;
     bool has_extra = false;
+    bool scattered = false;                // rank 0: the prime kernel already stored the slices of the plane into their owners
 };
 
 int32_t validate_pass(dipsb_ctx* c, const Pass& p) {
@@ -600,8 +626,16 @@ int32_t pass_begin(dipsb_ctx* c, Pass& p) {
     const uint64_t fb = g.npx * g.bpp;
     if (c->cfg.mode == DIPSB_MODE_OVERALL) {
         if (m->rank == 0) {
+            if (c->state_cur != 0) return fail(c, DIPSB_ERR_STATE, "run_clip_sharded: overall mode expects the reference in state plane 0 (dipsb_reset first)");
+            const bool fuse = use_p2p_reduce(m);
             if (p.d_frames) {
-                CK(c, launch_prime(g, p.d_frames, c->state[c->state_cur], c->stream));
+                if (fuse && prime_fast_path(g, p.d_frames)) {
+                    const PlaneScatter sc = make_scatter(c);
+                    CK(c, launch_prime(g, p.d_frames, c->state[0], c->stream, &sc));
+                    p.scattered = true;
+                } else {
+                    CK(c, launch_prime(g, p.d_frames, c->state[0], c->stream));
+                }
             } else {   // host clip: frame 0 goes up on its own first
                 if (c->d_frame_bytes < fb) {
                     cudaFree(c->d_frame); c->d_frame = nullptr; c->d_frame_bytes = 0;
@@ -624,7 +658,13 @@ int32_t pass_begin(dipsb_ctx* c, Pass& p) {
                     host_copy2d(c->h_pin, fb, p.h_frames, fb, fb, 1);
                     CK(c, cudaMemcpyAsync(c->d_frame, c->h_pin, fb, cudaMemcpyHostToDevice, c->stream));
                 }
-                CK(c, launch_prime(g, c->d_frame, c->state[c->state_cur], c->stream));
+                if (fuse && prime_fast_path(g, c->d_frame)) {
+                    const PlaneScatter sc = make_scatter(c);
+                    CK(c, launch_prime(g, c->d_frame, c->state[0], c->stream, &sc));
+                    p.scattered = true;
+                } else {
+                    CK(c, launch_prime(g, c->d_frame, c->state[0], c->stream));
+                }
             }
             c->state_valid = true;
         }
@@ -692,26 +732,57 @@ int32_t push_halo_after_upload(dipsb_ctx* c, const uint8_t* d_first_frame, void*
 }
 
 // phase B: the exchange before the pass that needs every rank (inside ncclGroupStart/End when one thread drives several)
-int32_t pass_exchange(dipsb_ctx* c, Pass& p) {
+int32_t pass_exchange(dipsb_ctx* c, Pass& p, int phase = 7) {
     Comm* m = c->comm;
     const Geometry& g = c->g;
     if (m->nranks == 1) return DIPSB_OK;
     if (c->cfg.mode == DIPSB_MODE_OVERALL) {
-        if (m->comm) {
-            uint16_t* plane = c->state[c->state_cur];
-            NK(c, m->nccl, m->nccl->Broadcast(plane, plane, g.npx * sizeof(uint16_t), ncclUint8, 0, m->comm, c->stream));
-        } else if (m->rank == 0) {   // no NCCL (loopback group): copy-engine pushes and a stamp
-            StampTargets t{};
+        if (!use_p2p_reduce(m)) {   // NCCL: one broadcast of the u16 plane from rank 0
+            if (!m->comm) return fail(c, DIPSB_ERR_STATE, "run_clip_sharded: neither peer memory nor NCCL available");
+            if (phase & 1) NK(c, m->nccl, m->nccl->Broadcast(c->state[0], c->state[0], g.npx * sizeof(uint16_t), ncclUint8, 0, m->comm, c->stream));
+            return DIPSB_OK;
+        }
+        // Peer memory: scatter + all-gather.  Rank 0 stores slice j of the plane into rank j (fused into its prime kernel when
+        // the frame allows) and starts its pass at once; every other rank forwards its slice to the rest, then waits for theirs.
+        // Every NVLink carries 1/N of the plane per step instead of rank 0 sending the whole plane N-1 times or a ring passing it
+        // on hop by hop (measured at 8 GPUs: the last rank of NCCL's broadcast ring started 0.26 ms after the first).
+        const uint64_t slice_px = plane_slice_px(g, m->nranks), top = (g.npx + 15) / 16 * 16;
+        PlanePush P{};
+        P.plane = c->state[0]; P.nranks = (uint32_t)m->nranks; P.rank = (uint32_t)m->rank;
+        P.timeout_ns = m->timeout_ns; P.status = &ctrl_of(m->win)->status;
+        if ((phase & 1) && m->rank == 0 && !p.scattered) {
             for (int r = 1; r < m->nranks; ++r) {
-                CK(c, cudaMemcpyAsync(m->state_peer[r][0], c->state[c->state_cur], g.npx * sizeof(uint16_t), cudaMemcpyDeviceToDevice, c->stream));
-                t.p[t.n++] = &ctrl_of(m->win_peer[r])->plane_stamp;
+                P.dst[r] = m->state_peer[r][0];
+                P.lo[r] = std::min((uint64_t)r * slice_px, top) / 8; P.hi[r] = std::min((uint64_t)(r + 1) * slice_px, top) / 8;
+                P.stamp_peer[r] = &ctrl_of(m->win_peer[r])->plane_stamp;
             }
-            stamp_peers_kernel<<<1, 32, 0, c->stream>>>(t, m->epoch);
+            P.stamp = m->epoch; P.blocks_done = &ctrl_of(m->win)->blocks_done[2];
+            plane_push_kernel<<<kXchgBlocks, kXchgThreads, 0, c->stream>>>(P);
+            count_launch();
+            CK(c, cudaGetLastError());
+        }
+        if ((phase & 2) && m->rank > 0) {
+            for (int r = 1; r < m->nranks; ++r) {
+                if (r == m->rank) continue;
+                P.dst[r] = m->state_peer[r][0];
+                P.lo[r] = std::min((uint64_t)m->rank * slice_px, top) / 8; P.hi[r] = std::min((uint64_t)(m->rank + 1) * slice_px, top) / 8;
+                P.stamp_peer[r] = ctrl_of(m->win_peer[r])->plane_stamp2 + m->rank;
+            }
+            P.wait_flag = &ctrl_of(m->win)->plane_stamp; P.wait_value = m->epoch;
+            P.stamp = m->epoch; P.blocks_done = &ctrl_of(m->win)->blocks_done[3];
+            plane_push_kernel<<<kXchgBlocks / 2, kXchgThreads, 0, c->stream>>>(P);
+            count_launch();
+            CK(c, cudaGetLastError());
+        }
+        if ((phase & 4) && m->rank > 0 && m->nranks > 2) {
+            const uint32_t mask = ((1u << m->nranks) - 1u) & ~1u & ~(1u << m->rank);
+            wait_sources_kernel<<<1, 32, 0, c->stream>>>(ctrl_of(m->win)->plane_stamp2, mask, m->epoch, m->timeout_ns, &ctrl_of(m->win)->status);
             count_launch();
             CK(c, cudaGetLastError());
         }
         return DIPSB_OK;
     }
+    if (!(phase & 1)) return DIPSB_OK;
     if (!m->p2p && m->comm) {   // halo by NCCL: my first frame -> previous rank (device clips only; host clips upload it first)
         const uint64_t fb = g.npx * g.bpp;
         const uint8_t* src = p.d_frames;
@@ -735,12 +806,7 @@ int32_t pass_exchange(dipsb_ctx* c, Pass& p) {
 // phase C: the pass itself
 int32_t pass_run(dipsb_ctx* c, Pass& p) {
     Comm* m = c->comm;
-    if (m->nranks > 1 && c->cfg.mode == DIPSB_MODE_OVERALL && m->rank > 0) {
-        if (!m->comm) {   // plane pushed by rank 0's copy engine: wait for its stamp
-            CK(c, launch_wait_flag(&ctrl_of(m->win)->plane_stamp, m->epoch, m->timeout_ns, &ctrl_of(m->win)->status, c->stream));
-        }
-        c->state_valid = true;
-    }
+    if (m->nranks > 1 && c->cfg.mode == DIPSB_MODE_OVERALL && m->rank > 0) c->state_valid = true;   // the plane has arrived
     const ShardExtra* extra = p.has_extra ? &p.extra : nullptr;
     if (p.d_frames) return run_clip_on_stream(c, p.d_frames, p.n, p.stride, p.first, false, extra);
     HostClipHooks hooks;
@@ -766,11 +832,12 @@ int32_t pass_reduce(dipsb_ctx* c, Pass& p, int phase = 15) {
         X.recv_local = recv_area(m, m->win, parity);
         for (int r = 0; r < m->nranks; ++r) {
             X.recv_peer[r] = recv_area(m, m->win_peer[r], parity);
-            X.arrived_peer[r] = ctrl_of(m->win_peer[r])->xchg_arrived;
+            X.stamp_peer[r] = r == m->rank ? nullptr : ctrl_of(m->win_peer[r])->xchg_arrived + m->rank;
         }
         X.arrived_local = ctrl_of(m->win)->xchg_arrived;
-        X.target = m->epoch * (uint64_t)kXchgBlocks;
+        X.target = m->epoch;                       // stamp of this pass
         X.timeout_ns = m->timeout_ns; X.status = &ctrl_of(m->win)->status;
+        X.blocks_done = &ctrl_of(m->win)->blocks_done[0];
         if (perframe && m->rank + 1 < m->nranks) {
             X.sad_src = reinterpret_cast<const unsigned long long*>(c->d_sad + p.first + p.n);
             X.cnt_src = reinterpret_cast<const unsigned long long*>(c->d_cnt + p.first + p.n);
@@ -886,8 +953,68 @@ extern "C" int32_t dipsb_comm_phase_times(dipsb_ctx* c, double out_ms[3], uint64
     return DIPSB_OK;
 }
 
+static int32_t gather_enqueue(dipsb_ctx* c, int phase);
+
+// Measurement aid (collective): mean milliseconds of `reps` back-to-back exchanges on this rank's stream, without a pass in
+// between -- what = 0: accumulator reduce-scatter over peer memory (push + reduce kernels), 1: reference-plane ncclBroadcast
+// from rank 0, 2: all-gather of the totals, 3: pack + ncclAllReduce + unpack, 4: reference-plane scatter + all-gather over
+// peer memory.  Leaves the accumulators and the state plane undefined (dipsb_reset).
+extern "C" int32_t dipsb_comm_probe(dipsb_ctx* c, int32_t what, uint64_t total_frames, uint32_t reps, float* ms) {
+    if (!c || !ms || !reps || what < 0 || what > 4) return DIPSB_ERR_INVALID;
+    Comm* m = c->comm;
+    if (!m || m->nranks < 2 || m->single_process) return fail(c, DIPSB_ERR_STATE, "comm_probe: needs a multi-process communicator of at least 2 ranks");
+    if ((what == 0 || what == 2 || what == 4) && !m->p2p) return fail(c, DIPSB_ERR_STATE, "comm_probe: peer memory is not mapped");
+    if ((what == 1 || what == 3) && !m->comm) return fail(c, DIPSB_ERR_STATE, "comm_probe: no NCCL communicator");
+    CK(c, cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CK(c, cudaEventCreate(&e0));
+    CK(c, cudaEventCreate(&e1));
+    Pass p;
+    p.total = total_frames ? total_frames : 1; p.n = 1; p.first = (uint64_t)m->rank;
+    const int keep_path = m->reduce_path;
+    for (uint32_t r = 0; r <= reps; ++r) {          // rep 0 is a warm-up
+        if (r == 1) CK(c, cudaEventRecord(e0, c->stream));
+        int32_t rc = DIPSB_OK;
+        if (what == 0 || what == 3) {
+            m->epoch += 1;
+            m->reduce_path = what == 0 ? DIPSB_REDUCE_P2P : DIPSB_REDUCE_NCCL;
+            const int mode = c->cfg.mode;
+            c->cfg.mode = DIPSB_MODE_OVERALL;        // no boundary scalars in the probe
+            const uint64_t fp = c->frames_processed;
+            c->frames_processed = 0;
+            rc = pass_reduce(c, p);
+            c->frames_processed = fp;
+            c->cfg.mode = mode;
+            m->reduce_path = keep_path;
+        } else if (what == 1) {
+            uint16_t* plane = c->state[c->state_cur];
+            NK(c, m->nccl, m->nccl->Broadcast(plane, plane, c->g.npx * sizeof(uint16_t), ncclUint8, 0, m->comm, c->stream));
+        } else if (what == 4) {                      // scatter + forward + wait over peer memory (the plane itself, no prime)
+            m->epoch += 1;
+            m->reduce_path = DIPSB_REDUCE_P2P;
+            const int mode = c->cfg.mode;
+            c->cfg.mode = DIPSB_MODE_OVERALL;
+            rc = pass_exchange(c, p, 7);
+            c->cfg.mode = mode;
+            m->reduce_path = keep_path;
+        } else {
+            c->acc_sharded = true;
+            rc = gather_enqueue(c, 3);
+        }
+        if (rc) return rc;
+    }
+    CK(c, cudaEventRecord(e1, c->stream));
+    CK(c, cudaEventSynchronize(e1));
+    float total = 0.f;
+    CK(c, cudaEventElapsedTime(&total, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->acc_sharded = false;
+    *ms = total / (float)reps;
+    return DIPSB_OK;
+}
+
 // collective: after it every rank holds the complete accumulator planes
-static int32_t gather_enqueue(dipsb_ctx* c, int phase = 3) {
+static int32_t gather_enqueue(dipsb_ctx* c, int phase) {
     Comm* m = c->comm;
     if (!m || m->nranks == 1 || !c->acc_sharded) { c->acc_sharded = false; return DIPSB_OK; }
     const Geometry& g = c->g;
@@ -895,20 +1022,21 @@ static int32_t gather_enqueue(dipsb_ctx* c, int phase = 3) {
     G.acc = c->acc; G.n_elems = g.n_elems; G.chunk = m->chunk; G.nranks = (uint32_t)m->nranks; G.rank = (uint32_t)m->rank;
     for (int r = 0; r < m->nranks; ++r) {
         G.acc_peer[r] = m->acc_peer[r];
-        G.arrived_peer[r] = ctrl_of(m->win_peer[r])->gather_arrived;
+        G.stamp_peer[r] = r == m->rank ? nullptr : ctrl_of(m->win_peer[r])->gather_arrived + m->rank;
     }
     G.arrived_local = ctrl_of(m->win)->gather_arrived;
-    G.target = m->gathers * (uint64_t)kXchgBlocks;
+    G.target = m->gathers;
     G.timeout_ns = m->timeout_ns; G.status = &ctrl_of(m->win)->status;
+    G.blocks_done = &ctrl_of(m->win)->blocks_done[1];
     if (phase & 1) {
         m->gathers += 1;
-        G.target = m->gathers * (uint64_t)kXchgBlocks;
+        G.target = m->gathers;
         gather_push_kernel<<<kXchgBlocks, kXchgThreads, 0, c->stream>>>(G);
         count_launch();
         CK(c, cudaGetLastError());
     }
     if (phase & 2) {
-        wait_sources_kernel<<<1, 32, 0, c->stream>>>(G.arrived_local, G.nranks, G.rank, G.target, G.timeout_ns, G.status);
+        wait_sources_kernel<<<1, 32, 0, c->stream>>>(G.arrived_local, ((1u << m->nranks) - 1u) & ~(1u << m->rank), G.target, G.timeout_ns, G.status);
         count_launch();
         CK(c, cudaGetLastError());
         c->acc_sharded = false;
@@ -921,7 +1049,7 @@ extern "C" int32_t dipsb_gather_accumulators(dipsb_ctx* c) {
     CK(c, cudaSetDevice(c->device));
     if (c->comm && c->comm->single_process && c->comm->nranks > 1)
         return fail(c, DIPSB_ERR_STATE, "gather_accumulators: this context belongs to a single-process group; use dipsb_group_gather_accumulators");
-    return gather_enqueue(c);
+    return gather_enqueue(c, 3);
 }
 
 // ---- single-process group: one handle, all GPUs (SURVEY.md 8(b) dipsb_create_group, 8(e) ncclCommInitAll) -------------
@@ -1073,11 +1201,14 @@ extern "C" int32_t dipsb_group_run_clip_device(dipsb_group* grp, const void* con
         return DIPSB_OK;
     }
     for (size_t i = 0; i < R; ++i) { cudaSetDevice(grp->ctx[i]->device); GRP(grp, i, pass_begin(grp->ctx[i], pass[i])); }
-    if (grp->nccl) grp->nccl->GroupStart();
-    for (size_t i = 0; i < R; ++i) { cudaSetDevice(grp->ctx[i]->device); GRP(grp, i, pass_exchange(grp->ctx[i], pass[i])); }
-    if (grp->nccl) grp->nccl->GroupEnd();
-    int32_t rc = loopback_fence(grp);   // per-frame: the halo pushes; overall: the plane pushes
-    if (rc) return rc;
+    int32_t rc = DIPSB_OK;
+    for (int bit : {1, 2, 4}) {         // scatter (or the NCCL calls, grouped) | forward | wait; loopback: one phase at a time
+        if (grp->loopback && (rc = loopback_fence(grp))) return rc;
+        if (grp->nccl && bit == 1) grp->nccl->GroupStart();
+        for (size_t i = 0; i < R; ++i) { cudaSetDevice(grp->ctx[i]->device); GRP(grp, i, pass_exchange(grp->ctx[i], pass[i], bit)); }
+        if (grp->nccl && bit == 1) grp->nccl->GroupEnd();
+    }
+    if ((rc = loopback_fence(grp))) return rc;   // per-frame: the halo pushes; overall: the plane
     for (size_t i = 0; i < R; ++i) { cudaSetDevice(grp->ctx[i]->device); GRP(grp, i, pass_run(grp->ctx[i], pass[i])); }
     if (!use_p2p_reduce(grp->ctx[0]->comm)) {   // NCCL path (the same on every rank): its collective bits grouped
         for (int bit : {1, 2, 4, 8}) {

@@ -9,6 +9,7 @@ namespace dipsb {
 constexpr int kPxPerThread = 16;        // pixels owned by one thread of the clip kernel (8 packed u16x2 registers)
 constexpr int kFlushFrames = 128;       // 510*128 < 65536: packed u16 accumulators are flushed to u32 every 128 frames
 constexpr int kMaxStages = 8;
+constexpr int kMaxRanks = 16;          // GPUs one clip can be sharded over (one box)
 
 // Geometry of one context (fixed at create time so that the internal accumulator order never changes).
 struct Geometry {
@@ -80,7 +81,19 @@ uint32_t clip_active_warps(const Geometry& g);
 cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s);
 cudaError_t launch_stream_probe(const Geometry& g, const uint8_t* frames, uint64_t stride, uint32_t n_frames, cudaStream_t s);
 
-cudaError_t launch_prime(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s);
+// Scatter step of the reference-plane broadcast, fused into rank 0's prime kernel (comm.cu): slice j of the plane is also
+// stored into rank j's state plane over NVLink, and the kernel's last block stamps every peer.
+struct PlaneScatter {
+    uint32_t nranks = 0;                          // 0: no scatter
+    uint64_t slice_px = 0;                        // pixels per slice (multiple of 512); slice j belongs to rank j
+    uint16_t* plane_peer[kMaxRanks] = {};
+    unsigned long long* stamp_peer[kMaxRanks] = {};   // null: nobody to tell
+    unsigned long long epoch = 0;
+    uint32_t* blocks_done = nullptr;
+};
+// true when the vectorised prime kernel (16 pixels per thread, 128-bit loads) can take this frame
+bool prime_fast_path(const Geometry& g, const uint8_t* frame);
+cudaError_t launch_prime(const Geometry& g, const uint8_t* frame, uint16_t* state, cudaStream_t s, const PlaneScatter* scatter = nullptr);
 cudaError_t launch_prime_median4(const Geometry& g, const uint8_t* frames, uint64_t stride, uint16_t* state,
                                  cudaStream_t s);
 cudaError_t launch_finalize_scalars(const Geometry& g, const uint32_t* partials, uint32_t n_frames,

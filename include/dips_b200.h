@@ -208,7 +208,9 @@ int32_t dipsb_get_frame_means(dipsb_ctx *ctx, uint64_t first, uint64_t n, float 
  * The reference drives one adapter (dips/src/gpu/mod.rs:71-78); long clips shard naturally by frame range over the GPUs of
  * a box.  Rank r of R owns the contiguous frames dipsb_shard_range gives it and runs them through its own
  * context; per clip the library exchanges
- *   overall mode    the u16 reference plane of frame 0, ncclBroadcast from rank 0 before the pass;
+ *   overall mode    the u16 reference plane of frame 0, before the pass: rank 0's prime kernel stores slice j of it straight
+ *                   into rank j over NVLink and starts at once, the other ranks forward their slices to each other
+ *                   (scatter + all-gather over peer memory); or one ncclBroadcast (DIPSB_REDUCE_NCCL);
  *   per-frame mode  the one-frame halo: every rank starts at once from its own first frame while its copy engine pushes
  *                   that frame over NVLink to the previous rank, whose clip kernel differences it as one extra trailing
  *                   frame (nothing is exchanged before the pass; the boundary frame's scalars are handed to the rank
@@ -263,6 +265,11 @@ int32_t dipsb_run_clip_sharded_host(dipsb_ctx *ctx, const uint8_t *frames, uint6
  * / halo exchange before the pass, [1] the pass (prime, clip kernel, scalars), [2] accumulator exchange -- and their number.
  * Event pairs on the context's stream; a phase that waits for a slower rank contains that wait.  Synchronises. */
 int32_t dipsb_comm_phase_times(dipsb_ctx *ctx, double out_ms[3], uint64_t *passes);
+/* measurement aid (collective, multi-process communicators): mean milliseconds of `reps` back-to-back exchanges without a
+ * pass in between -- what 0: accumulator reduce-scatter over peer memory, 1: reference-plane ncclBroadcast, 2: all-gather of
+ * the totals, 3: pack + ncclAllReduce + unpack, 4: reference-plane scatter + all-gather over peer memory.  Leaves the
+ * accumulators and the state plane undefined: dipsb_reset afterwards. */
+int32_t dipsb_comm_probe(dipsb_ctx *ctx, int32_t what, uint64_t total_frames, uint32_t reps, float *ms);
 /* collective: complete the accumulator planes on every rank (no-op when they already are); then dipsb_get_accumulators,
  * dipsb_get_intensity_map ... work as on one GPU.  Those calls fail with DIPSB_ERR_STATE while the totals are sharded. */
 int32_t dipsb_gather_accumulators(dipsb_ctx *ctx);

@@ -126,6 +126,7 @@ extern "C" {
     pub fn dipsb_run_clip_sharded_device(ctx: *mut dipsb_ctx, d_frames: *const c_void, n_frames: u64, frame_stride_bytes: u64, first_frame_index: u64, total_frames: u64) -> i32;
     pub fn dipsb_run_clip_sharded_host(ctx: *mut dipsb_ctx, frames: *const u8, n_frames: u64, frame_stride_bytes: u64, first_frame_index: u64, total_frames: u64) -> i32;
     pub fn dipsb_comm_phase_times(ctx: *mut dipsb_ctx, out_ms: *mut f64, passes: *mut u64) -> i32;
+    pub fn dipsb_comm_probe(ctx: *mut dipsb_ctx, what: i32, total_frames: u64, reps: u32, ms: *mut f32) -> i32;
     pub fn dipsb_gather_accumulators(ctx: *mut dipsb_ctx) -> i32;
     pub fn dipsb_create_group(cfg: *const dipsb_config, ndev: u32, devices: *const i32, out: *mut *mut dipsb_group) -> i32;
     pub fn dipsb_destroy_group(grp: *mut dipsb_group);
