@@ -516,7 +516,9 @@ int32_t dipsb::run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
                                   bool zero_padded, const ShardExtra* extra) {
     const Geometry& g = c->g;
     if (n == 0) return DIPSB_OK;
-    if (extra && (!extra->frame || c->cfg.mode != DIPSB_MODE_PERFRAME)) extra = nullptr;
+    const ShardPush* push = (extra && extra->push.nranks) ? &extra->push : nullptr;
+    bool* pushed = extra ? extra->pushed : nullptr;
+    if (extra && (!extra->frame || c->cfg.mode != DIPSB_MODE_PERFRAME)) extra = nullptr;   // no trailing frame
     const uint64_t n_scal = n + (extra ? 1 : 0);   // scalar rows this call produces
     if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0) return fail(c, DIPSB_ERR_STATE, "run_clip: the ring flavours are streaming-only (dipsb_push_frame)");
     if (n > 0x7FFFFFFFull) return fail(c, DIPSB_ERR_INVALID, "run_clip: too many frames in one call");
@@ -581,6 +583,10 @@ int32_t dipsb::run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         if (extra) {
             a.extra_frame = extra->frame; a.halo_flag = extra->flag; a.halo_epoch = extra->epoch;
             a.wait_timeout_ns = extra->timeout_ns; a.status = extra->status;
+        }
+        if (push && clip_can_push(g, segs)) {
+            a.push = push;
+            if (pushed) *pushed = true;
         }
         if (c->timing) {
             if (c->tev_used + 2 > c->tev.size()) {

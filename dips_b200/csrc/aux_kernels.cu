@@ -40,32 +40,46 @@ __global__ void prime_kernel(const uint8_t* __restrict__ frame, uint64_t npx, in
         state[p] = (uint16_t)intensity2(frame + p * bpp, chan_byte);
 }
 
-// K1, vectorised: 16 pixels per thread -- 3 or 4 128-bit loads, packed intensity, two 128-bit stores (base 16-byte aligned,
-// npx a multiple of 16).  With a PlaneScatter (rank 0 of a sharded overall-mode pass) slice j of the plane is stored into
-// rank j's state plane as well, and the last block stamps the peers: the scatter half of the reference-plane broadcast.
+// K1, vectorised: 16 pixels per thread -- 3 or 4 128-bit loads, packed intensity (base 16-byte aligned, npx a multiple of
+// 16).  The 32 bytes a thread produces are exchanged through shared memory so that every store instruction of a warp covers
+// 512 contiguous bytes: half-filled 32-byte sectors cost nothing in the local L2 but double the packets of a remote store.
+// With a PlaneScatter (rank 0 of a sharded overall-mode pass) slice k of the plane is stored into rank k+1's state plane as
+// well, and the last block stamps the peers: the scatter half of the reference-plane broadcast.
 template <int BPP, int CH>
 __global__ void __launch_bounds__(256) prime16_kernel(const uint8_t* __restrict__ frame, uint64_t npx, uint16_t* __restrict__ state,
                                                       const PlaneScatter sc) {
+    __shared__ uint4 xbuf[8][64];
     const uint64_t groups = npx / 16;
-    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4* src = reinterpret_cast<const uint4*>(frame + g * (16 * BPP));
-        uint32_t w[BPP * 4];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    // whole warps iterate together (g0 = the warp's first group): the exchange below needs all 32 lanes
+    for (uint64_t g0 = blockIdx.x * (uint64_t)blockDim.x + warp * 32u; g0 < groups; g0 += stride) {
+        const uint64_t g = g0 + lane;
+        uint32_t I[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (g < groups) {
+            const uint4* src = reinterpret_cast<const uint4*>(frame + g * (16 * BPP));
+            uint32_t w[BPP * 4];
 #pragma unroll
-        for (int v = 0; v < BPP; ++v) {
-            const uint4 x = __ldg(src + v);
-            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
-        }
-        uint32_t I[8];
-        intensity16<BPP, CH>(w, I);
-        const uint4 lo = make_uint4(I[0], I[1], I[2], I[3]), hi = make_uint4(I[4], I[5], I[6], I[7]);
-        uint4* dst = reinterpret_cast<uint4*>(state + g * 16);
-        dst[0] = lo; dst[1] = hi;
-        if (sc.nranks) {
-            const uint32_t owner = (uint32_t)((g * 16) / sc.slice_px);
-            if (owner != 0u) {
-                uint4* rdst = reinterpret_cast<uint4*>(sc.plane_peer[owner] + g * 16);
-                rdst[0] = lo; rdst[1] = hi;
+            for (int v = 0; v < BPP; ++v) {
+                const uint4 x = __ldg(src + v);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
             }
+            intensity16<BPP, CH>(w, I);
+        }
+        xbuf[warp][2 * lane] = make_uint4(I[0], I[1], I[2], I[3]);
+        xbuf[warp][2 * lane + 1] = make_uint4(I[4], I[5], I[6], I[7]);
+        __syncwarp();
+        const uint4 a = xbuf[warp][lane], b = xbuf[warp][32 + lane];
+        __syncwarp();
+        // 16-byte unit u of the warp's 1 KB holds pixels 8u .. 8u+7 of the 512 starting at 16*g0
+        const uint64_t valid_units = min((uint64_t)64, 2 * (groups - g0));
+        uint4* dst = reinterpret_cast<uint4*>(state + g0 * 16);
+        if (lane < valid_units) dst[lane] = a;
+        if (32 + lane < valid_units) dst[32 + lane] = b;
+        if (sc.nranks) {   // slice k of the plane belongs to rank k + 1; a warp's 512 pixels may straddle two slices
+            const uint64_t pa = g0 * 16 + 8ull * lane, pb = pa + 256;
+            if (lane < valid_units) reinterpret_cast<uint4*>(sc.plane_peer[1u + (uint32_t)(pa / sc.slice_px)] + g0 * 16)[lane] = a;
+            if (32 + lane < valid_units) reinterpret_cast<uint4*>(sc.plane_peer[1u + (uint32_t)(pb / sc.slice_px)] + g0 * 16)[32 + lane] = b;
         }
     }
     if (sc.nranks) stamp_when_last(sc.blocks_done, sc.stamp_peer, sc.nranks, sc.epoch);

@@ -163,6 +163,13 @@ struct KParams {
     unsigned long long halo_epoch;
     unsigned long long wait_timeout_ns;
     uint32_t* status;        // set to 1 when that wait timed out (the results of this pass are then invalid)
+    // frame-range shards: the LAST flush of the pass hands the elements this rank does not own straight to their owners --
+    // total so far (local plane + registers), packed, stored into the owner's receive slot over NVLink -- so the accumulator
+    // exchange needs no separate pass over the planes and overlaps the streaming of the tiles that are still running
+    uint32_t xchg_nranks;    // 0: ordinary flush
+    uint32_t xchg_own_lo, xchg_own_len, xchg_chunk;   // owned element range of this rank, elements per owner
+    uint32_t xchg_fmt, xchg_sum_bits;                 // 1: sum | cnt << bits in one u32; 2: two u32 (cnt at +chunk)
+    uint32_t* xchg_recv[kMaxRanks];                   // owner's receive slot for this rank, this pass
 };
 
 // a + b on the FMA pipe (IMAD with a multiplier the compiler cannot fold): the integer ALU pipe is the busier one here
@@ -538,6 +545,27 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
             accD[j] = accM[j] = 0u;
         }
     };
+    // last flush of a sharded pass (KParams::xchg_*): owned elements as above; every other element's total goes to its owner
+    auto flush_to_owners = [&]() {
+        const uint32_t base = tile * slots + tid;          // the host takes this path only for planes of < 2^32 elements
+#pragma unroll
+        for (int k = 0; k < 2 * R; ++k) {
+            const uint32_t idx = base + (uint32_t)k * nthr;
+            const uint32_t d = (k & 1) ? accD[k / 2] >> 16 : accD[k / 2] & 0xFFFFu;
+            const uint32_t m = (k & 1) ? accM[k / 2] >> 16 : accM[k / 2] & 0xFFFFu;
+            if (idx - P.xchg_own_lo < P.xchg_own_len) {
+                atomicAdd(P.acc_sum + idx, d);
+                atomicAdd(P.acc_cnt + idx, m);
+            } else {
+                // atomics with return: ordered behind this thread's earlier RED.ADDs to the same words
+                const uint32_t sum = atomicAdd(P.acc_sum + idx, d) + d, cnt = atomicAdd(P.acc_cnt + idx, m) + m;
+                const uint32_t owner = idx / P.xchg_chunk, off = idx - owner * P.xchg_chunk;
+                uint32_t* slot = P.xchg_recv[owner];
+                if (P.xchg_fmt == 1u) slot[off] = sum | (cnt << P.xchg_sum_bits);
+                else { slot[off] = sum; slot[P.xchg_chunk + off] = cnt; }
+            }
+        }
+    };
     // bytes -> packed intensities of one frame sitting in buffer `stage` (compile-time or run-time index)
     auto fetch = [&](uint32_t stage, uint32_t par, uint32_t* cur, uint32_t token) {
         mbar_wait_after(full_bar + 8u * stage, par, token);
@@ -617,7 +645,7 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
         if (++rs == (uint32_t)S) { rs = 0; par ^= 1u; }
         if (++since_flush >= (uint32_t)kFlushFrames) { flush(); since_flush = 0; }
     }
-    flush();
+    if (P.xchg_nranks) flush_to_owners(); else flush();
     (void)kFlushEvery;
 
     if (MODE == 1 && seg == P.n_segments - 1) {
@@ -738,6 +766,8 @@ inline uint32_t stage_bytes_of(uint32_t threads, int bpp, int groups) { return (
 
 }  // namespace
 
+bool clip_can_push(const Geometry& g, uint32_t n_segments) { return g.kernel == 1 && n_segments == 1 && g.n_elems < (1ull << 32); }
+
 int clip_groups(int regs) { return regs >= 128 ? 2 : 1; }
 
 size_t clip_smem_bytes(uint32_t threads, int bpp, uint32_t stages, int regs) {
@@ -792,6 +822,15 @@ cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
     kp.one = 1u;
     kp.extra_frame = a.extra_frame; kp.halo_flag = a.halo_flag; kp.halo_epoch = a.halo_epoch;
     kp.wait_timeout_ns = a.wait_timeout_ns; kp.status = a.status;
+    kp.xchg_nranks = 0;
+    if (a.push && a.push->nranks && clip_can_push(g, a.n_segments)) {
+        const ShardPush& x = *a.push;
+        kp.xchg_nranks = x.nranks; kp.xchg_chunk = (uint32_t)x.chunk;
+        kp.xchg_own_lo = (uint32_t)((uint64_t)x.rank * x.chunk);
+        kp.xchg_own_len = (uint32_t)(std::min<uint64_t>((uint64_t)(x.rank + 1) * x.chunk, g.n_elems) - kp.xchg_own_lo);
+        kp.xchg_fmt = (uint32_t)x.fmt; kp.xchg_sum_bits = (uint32_t)x.sum_bits;
+        for (uint32_t r = 0; r < x.nranks; ++r) kp.xchg_recv[r] = x.recv[r];
+    }
     const size_t smem = clip_smem_bytes(g.threads, g.bpp, g.stages, g.regs);
     return g.bpp == 3 ? launch_c<3>(g, a, kp, smem, s) : launch_c<4>(g, a, kp, smem, s);
 }

@@ -149,6 +149,7 @@ struct Comm {
     cudaEvent_t ev_start = nullptr, ev_halo[2] = {nullptr, nullptr};
     bool halo_used[2] = {false, false};
     uint8_t* halo_local = nullptr;        // NCCL-only halo path: receive buffer (no window)
+    bool fuse_push = true;                // let the clip kernel's last flush push the partial sums (DIPSB_COMM_FUSE_PUSH=0: separate kernel)
     struct dipsb_group* group = nullptr;
     void* packed = nullptr; uint64_t packed_words = 0;   // NCCL path: the packed exchange buffer between its phases
 };
@@ -388,6 +389,7 @@ static int32_t alloc_window(dipsb_ctx* c, Comm* m) {
     CK(c, cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) CK(c, cudaEventCreateWithFlags(&m->ev_halo[k], cudaEventDisableTiming));
     m->timeout_ns = timeout_from_env();
+    if (const char* e = getenv("DIPSB_COMM_FUSE_PUSH")) m->fuse_push = atoi(e) != 0;
     return DIPSB_OK;
 }
 
@@ -571,11 +573,11 @@ namespace {
 
 bool use_p2p_reduce(const Comm* m) { return m->p2p && m->reduce_path != DIPSB_REDUCE_NCCL; }   // both exchanges follow it
 
-// slices of the reference plane for its broadcast over peer memory: slice j (pixels [j*slice_px, (j+1)*slice_px)) is
-// rank j's to forward
+// slices of the reference plane for its broadcast over peer memory: the plane is cut into nranks-1 slices; slice j-1 (pixels
+// [(j-1)*slice_px, j*slice_px)) is rank j's to receive from rank 0 and to forward to the other ranks > 0
 uint64_t plane_slice_px(const Geometry& g, int nranks) {
-    const uint64_t groups = (g.npx + 15) / 16;
-    return 16 * ((groups + (uint64_t)nranks - 1) / (uint64_t)nranks);
+    const uint64_t groups = (g.npx + 15) / 16, parts = (uint64_t)std::max(1, nranks - 1);
+    return 16 * ((groups + parts - 1) / parts);
 }
 PlaneScatter make_scatter(dipsb_ctx* c) {
     Comm* m = c->comm;
@@ -598,6 +600,7 @@ struct Pass {
     ShardExtra extra;
     bool has_extra = false;
     bool scattered = false;                // rank 0: the prime kernel already stored the slices of the plane into their owners
+    bool pushed = false;                   // the clip kernel's last flush already handed the partial sums to their owners
 };
 
 int32_t validate_pass(dipsb_ctx* c, const Pass& p) {
@@ -742,10 +745,10 @@ int32_t pass_exchange(dipsb_ctx* c, Pass& p, int phase = 7) {
             if (phase & 1) NK(c, m->nccl, m->nccl->Broadcast(c->state[0], c->state[0], g.npx * sizeof(uint16_t), ncclUint8, 0, m->comm, c->stream));
             return DIPSB_OK;
         }
-        // Peer memory: scatter + all-gather.  Rank 0 stores slice j of the plane into rank j (fused into its prime kernel when
+        // Peer memory: scatter + all-gather.  Rank 0 stores slice j-1 of the plane into rank j (fused into its prime kernel when
         // the frame allows) and starts its pass at once; every other rank forwards its slice to the rest, then waits for theirs.
-        // Every NVLink carries 1/N of the plane per step instead of rank 0 sending the whole plane N-1 times or a ring passing it
-        // on hop by hop (measured at 8 GPUs: the last rank of NCCL's broadcast ring started 0.26 ms after the first).
+        // Rank 0 sends the plane once in total (not N-1 times), and nothing is passed on hop by hop as in a ring (measured at
+        // 8 GPUs: the last rank of NCCL's broadcast ring started 0.26 ms after the first).
         const uint64_t slice_px = plane_slice_px(g, m->nranks), top = (g.npx + 15) / 16 * 16;
         PlanePush P{};
         P.plane = c->state[0]; P.nranks = (uint32_t)m->nranks; P.rank = (uint32_t)m->rank;
@@ -753,7 +756,7 @@ int32_t pass_exchange(dipsb_ctx* c, Pass& p, int phase = 7) {
         if ((phase & 1) && m->rank == 0 && !p.scattered) {
             for (int r = 1; r < m->nranks; ++r) {
                 P.dst[r] = m->state_peer[r][0];
-                P.lo[r] = std::min((uint64_t)r * slice_px, top) / 8; P.hi[r] = std::min((uint64_t)(r + 1) * slice_px, top) / 8;
+                P.lo[r] = std::min((uint64_t)(r - 1) * slice_px, top) / 8; P.hi[r] = std::min((uint64_t)r * slice_px, top) / 8;
                 P.stamp_peer[r] = &ctrl_of(m->win_peer[r])->plane_stamp;
             }
             P.stamp = m->epoch; P.blocks_done = &ctrl_of(m->win)->blocks_done[2];
@@ -765,7 +768,7 @@ int32_t pass_exchange(dipsb_ctx* c, Pass& p, int phase = 7) {
             for (int r = 1; r < m->nranks; ++r) {
                 if (r == m->rank) continue;
                 P.dst[r] = m->state_peer[r][0];
-                P.lo[r] = std::min((uint64_t)m->rank * slice_px, top) / 8; P.hi[r] = std::min((uint64_t)(m->rank + 1) * slice_px, top) / 8;
+                P.lo[r] = std::min((uint64_t)(m->rank - 1) * slice_px, top) / 8; P.hi[r] = std::min((uint64_t)m->rank * slice_px, top) / 8;
                 P.stamp_peer[r] = ctrl_of(m->win_peer[r])->plane_stamp2 + m->rank;
             }
             P.wait_flag = &ctrl_of(m->win)->plane_stamp; P.wait_value = m->epoch;
@@ -807,7 +810,18 @@ int32_t pass_exchange(dipsb_ctx* c, Pass& p, int phase = 7) {
 int32_t pass_run(dipsb_ctx* c, Pass& p) {
     Comm* m = c->comm;
     if (m->nranks > 1 && c->cfg.mode == DIPSB_MODE_OVERALL && m->rank > 0) c->state_valid = true;   // the plane has arrived
-    const ShardExtra* extra = p.has_extra ? &p.extra : nullptr;
+    if (m->nranks > 1 && use_p2p_reduce(m) && m->fuse_push) {
+        const int parity = (int)(m->epoch & 1);
+        uint64_t plan[4];
+        dipsb_xchg_plan_query(p.total, (uint32_t)m->nranks, c->g.n_elems, plan);
+        ShardPush& x = p.extra.push;
+        x.nranks = (uint32_t)m->nranks; x.rank = (uint32_t)m->rank; x.chunk = m->chunk;
+        x.fmt = plan[0] == 4 ? 1 : 2; x.sum_bits = (int)plan[1];
+        for (int r = 0; r < m->nranks; ++r)
+            x.recv[r] = reinterpret_cast<uint32_t*>(recv_area(m, m->win_peer[r], parity) + (uint64_t)m->rank * m->slot_bytes);
+        p.extra.pushed = &p.pushed;
+    }
+    const ShardExtra* extra = (p.has_extra || p.extra.push.nranks) ? &p.extra : nullptr;
     if (p.d_frames) return run_clip_on_stream(c, p.d_frames, p.n, p.stride, p.first, false, extra);
     HostClipHooks hooks;
     hooks.extra = extra;
@@ -849,7 +863,10 @@ int32_t pass_reduce(dipsb_ctx* c, Pass& p, int phase = 15) {
             X.cnt_dst = reinterpret_cast<unsigned long long*>(c->d_cnt + p.first);
         }
         if (phase & 1) {
-            xchg_push_kernel<<<kXchgBlocks, kXchgThreads, 0, c->stream>>>(X);
+            // the clip kernel's last flush may have stored the partials into their owners already: then one block hands
+            // over the boundary scalars and stamps the peers (its launch follows the clip kernel's completion, hence its stores)
+            if (p.pushed) { X.n_elems = 0; xchg_push_kernel<<<1, kXchgThreads, 0, c->stream>>>(X); X.n_elems = g.n_elems; }
+            else xchg_push_kernel<<<kXchgBlocks, kXchgThreads, 0, c->stream>>>(X);
             count_launch();
             CK(c, cudaGetLastError());
         }

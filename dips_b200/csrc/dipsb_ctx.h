@@ -110,6 +110,10 @@ struct ShardExtra {
     const unsigned long long* flag = nullptr;
     unsigned long long epoch = 0, timeout_ns = 0;
     uint32_t* status = nullptr;
+    // accumulator exchange fused into the last flush of the call's clip kernel (nranks == 0: none); *pushed tells the
+    // caller whether the kernel took it (it cannot on re-packed, segmented or per-frame-kernel paths)
+    ShardPush push;
+    bool* pushed = nullptr;
 };
 
 // api.cu internals used by comm.cu

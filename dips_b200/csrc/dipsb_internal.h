@@ -31,6 +31,16 @@ struct Geometry {
     uint32_t num_sms;
 };
 
+// Accumulator exchange fused into the clip kernel's last flush (comm.cu): where each owner receives this rank's partials.
+struct ShardPush {
+    uint32_t nranks = 0, rank = 0;
+    uint64_t chunk = 0;              // accumulator elements owned per rank
+    int fmt = 1, sum_bits = 0;       // 1: sum | cnt << sum_bits in one u32; 2: two u32 (counts at +chunk)
+    uint32_t* recv[kMaxRanks] = {};  // owner r's receive slot for this rank, this pass (unused for r == rank)
+};
+// true when launch_clip would fuse the push for this geometry / call shape
+bool clip_can_push(const Geometry& g, uint32_t n_segments);
+
 struct ClipArgs {
     const uint8_t* frames;       // frame k at frames + k*stride
     uint64_t stride;             // bytes
@@ -49,6 +59,7 @@ struct ClipArgs {
     const unsigned long long* halo_flag = nullptr;
     unsigned long long halo_epoch = 0, wait_timeout_ns = 0;
     uint32_t* status = nullptr;
+    const ShardPush* push = nullptr; // last launch of a sharded pass: hand the non-owned totals to their owners
 };
 
 // Which pixel of its tile does register slot k (0 .. 16*groups-1) of thread `thread` hold?
@@ -81,11 +92,11 @@ uint32_t clip_active_warps(const Geometry& g);
 cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s);
 cudaError_t launch_stream_probe(const Geometry& g, const uint8_t* frames, uint64_t stride, uint32_t n_frames, cudaStream_t s);
 
-// Scatter step of the reference-plane broadcast, fused into rank 0's prime kernel (comm.cu): slice j of the plane is also
-// stored into rank j's state plane over NVLink, and the kernel's last block stamps every peer.
+// Scatter step of the reference-plane broadcast, fused into rank 0's prime kernel (comm.cu): the plane is cut into nranks-1
+// slices, slice k is also stored into rank k+1's state plane over NVLink, and the kernel's last block stamps every peer.
 struct PlaneScatter {
     uint32_t nranks = 0;                          // 0: no scatter
-    uint64_t slice_px = 0;                        // pixels per slice (multiple of 512); slice j belongs to rank j
+    uint64_t slice_px = 0;                        // pixels per slice (multiple of 16); slice k belongs to rank k + 1
     uint16_t* plane_peer[kMaxRanks] = {};
     unsigned long long* stamp_peer[kMaxRanks] = {};   // null: nobody to tell
     unsigned long long epoch = 0;
