@@ -182,6 +182,7 @@ static int32_t alloc_planes(dipsb_ctx* c) {
     }
     CK(c, cudaMalloc(&c->acc, 2 * g.n_elems * sizeof(uint32_t)));
     CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
+    c->acc_zero_pending = false;
     CK(c, cudaMalloc(&c->planar, 2 * g.npx * sizeof(uint32_t)));
     if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0 && !c->ring) {
         CK(c, cudaMalloc(&c->ring, 4 * g.npx * sizeof(uint16_t)));
@@ -266,11 +267,20 @@ extern "C" void dipsb_destroy(dipsb_ctx* c) {
 
 extern "C" const char* dipsb_last_error(const dipsb_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
 
+int32_t dipsb::ensure_acc_zero(dipsb_ctx* c) {
+    if (!c->acc_zero_pending) return DIPSB_OK;
+    CK(c, cudaMemsetAsync(c->acc, 0, 2 * c->g.n_elems * sizeof(uint32_t), c->stream));
+    c->acc_zero_pending = false;
+    return DIPSB_OK;
+}
+
 extern "C" int32_t dipsb_reset(dipsb_ctx* c) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     const Geometry& g = c->g;
-    CK(c, cudaMemsetAsync(c->acc, 0, 2 * g.n_elems * sizeof(uint32_t), c->stream));
+    // The accumulator planes (8 bytes per pixel) are not cleared here: the clip kernel that normally follows clears each
+    // thread's words in its prologue, under the fill of its TMA ring; every other user of the planes clears them first.
+    c->acc_zero_pending = true;
     if (c->ring) {
         CK(c, cudaMemsetAsync(c->ring, 0, 4 * g.npx * sizeof(uint16_t), c->stream));
         for (int k = 0; k < 2; ++k) CK(c, cudaMemsetAsync(c->state[k], 0, g.state_elems * sizeof(uint16_t), c->stream));
@@ -588,6 +598,10 @@ int32_t dipsb::run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
             a.push = push;
             if (pushed) *pushed = true;
         }
+        if (c->acc_zero_pending) {
+            if (clip_can_store_first(g, segs)) { a.first_store = true; c->acc_zero_pending = false; }
+            else if ((rc = ensure_acc_zero(c))) return rc;
+        }
         if (c->timing) {
             if (c->tev_used + 2 > c->tev.size()) {
                 cudaEvent_t e0, e1;
@@ -607,6 +621,7 @@ int32_t dipsb::run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
         c->last_plan[1] = segs;
         c->last_plan[7] = 1;
     } else {   // spatial window, or a single unaligned frame: per-frame kernels
+        if ((rc = ensure_acc_zero(c))) return rc;
         CK(c, cudaMemsetAsync(c->d_sad + first, 0, n * sizeof(uint64_t), c->stream));
         CK(c, cudaMemsetAsync(c->d_cnt + first, 0, n * sizeof(uint64_t), c->stream));
         for (uint64_t k = 0; k < n; ++k) {
@@ -788,6 +803,7 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     if (rc) return rc;
     rc = ensure_scalars(c, c->stream_index + 1);
     if (rc) return rc;
+    if ((rc = ensure_acc_zero(c))) return rc;
     const uint16_t* i2src = nullptr;
     if (windowed(c)) {   // N4: spatially filtered intensity of this frame (dips_shader.wgsl:187), computed below
         rc = ensure_i2_scratch(c);
@@ -1001,6 +1017,7 @@ extern "C" uint64_t dipsb_frames_processed(const dipsb_ctx* c) { return c ? c->f
 extern "C" int32_t dipsb_get_accumulators(dipsb_ctx* c, uint32_t* acc_sum, uint32_t* acc_cnt) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    { int32_t zrc = ensure_acc_zero(c); if (zrc) return zrc; }
     if (c->acc_sharded) return fail(c, DIPSB_ERR_STATE, "%s: the totals are sharded by pixel range over the ranks; call dipsb_gather_accumulators (collective) first", __func__);
     const Geometry& g = c->g;
     if (acc_sum) {
@@ -1018,6 +1035,7 @@ extern "C" int32_t dipsb_get_accumulators(dipsb_ctx* c, uint32_t* acc_sum, uint3
 extern "C" int32_t dipsb_set_accumulators(dipsb_ctx* c, const uint32_t* acc_sum, const uint32_t* acc_cnt) {
     if (!c) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    { int32_t zrc = ensure_acc_zero(c); if (zrc) return zrc; }
     if (c->acc_sharded) return fail(c, DIPSB_ERR_STATE, "%s: the totals are sharded by pixel range over the ranks; call dipsb_gather_accumulators (collective) first", __func__);
     const Geometry& g = c->g;
     if (acc_sum) {
@@ -1034,6 +1052,8 @@ extern "C" int32_t dipsb_set_accumulators(dipsb_ctx* c, const uint32_t* acc_sum,
 
 extern "C" int32_t dipsb_accumulators_device(dipsb_ctx* c, void** d_acc, uint64_t* n_elems) {
     if (!c || !d_acc || !n_elems) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    { int32_t zrc = ensure_acc_zero(c); if (zrc) return zrc; }
     *d_acc = c->acc;
     *n_elems = c->g.n_elems;
     return DIPSB_OK;
@@ -1045,6 +1065,7 @@ extern "C" int32_t dipsb_pack_accumulators_device(dipsb_ctx* c, uint64_t total_f
     if (!c || !d_packed || !n_words || total_frames == 0) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     const Geometry& g = c->g;
+    { int32_t zrc = ensure_acc_zero(c); if (zrc) return zrc; }
     if (total_frames < c->frames_processed)
         return fail(c, DIPSB_ERR_INVALID, "pack_accumulators: total_frames %llu < the %llu frames this context accumulated since its last reset "
                     "(it must bound every frame accumulated on ALL ranks, or the packed fields carry into each other)",
@@ -1091,6 +1112,7 @@ extern "C" int32_t dipsb_get_scalars(dipsb_ctx* c, uint64_t first, uint64_t n, u
 extern "C" int32_t dipsb_get_intensity_map(dipsb_ctx* c, uint64_t n_eff, float* out) {
     if (!c || !out) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    { int32_t zrc = ensure_acc_zero(c); if (zrc) return zrc; }
     if (c->acc_sharded) return fail(c, DIPSB_ERR_STATE, "%s: the totals are sharded by pixel range over the ranks; call dipsb_gather_accumulators (collective) first", __func__);
     float* d = reinterpret_cast<float*>(c->planar);
     CK(c, launch_intensity_map(c->g, c->acc, n_eff, d, c->stream));

@@ -166,6 +166,8 @@ struct KParams {
     // frame-range shards: the LAST flush of the pass hands the elements this rank does not own straight to their owners --
     // total so far (local plane + registers), packed, stored into the owner's receive slot over NVLink -- so the accumulator
     // exchange needs no separate pass over the planes and overlaps the streaming of the tiles that are still running
+    uint32_t first_store;    // clip_kernel_ws, one segment: dipsb_reset left the zeroing of the planes to this launch -- every thread
+                             // clears its own 32 words while the TMA ring fills (no separate pass over 8 bytes per pixel)
     uint32_t xchg_nranks;    // 0: ordinary flush
     uint32_t xchg_own_lo, xchg_own_len, xchg_chunk;   // owned element range of this rank, elements per owner
     uint32_t xchg_fmt, xchg_sum_bits;                 // 1: sum | cnt << bits in one u32; 2: two u32 (cnt at +chunk)
@@ -501,6 +503,12 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
         }
         return;
     }
+    if (P.first_store) {   // my accumulator words start at zero (same thread, same addresses as the flushes that follow)
+        uint32_t* const acc_sum = P.acc_sum + (uint64_t)tile * slots + tid;
+        uint32_t* const acc_cnt = P.acc_cnt + (uint64_t)tile * slots + tid;
+#pragma unroll
+        for (int k = 0; k < 2 * R; ++k) { acc_sum[k * nthr] = 0u; acc_cnt[k * nthr] = 0u; }
+    }
     if (warp >= P.active_warps) return;
 
     uint32_t ra[R], rb[R];
@@ -766,6 +774,7 @@ inline uint32_t stage_bytes_of(uint32_t threads, int bpp, int groups) { return (
 
 }  // namespace
 
+bool clip_can_store_first(const Geometry& g, uint32_t n_segments) { return g.kernel == 1 && n_segments == 1; }
 bool clip_can_push(const Geometry& g, uint32_t n_segments) { return g.kernel == 1 && n_segments == 1 && g.n_elems < (1ull << 32); }
 
 int clip_groups(int regs) { return regs >= 128 ? 2 : 1; }
@@ -823,6 +832,7 @@ cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s) {
     kp.extra_frame = a.extra_frame; kp.halo_flag = a.halo_flag; kp.halo_epoch = a.halo_epoch;
     kp.wait_timeout_ns = a.wait_timeout_ns; kp.status = a.status;
     kp.xchg_nranks = 0;
+    kp.first_store = (a.first_store && clip_can_store_first(g, a.n_segments)) ? 1u : 0u;
     if (a.push && a.push->nranks && clip_can_push(g, a.n_segments)) {
         const ShardPush& x = *a.push;
         kp.xchg_nranks = x.nranks; kp.xchg_chunk = (uint32_t)x.chunk;

@@ -835,6 +835,7 @@ int32_t pass_reduce(dipsb_ctx* c, Pass& p, int phase = 15) {
     Comm* m = c->comm;
     const Geometry& g = c->g;
     if (m->nranks == 1) return DIPSB_OK;
+    { int32_t zrc = ensure_acc_zero(c); if (zrc) return zrc; }   // (only a pass that never reached a clip kernel leaves it pending)
     const bool perframe = c->cfg.mode == DIPSB_MODE_PERFRAME;
     if (use_p2p_reduce(m)) {
         const int parity = (int)(m->epoch & 1);
@@ -1034,6 +1035,7 @@ extern "C" int32_t dipsb_comm_probe(dipsb_ctx* c, int32_t what, uint64_t total_f
 static int32_t gather_enqueue(dipsb_ctx* c, int phase) {
     Comm* m = c->comm;
     if (!m || m->nranks == 1 || !c->acc_sharded) { c->acc_sharded = false; return DIPSB_OK; }
+    { int32_t zrc = ensure_acc_zero(c); if (zrc) return zrc; }
     const Geometry& g = c->g;
     GatherParams G{};
     G.acc = c->acc; G.n_elems = g.n_elems; G.chunk = m->chunk; G.nranks = (uint32_t)m->nranks; G.rank = (uint32_t)m->rank;

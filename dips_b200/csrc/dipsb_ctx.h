@@ -25,6 +25,8 @@ struct dipsb_ctx {
     bool state_valid = false;
     bool snapshot_pending = false;
     uint32_t* acc = nullptr;                   // u32[2*n_elems]: sum plane then count plane, internal order
+    bool acc_zero_pending = false;             // dipsb_reset deferred the zeroing of `acc`: the next clip kernel does it in its
+                                               // prologue, anything else that touches the planes calls ensure_acc_zero first
     uint32_t* planar = nullptr;                // u32[2*npx] scratch for get/set in pixel order
     uint64_t* d_sad = nullptr;                 // per logical frame index
     uint64_t* d_cnt = nullptr;
@@ -129,6 +131,7 @@ struct HostClipHooks {
 int32_t run_clip_host_impl(dipsb_ctx* c, const uint8_t* frames, uint64_t n, uint64_t stride, uint64_t first,
                            const HostClipHooks* hooks);
 int32_t ensure_scalars(dipsb_ctx* c, uint64_t upto);
+int32_t ensure_acc_zero(dipsb_ctx* c);      // materialise a deferred zeroing of the accumulator planes
 int bpp_of(int format);
 int bit_length(uint64_t v);
 // comm.cu: called by dipsb_destroy / geometry changes

@@ -40,6 +40,8 @@ struct ShardPush {
 };
 // true when launch_clip would fuse the push for this geometry / call shape
 bool clip_can_push(const Geometry& g, uint32_t n_segments);
+// true when launch_clip can take over the zeroing of the accumulator planes for this call shape
+bool clip_can_store_first(const Geometry& g, uint32_t n_segments);
 
 struct ClipArgs {
     const uint8_t* frames;       // frame k at frames + k*stride
@@ -60,6 +62,7 @@ struct ClipArgs {
     unsigned long long halo_epoch = 0, wait_timeout_ns = 0;
     uint32_t* status = nullptr;
     const ShardPush* push = nullptr; // last launch of a sharded pass: hand the non-owned totals to their owners
+    bool first_store = false;        // the planes were not zeroed: the launch clears them itself (only honoured when clip_can_store_first)
 };
 
 // Which pixel of its tile does register slot k (0 .. 16*groups-1) of thread `thread` hold?
