@@ -47,6 +47,8 @@ SYMBOLS = {
     "dipsb_push_frame": (_i32, [_vp, _vp, _u32, _u32, _u32, _i32, _vp, C.POINTER(FrameStats)]),
     "dipsb_push_frame_pipelined": (_i32, [_vp, _vp, _u32, _u32, _u32, _i32, _vp, C.POINTER(FrameStats)]),
     "dipsb_flush_frame": (_i32, [_vp, _vp, C.POINTER(FrameStats)]),
+    "dipsb_stage_frame": (_i32, [_vp, _vp, _u32, _u32, _u32, _i32]),
+    "dipsb_dispatch_staged": (_i32, [_vp, _vp, C.POINTER(FrameStats)]),
     "dipsb_snapshot": (_i32, [_vp]),
     "dipsb_frames_processed": (_u64, [_vp]),
     "dipsb_get_accumulators": (_i32, [_vp, _vp, _vp]),

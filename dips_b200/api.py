@@ -373,6 +373,22 @@ class Context:
                                                  _host_ptr(out) if want_rgba else None, C.byref(st)))
         return rc, out, (int(st.frame_index), int(st.sad), int(st.count))
 
+    def stage_frame(self, frame: np.ndarray, fmt: int | None = None, stride: int | None = None) -> None:
+        """first half of push_frame (the reference's add_texture): copy the frame into the library's slot, start its upload"""
+        fmt = self.fmt if fmt is None else fmt
+        frame = np.ascontiguousarray(frame, dtype=np.uint8)
+        stride = stride or self.width * bytes_per_pixel(fmt)
+        if frame.size < stride * self.height:
+            raise ValueError("frame smaller than height*stride")
+        self._ck(self._lib.dipsb_stage_frame(self._h, _host_ptr(frame), self.width, self.height, stride, fmt))
+
+    def dispatch_staged(self, want_rgba: bool = True, out: np.ndarray | None = None):
+        """second half (the reference's dispatch): same return value as push_frame"""
+        out = self._out_buffer(out) if want_rgba else None
+        st = _lib.FrameStats()
+        rc = self._ck(self._lib.dipsb_dispatch_staged(self._h, _host_ptr(out) if want_rgba else None, C.byref(st)))
+        return rc, out, (int(st.frame_index), int(st.sad), int(st.count))
+
     def push_frame_pipelined(self, frame: np.ndarray, fmt: int | None = None, stride: int | None = None,
                              out: np.ndarray | None = None):
         """Submit `frame`, get back the previous frame's result: (status, rgba or None, stats or None).

@@ -812,12 +812,14 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     }
     // The input slice is borrowed for the call only (frame_extractor.rs:224-226): it is either staged now or, when it is
     // page-locked, uploaded straight from the caller's buffer and the upload awaited before this call returns.
-    const bool in_direct = stride == row && host_pinned(px);
+    // px == nullptr: the frame was staged and its upload started by dipsb_stage_frame (slot 0); only kernels and read-back follow
+    const bool pre_staged = px == nullptr;
+    const bool in_direct = !pre_staged && stride == row && host_pinned(px);
     // The synchronous call works in row bands: upload of band k+1 (copy stream), kernels of band k (the context's stream)
     // and read-back of band k-1 (read-back stream) run concurrently, and so do the CPU staging copies on either side.  In
     // the pipelined call the neighbouring frames already overlap and the extra launches only cost; a spatial window
     // needs the whole frame.
-    const uint32_t bands = (overlap || windowed(c)) ? 1u : stage_pieces(std::max<uint64_t>(fb, g.npx * 4), height);
+    const uint32_t bands = (overlap || windowed(c) || pre_staged) ? 1u : stage_pieces(std::max<uint64_t>(fb, g.npx * 4), height);
     const bool banded = bands > 1;
     const bool side_upload = overlap || banded;
     cudaStream_t up = side_upload ? c->copy_stream : c->stream;
@@ -889,15 +891,19 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
         const uint32_t r0 = (uint32_t)((uint64_t)height * k / bands), r1 = (uint32_t)((uint64_t)height * (k + 1) / bands);
         const uint64_t p0 = (uint64_t)r0 * width, p1 = (uint64_t)r1 * width;
         // upload
-        const uint8_t* src = px + (uint64_t)r0 * stride;
-        if (!in_direct) {
-            host_copy2d(sl.h_in + (uint64_t)r0 * row, row, src, stride, row, r1 - r0);
-            src = sl.h_in + (uint64_t)r0 * row;
-        }
-        CK(c, cudaMemcpyAsync(sl.d_in + (uint64_t)r0 * row, src, (uint64_t)(r1 - r0) * row, cudaMemcpyHostToDevice, up));
-        if (side_upload) {
-            CK(c, cudaEventRecord(sl.ev_in[k], c->copy_stream));
-            CK(c, cudaStreamWaitEvent(c->stream, sl.ev_in[k], 0));
+        if (pre_staged) {
+            CK(c, cudaStreamWaitEvent(c->stream, sl.ev_in[0], 0));   // recorded by dipsb_stage_frame behind its upload
+        } else {
+            const uint8_t* src = px + (uint64_t)r0 * stride;
+            if (!in_direct) {
+                host_copy2d(sl.h_in + (uint64_t)r0 * row, row, src, stride, row, r1 - r0);
+                src = sl.h_in + (uint64_t)r0 * row;
+            }
+            CK(c, cudaMemcpyAsync(sl.d_in + (uint64_t)r0 * row, src, (uint64_t)(r1 - r0) * row, cudaMemcpyHostToDevice, up));
+            if (side_upload) {
+                CK(c, cudaEventRecord(sl.ev_in[k], c->copy_stream));
+                CK(c, cudaStreamWaitEvent(c->stream, sl.ev_in[k], 0));
+            }
         }
         // kernels
         if (windowed(c)) {
@@ -975,7 +981,43 @@ extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t wi
     if (!c || !px) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     if (c->slot[0].pending || c->slot[1].pending) return fail(c, DIPSB_ERR_STATE, "push_frame: a pipelined frame is in flight; call dipsb_flush_frame first");
+    if (c->staged) { CK(c, cudaEventSynchronize(c->slot[0].ev_in[0])); c->staged = false; }   // a staged frame is dropped
     int32_t rc = submit_frame(c, c->slot[0], px, width, height, stride, format, out_rgba != nullptr, false,
+                              out_rgba && host_pinned(out_rgba) ? out_rgba : nullptr);
+    if (rc) return rc;
+    return collect_frame(c, c->slot[0], out_rgba, stats);
+}
+
+// The reference splits its frame call in two -- ComputeState::add_texture (dips/src/gpu/mod.rs:170: keeps the borrowed frame)
+// and dispatch (:306: computes and returns it).  Staging copies the frame straight into the library's page-locked input slot
+// (threaded host copy) and starts its upload, so a wrapper need not keep a copy of its own for dispatch.
+extern "C" int32_t dipsb_stage_frame(dipsb_ctx* c, const uint8_t* px, uint32_t width, uint32_t height, uint32_t stride, int32_t format) {
+    if (!c || !px) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const Geometry& g = c->g;
+    if (c->slot[0].pending || c->slot[1].pending) return fail(c, DIPSB_ERR_STATE, "stage_frame: a pipelined frame is in flight; call dipsb_flush_frame first");
+    if (width != g.width || height != g.height) return fail(c, DIPSB_ERR_INVALID, "stage_frame: %ux%u does not match the context's %ux%u", width, height, g.width, g.height);
+    if (format < 0 || format > 3) return fail(c, DIPSB_ERR_INVALID, "stage_frame: bad format %d", format);
+    const uint64_t row = (uint64_t)width * bpp_of(format);
+    if (stride < row) return fail(c, DIPSB_ERR_INVALID, "stage_frame: stride %u smaller than a row (%llu)", stride, (unsigned long long)row);
+    dipsb_ctx::FrameSlot& sl = c->slot[0];
+    int32_t rc = ensure_slot(c, sl, row * height);
+    if (rc) return rc;
+    if (c->staged) CK(c, cudaEventSynchronize(sl.ev_in[0]));     // a staged frame that was never dispatched: its upload still reads h_in
+    host_copy2d(sl.h_in, row, px, stride, row, height);
+    CK(c, cudaMemcpyAsync(sl.d_in, sl.h_in, row * height, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(c, cudaEventRecord(sl.ev_in[0], c->copy_stream));
+    c->staged = true; c->staged_format = format;
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_dispatch_staged(dipsb_ctx* c, uint8_t* out_rgba, dipsb_frame_stats* stats) {
+    if (!c) return DIPSB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (!c->staged) return fail(c, DIPSB_ERR_STATE, "dispatch_staged: no frame staged (dipsb_stage_frame)");
+    c->staged = false;
+    const int bpp = bpp_of(c->staged_format);
+    int32_t rc = submit_frame(c, c->slot[0], nullptr, c->g.width, c->g.height, c->g.width * (uint32_t)bpp, c->staged_format, out_rgba != nullptr, false,
                               out_rgba && host_pinned(out_rgba) ? out_rgba : nullptr);
     if (rc) return rc;
     return collect_frame(c, c->slot[0], out_rgba, stats);

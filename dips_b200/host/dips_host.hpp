@@ -61,7 +61,10 @@ class ComputeState {
     void add_texture(uint32_t width, uint32_t height, const uint8_t* frame_data, size_t len) {
         if (len < static_cast<size_t>(width) * height * 4) throw std::runtime_error("add_texture: frame smaller than width*height*4");
         ensure(width, height);
-        pending_.assign(frame_data, frame_data + static_cast<size_t>(width) * height * 4);
+        // no copy of our own (the reference's `to_vec`, mod.rs:171): the frame goes straight into the library's page-locked
+        // input slot and its upload starts; dispatch() finishes the call
+        if (dipsb_stage_frame(ctx_, frame_data, width, height, width * 4, DIPSB_FMT_RGBX8) != DIPSB_OK)
+            throw std::runtime_error(std::string("dipsb_stage_frame: ") + dipsb_last_error(ctx_));
         have_frame_ = true;
     }
 
@@ -70,8 +73,8 @@ class ComputeState {
         if (!have_frame_ || !ctx_) return std::nullopt;
         have_frame_ = false;
         std::vector<uint8_t> out(static_cast<size_t>(width_) * height_ * 4);
-        const int32_t rc = dipsb_push_frame(ctx_, pending_.data(), width_, height_, width_ * 4, DIPSB_FMT_RGBX8, out.data(), &stats_);
-        if (rc < 0) throw std::runtime_error(std::string("dipsb_push_frame: ") + dipsb_last_error(ctx_));
+        const int32_t rc = dipsb_dispatch_staged(ctx_, out.data(), &stats_);
+        if (rc < 0) throw std::runtime_error(std::string("dipsb_dispatch_staged: ") + dipsb_last_error(ctx_));
         if (rc == DIPSB_NOT_READY) return std::nullopt;
         return out;
     }
@@ -95,7 +98,6 @@ class ComputeState {
     bool colorize_; int32_t window_; float sensitivity_; DiPsFilter filter_; ChromaFilter chroma_; bool exact_; int32_t device_;
     dipsb_ctx* ctx_ = nullptr;
     uint32_t width_ = 0, height_ = 0;
-    std::vector<uint8_t> pending_;
     bool have_frame_ = false;
     dipsb_frame_stats stats_{};
 };

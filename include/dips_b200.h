@@ -174,6 +174,14 @@ int32_t dipsb_push_frame(dipsb_ctx *ctx, const uint8_t *px, uint32_t width, uint
 int32_t dipsb_push_frame_pipelined(dipsb_ctx *ctx, const uint8_t *px, uint32_t width, uint32_t height, uint32_t stride,
                                    int32_t format, uint8_t *out_rgba_prev, dipsb_frame_stats *stats_prev);
 int32_t dipsb_flush_frame(dipsb_ctx *ctx, uint8_t *out_rgba, dipsb_frame_stats *stats);
+/*
+ * dipsb_push_frame in the two steps the reference's ComputeState takes (add_texture dips/src/gpu/mod.rs:170 keeps the
+ * borrowed frame, dispatch :306 computes and returns it): stage copies the frame straight into the library's page-locked
+ * input slot and starts the upload (px is free again on return), dispatch runs the kernels and hands back what
+ * dipsb_push_frame would have.  A wrapper built on this pair keeps no frame copy of its own.
+ */
+int32_t dipsb_stage_frame(dipsb_ctx *ctx, const uint8_t *px, uint32_t width, uint32_t height, uint32_t stride, int32_t format);
+int32_t dipsb_dispatch_staged(dipsb_ctx *ctx, uint8_t *out_rgba, dipsb_frame_stats *stats);
 /* the next pushed frame becomes the reference (dips_alt snapshot / refresh marker) */
 int32_t dipsb_snapshot(dipsb_ctx *ctx);
 

@@ -62,7 +62,6 @@ pub struct ComputeState {
     ctx: *mut sys::dipsb_ctx,
     width: u32,
     height: u32,
-    pending: Vec<u8>,
     have_frame: bool,
     /// true (default): the crate's own temporal semantics (median-of-4 ring); false: reference = first frame
     pub reference_exact: bool,
@@ -93,7 +92,6 @@ impl ComputeState {
             ctx: ptr::null_mut(),
             width: 0,
             height: 0,
-            pending: Vec::new(),
             have_frame: false,
             reference_exact: true,
         })
@@ -132,15 +130,15 @@ impl ComputeState {
         Ok(())
     }
 
-    /// dips/src/gpu/mod.rs:170 -- the slice is borrowed for the call only, so it is copied here.
+    /// dips/src/gpu/mod.rs:170 -- the slice is borrowed for the call only.  No copy of our own (the reference's `to_vec`,
+    /// :171): `dipsb_stage_frame` copies it straight into the library's page-locked input slot and starts the upload.
     pub fn add_texture(&mut self, width: u32, height: u32, frame_data: &[u8]) {
-        if self.ensure_ctx(width, height).is_err() {
-            self.have_frame = false;
+        self.have_frame = false;
+        if self.ensure_ctx(width, height).is_err() || frame_data.len() < (width as usize) * (height as usize) * 4 {
             return;
         }
-        self.pending.clear();
-        self.pending.extend_from_slice(frame_data);
-        self.have_frame = true;
+        let rc = unsafe { sys::dipsb_stage_frame(self.ctx, frame_data.as_ptr(), width, height, width * 4, sys::DIPSB_FMT_RGBX8) };
+        self.have_frame = rc == sys::DIPSB_OK;
     }
 
     /// dips/src/gpu/mod.rs:306 -- `None` while there is no reference yet (the caller passes the input through).
@@ -150,18 +148,7 @@ impl ComputeState {
         }
         self.have_frame = false;
         let mut out = vec![0u8; (self.width * self.height * 4) as usize];
-        let rc = unsafe {
-            sys::dipsb_push_frame(
-                self.ctx,
-                self.pending.as_ptr(),
-                self.width,
-                self.height,
-                self.width * 4,
-                sys::DIPSB_FMT_RGBX8,
-                out.as_mut_ptr(),
-                ptr::null_mut(),
-            )
-        };
+        let rc = unsafe { sys::dipsb_dispatch_staged(self.ctx, out.as_mut_ptr(), ptr::null_mut()) };
         match rc {
             sys::DIPSB_OK => Some(out),
             _ => None, // DIPSB_NOT_READY (reference frame) or an error: passthrough, like the reference's warm-up
@@ -204,9 +191,11 @@ pub struct DiPsProperties {
     pub chroma_filter: ChromaFilter,
 }
 
-/// `DiPsCompute::new(num_textures, w, h, window, device, queue, properties)` minus the wgpu handles, which have no
-/// meaning on the CUDA path (dips_alt/src/dips_compute/mod.rs:270-278); `send_frame` keeps its shape (:498-503) minus the
-/// swap-chain texture of the live-render path.
+/// `DiPsCompute` with the reference's own signatures (dips_alt/src/dips_compute/mod.rs:270-278, :498-503): the window, the
+/// wgpu device / queue handles and the swap-chain texture are accepted -- as generic parameters, so this crate needs neither
+/// wgpu nor winit -- and ignored: they have no meaning on the CUDA path.  `run_dips_on_file` (dips_alt/src/lib.rs:599-642)
+/// therefore compiles against this type unchanged; the live-render branch of `send_frame` (`surface_texture: Some(..)`,
+/// :565-595) is not reproduced: the difference frame is returned, presenting it stays with the caller.
 pub struct DiPsCompute {
     ctx: *mut sys::dipsb_ctx,
     width: u32,
@@ -214,7 +203,15 @@ pub struct DiPsCompute {
 }
 
 impl DiPsCompute {
-    pub fn new(_num_textures: usize, textures_width: u32, textures_height: u32, props: DiPsProperties) -> anyhow::Result<Self> {
+    pub fn new<W, D, Q>(
+        _num_textures: usize,
+        textures_width: u32,
+        textures_height: u32,
+        _dips_window: Option<&W>,
+        _device: D,
+        _queue: Q,
+        props: DiPsProperties,
+    ) -> anyhow::Result<Self> {
         let mut cfg: sys::dipsb_config = unsafe { std::mem::zeroed() };
         unsafe { sys::dipsb_default_config(&mut cfg) };
         cfg.width = textures_width;
@@ -236,7 +233,7 @@ impl DiPsCompute {
     }
 
     /// `snapshot: Some(())` makes this frame the new reference (dips_alt/src/lib.rs:222-225, refresh markers :668-670).
-    pub fn send_frame(&mut self, frame: &[u8], snapshot: Option<()>) -> Vec<u8> {
+    pub fn send_frame<S>(&mut self, frame: &[u8], snapshot: Option<()>, _surface_texture: Option<&S>) -> Vec<u8> {
         if snapshot.is_some() {
             unsafe { sys::dipsb_snapshot(self.ctx) };
         }
@@ -300,7 +297,7 @@ where
 {
     let mut schedule = SnapshotSchedule::new(refresh_markers);
     for (t, frame) in frames.into_iter().enumerate() {
-        let out = compute.send_frame(frame, schedule.snapshot_now());
+        let out = compute.send_frame(frame, schedule.snapshot_now(), None::<&()>);
         schedule.frame_sent();
         sink(t, out);
     }

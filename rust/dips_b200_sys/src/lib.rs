@@ -91,6 +91,8 @@ extern "C" {
     pub fn dipsb_push_frame(ctx: *mut dipsb_ctx, px: *const u8, width: u32, height: u32, stride: u32, format: i32, out_rgba: *mut u8, stats: *mut dipsb_frame_stats) -> i32;
     pub fn dipsb_push_frame_pipelined(ctx: *mut dipsb_ctx, px: *const u8, width: u32, height: u32, stride: u32, format: i32, out_rgba_prev: *mut u8, stats_prev: *mut dipsb_frame_stats) -> i32;
     pub fn dipsb_flush_frame(ctx: *mut dipsb_ctx, out_rgba: *mut u8, stats: *mut dipsb_frame_stats) -> i32;
+    pub fn dipsb_stage_frame(ctx: *mut dipsb_ctx, px: *const u8, width: u32, height: u32, stride: u32, format: i32) -> i32;
+    pub fn dipsb_dispatch_staged(ctx: *mut dipsb_ctx, out_rgba: *mut u8, stats: *mut dipsb_frame_stats) -> i32;
     pub fn dipsb_snapshot(ctx: *mut dipsb_ctx) -> i32;
     pub fn dipsb_frames_processed(ctx: *const dipsb_ctx) -> u64;
     pub fn dipsb_get_accumulators(ctx: *mut dipsb_ctx, acc_sum: *mut u32, acc_cnt: *mut u32) -> i32;

@@ -656,3 +656,48 @@ def test_accumulator_range_guard(torch_cuda, oracle):
         ctx.reset()
         ctx.run_clip_device(big.data_ptr(), 10, 16, 0)
         assert np.array_equal(ctx.get_accumulators()[0], want.acc_sum)
+
+
+def test_run_clip_host_back_to_back_without_sync(torch_cuda, oracle):
+    """Several dipsb_run_clip_host calls with no synchronisation in between (a long video fed in pieces; reset + run loops):
+    the staging slots are guarded across calls, pageable and page-locked clips alike."""
+    import dips_b200
+    torch = torch_cuda
+    w, h, fmt, tau = 512, 288, 0, 9
+    n = 48
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    pinned = torch.from_numpy(clip.copy()).pin_memory()
+    for mode in (0, 1):
+        want = oracle.run_clip(clip, fmt, mode, tau)
+        for src in (clip, pinned.numpy()):
+            with dips_b200.Context(w, h, fmt, mode, tau) as ctx:
+                for rep in range(3):                       # reset + run, three times, never synchronising
+                    ctx.reset()
+                    for a, b in ((0, 7), (7, 8), (8, 31), (31, n)):
+                        ctx.run_clip_host(src[a:b], first_frame=a)
+                s, c = ctx.get_accumulators()
+                sad, cnt = ctx.get_scalars(0, n)
+            assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+            assert np.array_equal(sad, want.sad) and np.array_equal(cnt, want.cnt)
+
+
+def test_shard_engine_on_a_default_stream_context(torch_cuda, oracle):
+    """GpuShardEngine puts a Context that still runs on its private stream onto torch's current stream, so that torch's
+    collectives and copies are ordered with the library's kernels."""
+    import dips_b200
+    from dips_b200 import sharding
+    torch = torch_cuda
+    w, h, fmt, tau, n = 256, 128, 1, 5, 10
+    clip = oracle.synth_clip(n, w, h, fmt)
+    dev = to_device(torch, clip)
+    want = oracle.run_clip(clip, fmt, 0, tau)
+    with dips_b200.Context(w, h, fmt, 0, tau) as ctx:          # private stream, never set_stream by the caller
+        eng = sharding.GpuShardEngine(ctx, dev, torch)
+        eng.prime(dev[0])
+        sharding.run_sharded(eng, 0, 0)
+        acc = eng.acc_tensor().clone()                          # torch op on torch's stream right behind the kernels
+        torch.cuda.current_stream().synchronize()
+        ptr, ne = ctx.accumulators_device()
+        s, c = ctx.get_accumulators()
+    assert np.array_equal(s, want.acc_sum) and np.array_equal(c, want.acc_cnt)
+    assert int(acc[:ne].to(torch.int64).sum()) == int(want.acc_sum.astype(np.int64).sum())

@@ -333,3 +333,31 @@ def test_large_frames_take_the_row_band_path_with_identical_results(oracle, flav
                     assert np.array_equal(rgba, want[t][1]), t
                 acc = ctx.get_accumulators()
                 assert np.array_equal(acc[0], acc_want[0]) and np.array_equal(acc[1], acc_want[1])
+
+
+def test_stage_and_dispatch_equal_push_frame(torch_cuda, oracle):
+    """dipsb_stage_frame + dipsb_dispatch_staged (the reference's add_texture + dispatch split, dips/src/gpu/mod.rs:170, :306)
+    give exactly what dipsb_push_frame gives, frame by frame, for the north-star and the ring flavours."""
+    import dips_b200
+    w, h, n = 320, 184, 9
+    clip = oracle.synth_clip(n, w, h, 1, profile=oracle.SYNTH_SCENE)
+    for flavor in (dips_b200.FLAVOR_FRAME0, dips_b200.FLAVOR_DIPS_RING4, dips_b200.FLAVOR_ALT_RING2):
+        with dips_b200.Context(w, h, 1, 0, 12, colorize=True, filt=0, flavor=flavor) as a, \
+                dips_b200.Context(w, h, 1, 0, 12, colorize=True, filt=0, flavor=flavor) as b:
+            for t in range(n):
+                if flavor == dips_b200.FLAVOR_ALT_RING2 and t == 2:
+                    a.snapshot(); b.snapshot()
+                ra, oa, sa = a.push_frame(clip[t])
+                b.stage_frame(clip[t])
+                rb, ob, sb = b.dispatch_staged()
+                assert ra == rb and sa == sb and np.array_equal(oa, ob), (flavor, t)
+            sa_, ca_ = a.get_accumulators()
+            sb_, cb_ = b.get_accumulators()
+            assert np.array_equal(sa_, sb_) and np.array_equal(ca_, cb_)
+        with dips_b200.Context(w, h, 1, 0, 12) as c:
+            with pytest.raises(dips_b200.DipsError):
+                c.dispatch_staged()                      # nothing staged
+            c.stage_frame(clip[0])
+            c.stage_frame(clip[1])                       # re-staging replaces the frame
+            rc, _, st = c.dispatch_staged()
+            assert rc == dips_b200.NOT_READY and st[0] == 0
