@@ -37,6 +37,7 @@ WORKLOADS = {
     "c2": ("C2: synthetic 1920x1080 RGB8 1800-frame clip, overall-difference + threshold", 1920, 1080, 0, 0, 32, 1800),
     "c3": ("C3: synthetic 1920x1080 RGB8 1800-frame clip, per-frame difference + per-frame scalars", 1920, 1080, 0, 1, 32, 1800),
     "c4": ("C4: synthetic 3840x2160 RGBx8 3600-frame clip, overall-difference, frame-sharded with accumulator reduction", 3840, 2160, 1, 0, 32, 3600),
+    "c4p": ("C4 geometry, per-frame mode: synthetic 3840x2160 RGBx8 3600-frame clip, per-frame difference + scalars", 3840, 2160, 1, 1, 32, 3600),
     "c5o": ("C5: synthetic 7680x4320 RGB8 1200-frame clip, overall-difference, frame-sharded", 7680, 4320, 0, 0, 32, 1200),
     "c5p": ("C5: synthetic 7680x4320 RGB8 1200-frame clip, per-frame difference, halo exchange at shard boundaries", 7680, 4320, 0, 1, 32, 1200),
 }
@@ -610,15 +611,21 @@ class Bench:
             src = frames_rgba if kind == "pageable" else pin_in.array.reshape(8, -1)
             dst = (np.empty((2, sw * sh * 4), np.uint8) if kind == "pageable" else pin_out.array.reshape(2, -1))
             dst[:] = 0
-            for name in ("dipsb_push_frame", "dipsb_push_frame_pipelined"):
+            for name in ("dipsb_push_frame", "dipsb_push_frame_pipelined", "dipsb_stage_frame+dipsb_dispatch_staged"):
                 with lib.Context(sw, sh, lib.FMT_RGBX8, 0, tau, device=self.local_rank) as sctx:
-                    fn = sctx.push_frame if name == "dipsb_push_frame" else sctx.push_frame_pipelined
+                    if name.startswith("dipsb_stage"):
+                        # the call pair the C++ / Rust mirrors of ComputeState::{add_texture, dispatch} are built on
+                        def fn(frame, out, _c=sctx):
+                            _c.stage_frame(frame)
+                            return _c.dispatch_staged(out=out)
+                    else:
+                        fn = sctx.push_frame if name == "dipsb_push_frame" else sctx.push_frame_pipelined
                     for k in range(4):
                         fn(src[k % 8], out=dst[k & 1])
                     t0 = time.perf_counter()
                     for k in range(sn):
                         fn(src[k % 8], out=dst[k & 1])
-                    if name != "dipsb_push_frame":
+                    if name == "dipsb_push_frame_pipelined":
                         sctx.flush_frame(out=dst[sn & 1])
                     info[name + ("_fps" if kind == "pageable" else "_pinned_fps")] = sn / (time.perf_counter() - t0)
         pin_in.close()

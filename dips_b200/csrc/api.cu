@@ -122,9 +122,11 @@ static int32_t filtered_plane(dipsb_ctx* c, const uint8_t* d_frame, int format, 
 
 // clip_kernel_ws (producer warp, stage-unrolled; +7-10 % sustained on 3 B/px clips, equal elsewhere: profiles/r01_sweeps.md)
 // exists for 64 registers and 3 or 4 stages; any other forced tuning selects clip_kernel
-static int pick_kernel(int requested, uint32_t stages, uint32_t regs) {
-    if (requested >= 0) return requested;
-    return ((regs == 0 || regs == 64) && (stages == 0 || stages == 3 || stages == 4)) ? 1 : 0;
+// (and not for 4 B/px frames with a chroma filter in per-frame mode: those six instantiations do not fit 64 registers)
+static int pick_kernel(const dipsb_ctx* c, int requested, uint32_t stages, uint32_t regs) {
+    const bool ws_exists = clip_ws_available(c->g.bpp, c->g.chan_byte, c->cfg.mode);
+    if (requested >= 0) return (requested == 1 && !ws_exists) ? -1 : requested;
+    return (ws_exists && (regs == 0 || regs == 64) && (stages == 0 || stages == 3 || stages == 4)) ? 1 : 0;
 }
 
 // ---- lifetime ------------------------------------------------------------------------------------------------------
@@ -229,7 +231,7 @@ extern "C" int32_t dipsb_create(const dipsb_config* cfg, dipsb_ctx** out) {
     g.width = cfg->width; g.height = cfg->height; g.npx = (uint64_t)cfg->width * cfg->height;
     g.format = cfg->format; g.bpp = bpp_of(cfg->format); g.chan_byte = chan_byte_of(cfg->format, cfg->chroma);
     g.num_sms = (uint32_t)prop.multiProcessorCount;
-    if (!plan_geometry(g, 0, 0, 0, 1)) {
+    if (!plan_geometry(g, 0, 0, 0, clip_ws_available(g.bpp, g.chan_byte, cfg->mode) ? 1 : 0)) {
         delete c;
         return fail(nullptr, DIPSB_ERR_INVALID, "dipsb_create: no kernel geometry fits %ux%u", cfg->width, cfg->height);
     }
@@ -351,7 +353,7 @@ extern "C" int32_t dipsb_set_tuning(dipsb_ctx* c, uint32_t stages, uint32_t tile
     if (c->comm) return fail(c, DIPSB_ERR_STATE, "set_tuning: the geometry is fixed once the context has a communicator (its planes are mapped by the peers)");
     CK(c, cudaStreamSynchronize(c->stream));
     Geometry g = c->g;
-    if (!plan_geometry(g, stages, tile_px, regs, pick_kernel(c->tune_kernel, stages, regs))) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u / regs %u do not fit", tile_px, stages, regs);
+    if (!plan_geometry(g, stages, tile_px, regs, pick_kernel(c, c->tune_kernel, stages, regs) < 0 ? 0 : pick_kernel(c, c->tune_kernel, stages, regs))) return fail(c, DIPSB_ERR_INVALID, "set_tuning: tile_px %u / stages %u / regs %u do not fit", tile_px, stages, regs);
     for (int k = 0; k < 2; ++k) { cudaFree(c->state[k]); c->state[k] = nullptr; }
     cudaFree(c->acc); c->acc = nullptr;
     cudaFree(c->planar); c->planar = nullptr;
@@ -379,7 +381,8 @@ extern "C" int32_t dipsb_set_kernel(dipsb_ctx* c, int32_t kernel) {
     CK(c, cudaSetDevice(c->device));
     if (kernel < -1 || kernel > 1) return fail(c, DIPSB_ERR_INVALID, "set_kernel: %d is not -1 (automatic), 0 (clip_kernel) or 1 (clip_kernel_ws)", kernel);
     const int requested = kernel;
-    kernel = pick_kernel(requested, c->tune_stages, c->tune_regs);
+    kernel = pick_kernel(c, requested, c->tune_stages, c->tune_regs);
+    if (kernel < 0) return fail(c, DIPSB_ERR_INVALID, "set_kernel: clip_kernel_ws has no variant for 4 B/px frames with a chroma filter in per-frame mode");
     if (kernel == c->g.kernel) { c->tune_kernel = requested; return DIPSB_OK; }
     if (c->frames_processed != 0) return fail(c, DIPSB_ERR_STATE, "set_kernel: only on a fresh or reset context");
     if (c->comm) return fail(c, DIPSB_ERR_STATE, "set_kernel: the geometry is fixed once the context has a communicator");

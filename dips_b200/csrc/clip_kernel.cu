@@ -128,6 +128,12 @@ __device__ __forceinline__ void wait_peer_flag(const unsigned long long* flag, u
     }
     asm volatile("fence.proxy.async.global;" ::: "memory");   // the frame is read through the async proxy (TMA)
 }
+// one lane of the (converged) warp, chosen by the hardware: no lane-id register has to stay live for "if (lane == 0)"
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+    return p != 0u;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -181,6 +187,12 @@ __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one
     return d;
 }
 
+// a * b + c that is executed where it stands (never hoisted out of a loop, never kept live across one)
+__device__ __forceinline__ uint32_t mad_volatile(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t mad_fma(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -422,8 +434,11 @@ __global__ void __maxnreg__(MAXREG) clip_kernel(const __grid_constant__ KParams 
 //   * the frame loop is unrolled over the S pipeline stages (x2 for odd S, for the prev/cur ping-pong): stage index,
 //     barrier addresses and mbarrier parities are compile-time, no per-frame stage bookkeeping;
 //   * per-frame sums use 3-input adds on the packed lanes and one IDP.2A fold instead of an IDP.2A per register.
+// The threshold counts of a flush interval (<= 128 frames) fit a byte: four pixels share one accumulator register, which
+// leaves the warp-specialised kernel 4 registers more than one u16 per count would (it runs at the 64-register limit).
+// accM4[i] holds pixels 4i .. 4i+3 of the thread as bytes 0, 2, 1, 3 (m[2i] + (m[2i+1] << 8)).
 template <int N>
-__device__ __forceinline__ uint32_t diff_px_ws(const uint32_t* cur, const uint32_t* ref, uint32_t* accD, uint32_t* accM,
+__device__ __forceinline__ uint32_t diff_px_ws(const uint32_t* cur, const uint32_t* ref, uint32_t* accD, uint32_t* accM4,
                                                uint32_t negtau2, uint32_t one) {
     uint32_t d[N], m[N];
 #pragma unroll
@@ -433,12 +448,18 @@ __device__ __forceinline__ uint32_t diff_px_ws(const uint32_t* cur, const uint32
         d[j] = mad_fma(hi, one + one, 0u - sum);
         m[j] = __viaddmin_s16x2_relu(d[j], negtau2, 0x00010001u);
         accD[j] = add_fma(accD[j], d[j], one);
-        accM[j] = add_fma(accM[j], m[j], one);
     }
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) accM4[i] = add_fma(accM4[i], m[2 * i + 1] * 256u + m[2 * i], one);
     uint32_t sD = 0u, sM = 0u;   // packed lane sums: <= 8*510 and <= 8 per lane
 #pragma unroll
     for (int j = 0; j + 1 < N; j += 2) { sD = sD + d[j] + d[j + 1]; sM = sM + m[j] + m[j + 1]; }
     return __dp2a_lo(sD, 0x0101u, __dp2a_lo(sM, 0x0101u, 0u) << 20);
+}
+// count of the thread's pixel `px` (0..15) out of the byte-packed accumulators
+__device__ __forceinline__ uint32_t count_of(const uint32_t* accM4, int px) {
+    const int e = px & 3, byte = (e == 1) ? 2 : (e == 2) ? 1 : e;
+    return (accM4[px >> 2] >> (8 * byte)) & 0xFFu;
 }
 
 template <int BPP, int CH, int MODE, int S>
@@ -530,9 +551,11 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
             ra[2 * q] = r.x; ra[2 * q + 1] = r.y;
         }
     }
-    uint32_t accD[R], accM[R];
+    uint32_t accD[R], accM[R / 2];   // sums as u16 pairs, counts as bytes (see diff_px_ws)
 #pragma unroll
-    for (int j = 0; j < R; ++j) accD[j] = accM[j] = 0u;
+    for (int j = 0; j < R; ++j) accD[j] = 0u;
+#pragma unroll
+    for (int j = 0; j < R / 2; ++j) accM[j] = 0u;
 
     const uint32_t tau = P.tau > 511u ? 511u : P.tau;
     const uint32_t negtau2 = ((0u - tau) & 0xFFFFu) * 0x00010001u;
@@ -548,10 +571,12 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
         for (int j = 0; j < R; ++j) {
             atomicAdd(acc_sum + (2 * j) * nthr, accD[j] & 0xFFFFu);
             atomicAdd(acc_sum + (2 * j + 1) * nthr, accD[j] >> 16);
-            atomicAdd(acc_cnt + (2 * j) * nthr, accM[j] & 0xFFFFu);
-            atomicAdd(acc_cnt + (2 * j + 1) * nthr, accM[j] >> 16);
-            accD[j] = accM[j] = 0u;
+            atomicAdd(acc_cnt + (2 * j) * nthr, count_of(accM, 2 * j));
+            atomicAdd(acc_cnt + (2 * j + 1) * nthr, count_of(accM, 2 * j + 1));
+            accD[j] = 0u;
         }
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) accM[j] = 0u;
     };
     // last flush of a sharded pass (KParams::xchg_*): owned elements as above; every other element's total goes to its owner
     auto flush_to_owners = [&]() {
@@ -560,7 +585,7 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
         for (int k = 0; k < 2 * R; ++k) {
             const uint32_t idx = base + (uint32_t)k * nthr;
             const uint32_t d = (k & 1) ? accD[k / 2] >> 16 : accD[k / 2] & 0xFFFFu;
-            const uint32_t m = (k & 1) ? accM[k / 2] >> 16 : accM[k / 2] & 0xFFFFu;
+            const uint32_t m = count_of(accM, k);
             if (idx - P.xchg_own_lo < P.xchg_own_len) {
                 atomicAdd(P.acc_sum + idx, d);
                 atomicAdd(P.acc_cnt + idx, m);
@@ -578,14 +603,14 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
     auto fetch = [&](uint32_t stage, uint32_t par, uint32_t* cur, uint32_t token) {
         mbar_wait_after(full_bar + 8u * stage, par, token);
         if constexpr (BPP == 4) {
-            // convert piece by piece: only 4 raw words are live next to the 32 state / accumulator registers
+            // convert piece by piece: only 4 raw words are live next to the state / accumulator registers
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
                 const uint4 x = lds128(my_smem + stage * stage_bytes + my_step * v);
                 intensity4_x<CH>(x, cur[2 * v], cur[2 * v + 1]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
+            if (elect_one()) mbar_arrive(empty_bar + 8u * stage);
         } else {
             uint32_t w[kWords];
 #pragma unroll
@@ -594,13 +619,13 @@ __global__ void __maxnreg__(64) clip_kernel_ws(const __grid_constant__ KParams P
                 w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
+            if (elect_one()) mbar_arrive(empty_bar + 8u * stage);
             intensity16<BPP, CH>(w, cur);
         }
     };
     auto emit = [&](uint32_t packed) {
         const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, packed);
-        if (lane == 0) P.partials[part] = wsum;
+        if (elect_one()) P.partials[part] = wsum;
         part += P.words_per_frame;
         return wsum;
     };
@@ -753,9 +778,12 @@ cudaError_t launch_ws(const Geometry& g, const ClipArgs& a, const KParams& kp, s
 template <int BPP, int CH>
 cudaError_t launch_m(const Geometry& g, const ClipArgs& a, const KParams& kp, size_t smem, cudaStream_t s) {
     if (g.kernel == 1) {   // warp-specialised variant: 16 px/thread, 64 registers, 3 or 4 compile-time stages
-        if (g.stages == 4) return a.mode == 0 ? launch_ws<BPP, CH, 0, 4>(g, a, kp, smem, s) : launch_ws<BPP, CH, 1, 4>(g, a, kp, smem, s);
-        if (g.stages == 3) return a.mode == 0 ? launch_ws<BPP, CH, 0, 3>(g, a, kp, smem, s) : launch_ws<BPP, CH, 1, 3>(g, a, kp, smem, s);
-        return cudaErrorInvalidValue;
+        if (g.stages != 3 && g.stages != 4) return cudaErrorInvalidValue;
+        if (a.mode == 0) return g.stages == 4 ? launch_ws<BPP, CH, 0, 4>(g, a, kp, smem, s) : launch_ws<BPP, CH, 0, 3>(g, a, kp, smem, s);
+        // 4 B/px + chroma filter + per-frame mode does not fit 64 registers without spilling: not instantiated, the planner
+        // gives such contexts clip_kernel (72 registers) -- clip_ws_available()
+        if constexpr (BPP == 4 && CH >= 0) return cudaErrorInvalidValue;
+        else return g.stages == 4 ? launch_ws<BPP, CH, 1, 4>(g, a, kp, smem, s) : launch_ws<BPP, CH, 1, 3>(g, a, kp, smem, s);
     }
     return a.mode == 0 ? launch_t<BPP, CH, 0>(g, a, kp, smem, s) : launch_t<BPP, CH, 1>(g, a, kp, smem, s);
 }
@@ -774,6 +802,7 @@ inline uint32_t stage_bytes_of(uint32_t threads, int bpp, int groups) { return (
 
 }  // namespace
 
+bool clip_ws_available(int bpp, int chan_byte, int mode) { return !(bpp == 4 && chan_byte >= 0 && mode == 1); }
 bool clip_can_store_first(const Geometry& g, uint32_t n_segments) { return g.kernel == 1 && n_segments == 1; }
 bool clip_can_push(const Geometry& g, uint32_t n_segments) { return g.kernel == 1 && n_segments == 1 && g.n_elems < (1ull << 32); }
 

@@ -92,6 +92,8 @@ int clip_max_threads_per_sm(int regs);
 // resident blocks/SM for (threads, stages, register variant), or 0 when it does not fit
 int clip_occupancy(uint32_t threads, int bpp, uint32_t stages, int regs);
 uint32_t clip_active_warps(const Geometry& g);
+// clip_kernel_ws is instantiated for every (bytes per pixel, channel, mode) but 4 B/px + chroma filter + per-frame mode
+bool clip_ws_available(int bpp, int chan_byte, int mode);
 cudaError_t launch_clip(const Geometry& g, const ClipArgs& a, cudaStream_t s);
 cudaError_t launch_stream_probe(const Geometry& g, const uint8_t* frames, uint64_t stride, uint32_t n_frames, cudaStream_t s);
 

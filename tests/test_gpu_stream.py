@@ -335,7 +335,7 @@ def test_large_frames_take_the_row_band_path_with_identical_results(oracle, flav
                 assert np.array_equal(acc[0], acc_want[0]) and np.array_equal(acc[1], acc_want[1])
 
 
-def test_stage_and_dispatch_equal_push_frame(torch_cuda, oracle):
+def test_stage_and_dispatch_equal_push_frame(oracle):
     """dipsb_stage_frame + dipsb_dispatch_staged (the reference's add_texture + dispatch split, dips/src/gpu/mod.rs:170, :306)
     give exactly what dipsb_push_frame gives, frame by frame, for the north-star and the ring flavours."""
     import dips_b200
