@@ -343,6 +343,179 @@ __global__ void ring_kernel(const RingK K) {
     }
 }
 
+// ---- 4 pixels per thread ("quad") versions of the per-frame kernels -----------------------------------------------------
+// One thread = 4 consecutive pixels of a row: one 128-bit load of RGBx (three 32-bit loads of RGB), packed intensity, one
+// 64-bit load / store per u16 plane, one 128-bit store of the RGBA output.  Row and column come from one 32-bit division per
+// quad; the accumulator slots of a quad are idx0 + e*threads (e = 0..3) in the clip kernel's tile order, so a warp touches
+// whole 32-byte sectors of the planes.  Taken when the width is a multiple of 4 and base / pitch are aligned; every other
+// frame goes to the one-pixel-per-thread kernels above.
+__device__ __forceinline__ uint32_t rgba_word(uchar4 v) { return (uint32_t)v.x | ((uint32_t)v.y << 8) | ((uint32_t)v.z << 16) | ((uint32_t)v.w << 24); }
+
+template <int FBPP, int CH>
+__device__ __forceinline__ void quad_intensity(const uint8_t* __restrict__ row, uint32_t x, uint32_t& i01, uint32_t& i23) {
+    if constexpr (FBPP == 4) {
+        intensity4_x<CH>(__ldg(reinterpret_cast<const uint4*>(row + 4ull * x)), i01, i23);
+    } else {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(row + 3ull * x);
+        intensity4_3<CH>(__ldg(w), __ldg(w + 1), __ldg(w + 2), i01, i23);
+    }
+}
+__device__ __forceinline__ void block_add_scalars(unsigned long long s, unsigned long long c, unsigned long long* sad, unsigned long long* cnt) {
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+        c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+    }
+    __shared__ unsigned long long sh_s[kThreads / 32], sh_c[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_c[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kThreads / 32; ++k) { s += sh_s[k]; c += sh_c[k]; }
+        if (s) atomicAdd(sad, s);
+        if (c) atomicAdd(cnt, c);
+    }
+}
+
+template <int FBPP, int CH>
+__global__ void __launch_bounds__(kThreads) frame4_kernel(const FrameK K) {
+    unsigned long long s = 0, c = 0;
+    const uint32_t q_begin = (uint32_t)(K.p_begin / 4), q_end = (uint32_t)(K.p_end / 4);
+    for (uint32_t q = q_begin + blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += gridDim.x * blockDim.x) {
+        const uint32_t p = 4u * q;
+        uint32_t cur01, cur23;
+        if (K.i2src) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(K.i2src + p));
+            cur01 = v.x; cur23 = v.y;
+        } else {
+            const uint32_t y = p / K.width, x = p - y * K.width;
+            quad_intensity<FBPP, CH>(K.frame + (uint64_t)y * K.pitch, x, cur01, cur23);
+        }
+        const uint2 ref = __ldg(reinterpret_cast<const uint2*>(K.state_in + p));
+        const int cur[4] = {(int)(cur01 & 0xFFFFu), (int)(cur01 >> 16), (int)(cur23 & 0xFFFFu), (int)(cur23 >> 16)};
+        const int rf[4] = {(int)(ref.x & 0xFFFFu), (int)(ref.x >> 16), (int)(ref.y & 0xFFFFu), (int)(ref.y >> 16)};
+        int sd[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sd[e] = rf[e] - cur[e];                 // sign convention start - current
+        if (K.accumulate) {
+            const uint64_t i0 = tile_order_index(p, K.tile_px, K.threads, K.geo_bpp, K.geo_groups);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t d = (uint32_t)(sd[e] < 0 ? -sd[e] : sd[e]), m = d > K.tau ? 1u : 0u;
+                K.acc_sum[i0 + (uint64_t)e * K.threads] += d;               // each slot is owned by exactly one thread
+                K.acc_cnt[i0 + (uint64_t)e * K.threads] += m;
+                s += d; c += m;
+            }
+        }
+        if (K.state_out) *reinterpret_cast<uint2*>(K.state_out + p) = make_uint2(cur01, cur23);
+        if (K.out_rgba)
+            *reinterpret_cast<uint4*>(K.out_rgba + 4ull * p) =
+                make_uint4(rgba_word(visual_pixel(sd[0], K.colorize, K.filter, K.sig)), rgba_word(visual_pixel(sd[1], K.colorize, K.filter, K.sig)),
+                           rgba_word(visual_pixel(sd[2], K.colorize, K.filter, K.sig)), rgba_word(visual_pixel(sd[3], K.colorize, K.filter, K.sig)));
+    }
+    if (K.accumulate) block_add_scalars(s, c, K.sad, K.cnt);
+}
+
+__device__ __forceinline__ uint32_t quad_elem(uint2 v, int e) { return e == 0 ? (v.x & 0xFFFFu) : e == 1 ? (v.x >> 16) : e == 2 ? (v.y & 0xFFFFu) : (v.y >> 16); }
+__device__ __forceinline__ uint32_t grey_i2(uint32_t i2) { return 2u * ((i2 + 1u) >> 1); }   // rgba8unorm store of an intensity, in I2 units
+
+template <int FBPP, int CH>
+__global__ void __launch_bounds__(kThreads) ring4_kernel(const RingK K) {
+    const uint64_t npx = (uint64_t)K.width * K.height;
+    unsigned long long s = 0, c = 0;
+    const uint32_t q_begin = (uint32_t)(K.p_begin / 4), q_end = (uint32_t)(K.p_end / 4);
+    for (uint32_t q = q_begin + blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += gridDim.x * blockDim.x) {
+        const uint32_t p = 4u * q;
+        uint2 raw;
+        if (K.i2src) raw = __ldg(reinterpret_cast<const uint2*>(K.i2src + p));
+        else {
+            const uint32_t y = p / K.width, x = p - y * K.width;
+            quad_intensity<FBPP, CH>(K.frame + (uint64_t)y * K.pitch, x, raw.x, raw.y);
+        }
+        // the ring slots of my 4 pixels (compile-time slot indices only: everything stays in registers)
+        const uint2 s0 = 0 == K.write_slot ? raw : *reinterpret_cast<const uint2*>(K.ring + p);
+        const uint2 s1 = 1 == K.write_slot ? raw : *reinterpret_cast<const uint2*>(K.ring + npx + p);
+        const uint2 s2 = K.n_slots < 4 ? make_uint2(0, 0) : (2 == K.write_slot ? raw : *reinterpret_cast<const uint2*>(K.ring + 2 * npx + p));
+        const uint2 s3 = K.n_slots < 4 ? make_uint2(0, 0) : (3 == K.write_slot ? raw : *reinterpret_cast<const uint2*>(K.ring + 3 * npx + p));
+        const uint2 st = *reinterpret_cast<const uint2*>(K.start + p);
+        uint32_t start[4], med[4], g0[4], g1[4], g2[4], g3[4];       // g*: the slots after the in-place grey quantisation
+        bool grey_out = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t a = quad_elem(s0, e), b = quad_elem(s1, e), cc = quad_elem(s2, e), d = quad_elem(s3, e);
+            start[e] = quad_elem(st, e);
+            if (K.n_slots == 4) {                                    // `dips`
+                if (K.compute_start) start[e] = grey_i2(upper_median4(a, b, cc, d));      // pre_compute_shader.wgsl:103-131
+                g0[e] = K.grey_slot == 0 ? grey_i2(a) : a; g1[e] = K.grey_slot == 1 ? grey_i2(b) : b;             // dips_shader.wgsl:187
+                g2[e] = K.grey_slot == 2 ? grey_i2(cc) : cc; g3[e] = K.grey_slot == 3 ? grey_i2(d) : d;
+                med[e] = upper_median4(g0[e], g1[e], g2[e], g3[e]);                       // :191-214
+            } else {                                                 // `dips_alt`, NUM_TEXTURES = 2
+                g0[e] = a; g1[e] = b; g2[e] = cc; g3[e] = d;
+                med[e] = K.median_is_max ? max(a, b) : min(a, b);
+                if (K.snapshot) start[e] = grey_i2(med[e]);          // pre_compute_shader.wgsl:231-235
+            }
+        }
+        if (K.n_slots == 4) {
+            if (K.compute_start) *reinterpret_cast<uint2*>(K.start + p) = make_uint2(start[0] | (start[1] << 16), start[2] | (start[3] << 16));
+            if (K.grey_slot == 0 || K.write_slot == 0) *reinterpret_cast<uint2*>(K.ring + p) = make_uint2(g0[0] | (g0[1] << 16), g0[2] | (g0[3] << 16));
+            if (K.grey_slot == 1 || K.write_slot == 1) *reinterpret_cast<uint2*>(K.ring + npx + p) = make_uint2(g1[0] | (g1[1] << 16), g1[2] | (g1[3] << 16));
+            if (K.grey_slot == 2 || K.write_slot == 2) *reinterpret_cast<uint2*>(K.ring + 2 * npx + p) = make_uint2(g2[0] | (g2[1] << 16), g2[2] | (g2[3] << 16));
+            if (K.grey_slot == 3 || K.write_slot == 3) *reinterpret_cast<uint2*>(K.ring + 3 * npx + p) = make_uint2(g3[0] | (g3[1] << 16), g3[2] | (g3[3] << 16));
+        } else {
+            *reinterpret_cast<uint2*>(K.ring + (uint64_t)K.write_slot * npx + p) = raw;
+            if (K.snapshot) {
+                *reinterpret_cast<uint2*>(K.start + p) = make_uint2(start[0] | (start[1] << 16), start[2] | (start[3] << 16));
+                grey_out = true;
+            }
+        }
+        if (!K.do_diff) continue;
+        if (grey_out) {
+            if (K.out_rgba)
+                *reinterpret_cast<uint4*>(K.out_rgba + 4ull * p) =
+                    make_uint4((start[0] >> 1) * 0x010101u | 0xFF000000u, (start[1] >> 1) * 0x010101u | 0xFF000000u,
+                               (start[2] >> 1) * 0x010101u | 0xFF000000u, (start[3] >> 1) * 0x010101u | 0xFF000000u);
+            continue;
+        }
+        const uint64_t i0 = tile_order_index(p, K.tile_px, K.threads, K.geo_bpp, K.geo_groups);
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int sdiff = (int)start[e] - (int)med[e];
+            const uint32_t d = (uint32_t)(sdiff < 0 ? -sdiff : sdiff), m = d > K.tau ? 1u : 0u;
+            K.acc_sum[i0 + (uint64_t)e * K.threads] += d;
+            K.acc_cnt[i0 + (uint64_t)e * K.threads] += m;
+            s += d; c += m;
+            if (K.out_rgba) o[e] = rgba_word(visual_pixel(sdiff, K.colorize, K.filter, K.sig));
+        }
+        if (K.out_rgba) *reinterpret_cast<uint4*>(K.out_rgba + 4ull * p) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    block_add_scalars(s, c, K.sad, K.cnt);
+}
+
+template <int FBPP>
+__global__ void __launch_bounds__(kThreads) passthrough4_kernel(const uint8_t* __restrict__ frame, uint64_t pitch, uint32_t width, uint32_t q_begin,
+                                                                uint32_t q_end, int bgr, uint8_t* __restrict__ out) {
+    for (uint32_t q = q_begin + blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += gridDim.x * blockDim.x) {
+        const uint32_t p = 4u * q, y = p / width, x = p - y * width;
+        const uint8_t* row = frame + (uint64_t)y * pitch;
+        uint32_t px[4];                                               // r | g<<8 | b<<16 | a<<24 per pixel
+        if constexpr (FBPP == 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + 4ull * x));
+            px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+        } else {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(row + 3ull * x);
+            const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);
+            px[0] = __byte_perm(a, 0xFF000000u, 0x7210);
+            px[1] = __byte_perm(a, b, 0x0543) | 0xFF000000u;
+            px[2] = __byte_perm(b, c, 0x0432) | 0xFF000000u;
+            px[3] = __byte_perm(c, 0xFF000000u, 0x7321);
+        }
+        if (bgr) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) px[e] = __byte_perm(px[e], 0u, 0x3012);      // swap bytes 0 and 2
+        }
+        *reinterpret_cast<uint4*>(out + 4ull * p) = make_uint4(px[0], px[1], px[2], px[3]);
+    }
+}
+
 // N4: spatial median of the intensity plane, window w in {3,5,7}.  A CORRECT median: the full symmetric window
 // [-w/2, +w/2]^2, zero for taps outside the frame (as the reference pads, dips_shader.wgsl:135-139), element w*w/2 of the
 // ascending order.  The reference's own loop covers only the half-open window [-w/2, w/2) and picks the wrong element
@@ -532,6 +705,21 @@ cudaError_t launch_intensity_map(const Geometry& g, const uint32_t* internal, ui
     count_launch();
     return cudaGetLastError();
 }
+// the 4-pixels-per-thread kernels need whole quads inside a row, aligned loads and 32-bit pixel indices
+static bool quad_path(const Geometry& g, const uint8_t* frame, uint64_t pitch, int frame_bpp, uint64_t p_begin, uint64_t p_end) {
+    const uint64_t align = frame_bpp == 4 ? 15u : 3u;
+    return (g.width & 3u) == 0 && g.npx < (1ull << 32) && ((p_begin | p_end) & 3u) == 0 &&
+           (frame == nullptr || (((uintptr_t)frame | pitch) & align) == 0);
+}
+#define DIPSB_DISPATCH_QUAD(LAUNCH, fbpp, ch)                                         \
+    do {                                                                              \
+        if ((fbpp) == 4) {                                                            \
+            switch (ch) { case 0: LAUNCH(4, 0); break; case 1: LAUNCH(4, 1); break; case 2: LAUNCH(4, 2); break; default: LAUNCH(4, -1); } \
+        } else {                                                                      \
+            switch (ch) { case 0: LAUNCH(3, 0); break; case 1: LAUNCH(3, 1); break; case 2: LAUNCH(3, 2); break; default: LAUNCH(3, -1); } \
+        }                                                                             \
+    } while (0)
+
 cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) {
     FrameK K;
     K.frame = a.frame; K.pitch = a.pitch; K.width = g.width; K.height = g.height;
@@ -542,7 +730,14 @@ cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) 
     K.accumulate = a.accumulate; K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
     K.p_begin = a.p_begin; K.p_end = a.p_end ? a.p_end : g.npx;
     if (K.p_end <= K.p_begin) return cudaSuccess;
-    frame_kernel<<<grid_for(K.p_end - K.p_begin, g), kThreads, 0, s>>>(K);
+    if (quad_path(g, a.frame, a.pitch, K.bpp, K.p_begin, K.p_end)) {
+        const int grid = grid_for((K.p_end - K.p_begin) / 4, g);
+#define DIPSB_FRAME4(FB, C) frame4_kernel<FB, C><<<grid, kThreads, 0, s>>>(K)
+        DIPSB_DISPATCH_QUAD(DIPSB_FRAME4, K.bpp, K.chan_byte);
+#undef DIPSB_FRAME4
+    } else {
+        frame_kernel<<<grid_for(K.p_end - K.p_begin, g), kThreads, 0, s>>>(K);
+    }
     count_launch();
     return cudaGetLastError();
 }
@@ -573,7 +768,14 @@ cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s) {
     K.colorize = a.colorize; K.filter = a.filter; K.sig = a.sig_scalar;
     K.p_begin = a.p_begin; K.p_end = a.p_end ? a.p_end : g.npx;
     if (K.p_end <= K.p_begin) return cudaSuccess;
-    ring_kernel<<<grid_for(K.p_end - K.p_begin, g), kThreads, 0, s>>>(K);
+    if (quad_path(g, a.frame, a.pitch, K.bpp, K.p_begin, K.p_end)) {
+        const int grid = grid_for((K.p_end - K.p_begin) / 4, g);
+#define DIPSB_RING4(FB, C) ring4_kernel<FB, C><<<grid, kThreads, 0, s>>>(K)
+        DIPSB_DISPATCH_QUAD(DIPSB_RING4, K.bpp, K.chan_byte);
+#undef DIPSB_RING4
+    } else {
+        ring_kernel<<<grid_for(K.p_end - K.p_begin, g), kThreads, 0, s>>>(K);
+    }
     count_launch();
     return cudaGetLastError();
 }
@@ -581,6 +783,14 @@ cudaError_t launch_passthrough_rgba(const Geometry& g, const uint8_t* frame, uin
                                     cudaStream_t s, uint64_t p_begin, uint64_t p_end) {
     if (!p_end) p_end = g.npx;
     if (p_end <= p_begin) return cudaSuccess;
+    const int fbpp = (format == 0 || format == 2) ? 3 : 4;
+    if (quad_path(g, frame, pitch, fbpp, p_begin, p_end) && ((uintptr_t)out & 15u) == 0) {
+        const int grid = grid_for((p_end - p_begin) / 4, g), bgr = (format == 2 || format == 3) ? 1 : 0;
+        if (fbpp == 4) passthrough4_kernel<4><<<grid, kThreads, 0, s>>>(frame, pitch, g.width, (uint32_t)(p_begin / 4), (uint32_t)(p_end / 4), bgr, out);
+        else passthrough4_kernel<3><<<grid, kThreads, 0, s>>>(frame, pitch, g.width, (uint32_t)(p_begin / 4), (uint32_t)(p_end / 4), bgr, out);
+        count_launch();
+        return cudaGetLastError();
+    }
     passthrough_kernel<<<grid_for(p_end - p_begin, g), kThreads, 0, s>>>(frame, pitch, g.width, p_begin, p_end, format, out);
     count_launch();
     return cudaGetLastError();

@@ -90,4 +90,27 @@ __device__ __forceinline__ void intensity4_x(const uint4 x, uint32_t& i01, uint3
     }
 }
 
+// 3 B/px: 4 pixels = 12 bytes = three words -> two packed registers (pixels 0,1 and 2,3)
+template <int CH>
+__device__ __forceinline__ void intensity4_3(const uint32_t a, const uint32_t b, const uint32_t c, uint32_t& i01, uint32_t& i23) {
+    const uint32_t w[3] = {a, b, c};
+    if constexpr (CH < 0) {
+        const uint32_t x01 = __byte_perm(a, 0u, 0x4340);  // (a0, a3)
+        const uint32_t t = __byte_perm(a, b, 0x5421);     // a1 a2 b0 b1
+        const uint32_t y01 = __byte_perm(t, 0u, 0x4240);  // (a1, b0)
+        const uint32_t z01 = __byte_perm(t, 0u, 0x4341);  // (a2, b1)
+        const uint32_t u = __byte_perm(b, c, 0x6532);     // b2 b3 c1 c2
+        const uint32_t x23 = __byte_perm(u, 0u, 0x4240);  // (b2, c1)
+        const uint32_t y23 = __byte_perm(u, 0u, 0x4341);  // (b3, c2)
+        const uint32_t z23 = __byte_perm(c, 0u, 0x4340);  // (c0, c3)
+        i01 = __vimax3_u16x2(x01, y01, z01) + __vimin3_u16x2(x01, y01, z01);
+        i23 = __vimax3_u16x2(x23, y23, z23) + __vimin3_u16x2(x23, y23, z23);
+    } else {
+        const uint32_t p01 = pair_bytes<CH, CH + 3>(w);
+        const uint32_t p23 = pair_bytes<CH + 6, CH + 9>(w);
+        i01 = p01 + p01;
+        i23 = p23 + p23;
+    }
+}
+
 }  // namespace dipsb
