@@ -822,7 +822,8 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     // and read-back of band k-1 (read-back stream) run concurrently, and so do the CPU staging copies on either side.  In
     // the pipelined call the neighbouring frames already overlap and the extra launches only cost; a spatial window
     // needs the whole frame.
-    const uint32_t bands = (overlap || windowed(c) || pre_staged) ? 1u : stage_pieces(std::max<uint64_t>(fb, g.npx * 4), height);
+    const uint32_t bands = pre_staged ? c->staged_bands
+                                      : (overlap || windowed(c)) ? 1u : stage_pieces(std::max<uint64_t>(fb, g.npx * 4), height);
     const bool banded = bands > 1;
     const bool side_upload = overlap || banded;
     cudaStream_t up = side_upload ? c->copy_stream : c->stream;
@@ -895,7 +896,7 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
         const uint64_t p0 = (uint64_t)r0 * width, p1 = (uint64_t)r1 * width;
         // upload
         if (pre_staged) {
-            CK(c, cudaStreamWaitEvent(c->stream, sl.ev_in[0], 0));   // recorded by dipsb_stage_frame behind its upload
+            CK(c, cudaStreamWaitEvent(c->stream, sl.ev_in[k], 0));   // recorded by dipsb_stage_frame behind the upload of band k
         } else {
             const uint8_t* src = px + (uint64_t)r0 * stride;
             if (!in_direct) {
@@ -984,7 +985,7 @@ extern "C" int32_t dipsb_push_frame(dipsb_ctx* c, const uint8_t* px, uint32_t wi
     if (!c || !px) return DIPSB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     if (c->slot[0].pending || c->slot[1].pending) return fail(c, DIPSB_ERR_STATE, "push_frame: a pipelined frame is in flight; call dipsb_flush_frame first");
-    if (c->staged) { CK(c, cudaEventSynchronize(c->slot[0].ev_in[0])); c->staged = false; }   // a staged frame is dropped
+    if (c->staged) { CK(c, cudaEventSynchronize(c->slot[0].ev_in[c->staged_bands - 1])); c->staged = false; }   // a staged frame is dropped
     int32_t rc = submit_frame(c, c->slot[0], px, width, height, stride, format, out_rgba != nullptr, false,
                               out_rgba && host_pinned(out_rgba) ? out_rgba : nullptr);
     if (rc) return rc;
@@ -1006,11 +1007,16 @@ extern "C" int32_t dipsb_stage_frame(dipsb_ctx* c, const uint8_t* px, uint32_t w
     dipsb_ctx::FrameSlot& sl = c->slot[0];
     int32_t rc = ensure_slot(c, sl, row * height);
     if (rc) return rc;
-    if (c->staged) CK(c, cudaEventSynchronize(sl.ev_in[0]));     // a staged frame that was never dispatched: its upload still reads h_in
-    host_copy2d(sl.h_in, row, px, stride, row, height);
-    CK(c, cudaMemcpyAsync(sl.d_in, sl.h_in, row * height, cudaMemcpyHostToDevice, c->copy_stream));
-    CK(c, cudaEventRecord(sl.ev_in[0], c->copy_stream));
-    c->staged = true; c->staged_format = format;
+    if (c->staged) CK(c, cudaEventSynchronize(sl.ev_in[c->staged_bands - 1]));   // a staged frame that was never dispatched: its upload still reads h_in
+    // in the same row bands as dipsb_push_frame: the upload of band k runs while the CPU copies band k+1
+    const uint32_t bands = windowed(c) ? 1u : stage_pieces(std::max<uint64_t>(row * height, g.npx * 4), height);
+    for (uint32_t k = 0; k < bands; ++k) {
+        const uint32_t r0 = (uint32_t)((uint64_t)height * k / bands), r1 = (uint32_t)((uint64_t)height * (k + 1) / bands);
+        host_copy2d(sl.h_in + (uint64_t)r0 * row, row, px + (uint64_t)r0 * stride, stride, row, r1 - r0);
+        CK(c, cudaMemcpyAsync(sl.d_in + (uint64_t)r0 * row, sl.h_in + (uint64_t)r0 * row, (uint64_t)(r1 - r0) * row, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(c, cudaEventRecord(sl.ev_in[k], c->copy_stream));
+    }
+    c->staged = true; c->staged_format = format; c->staged_bands = bands;
     return DIPSB_OK;
 }
 

@@ -60,7 +60,7 @@ struct dipsb_ctx {
         bool out_deferred = false;             // the read-back is enqueued at collection time (pipelined, pinned caller)
     } slot[2];
     int next_slot = 0;
-    bool staged = false; int32_t staged_format = 0;   // dipsb_stage_frame put a frame into slot 0 and started its upload
+    bool staged = false; int32_t staged_format = 0; uint32_t staged_bands = 1;   // dipsb_stage_frame put a frame into slot 0 and started its upload (in row bands)
     bool out_pinned_hint = false;              // the pipelined caller's output buffers are page-locked
     // host clip staging
     uint8_t* h_chunk[2] = {nullptr, nullptr};
