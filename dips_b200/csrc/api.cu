@@ -269,6 +269,13 @@ extern "C" void dipsb_destroy(dipsb_ctx* c) {
 
 extern "C" const char* dipsb_last_error(const dipsb_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
 
+int32_t dipsb::finalize_pending(dipsb_ctx* c) {
+    if (!c->fin.pending) return DIPSB_OK;
+    c->fin.pending = false;
+    CK(c, launch_finalize_scalars(c->g, c->partials, c->fin.n, c->fin.words, c->d_sad + c->fin.first, c->d_cnt + c->fin.first, c->stream));
+    return DIPSB_OK;
+}
+
 int32_t dipsb::ensure_acc_zero(dipsb_ctx* c) {
     if (!c->acc_zero_pending) return DIPSB_OK;
     CK(c, cudaMemsetAsync(c->acc, 0, 2 * c->g.n_elems * sizeof(uint32_t), c->stream));
@@ -516,6 +523,35 @@ int32_t dipsb::ensure_scalars(dipsb_ctx* c, uint64_t upto) {
 }
 
 // ---- batch ---------------------------------------------------------------------------------------------------------
+// What the next frame does to a reference-flavour ring (N1): which slot it overwrites, whether the start plane / snapshot is
+// (re)computed, whether a difference is produced.  Advances the context's ring bookkeeping; returns true while the frame is
+// only passed through (the `dips` warm-up).  Shared by the per-frame call and the batch call.
+static bool ring_next_frame(dipsb_ctx* c, RingArgs& r) {
+    r.grey_slot = -1; r.compute_start = 0; r.snapshot = 0; r.median_is_max = 0; r.do_diff = 1;
+    if (c->cfg.flavor == DIPSB_FLAVOR_DIPS_RING4) {
+        if (c->snapshot_pending) { c->ring_seen = 0; c->ring_index = 0; c->snapshot_pending = false; }   // restart the warm-up
+        r.n_slots = 4;
+        const uint32_t seen = ++c->ring_seen;                     // frames including this one
+        if (seen < 4) {                                            // dispatch() == None: passthrough (mod.rs:394-396)
+            r.write_slot = (int)seen - 1; r.do_diff = 0;
+        } else if (seen == 4) {                                    // pre-compute + first dispatch on slot 0 (mod.rs:177-214)
+            r.write_slot = 3; r.compute_start = 1; r.grey_slot = 0;
+        } else {                                                   // update_temporal_texture (bind_groups.rs:407-427)
+            r.write_slot = r.grey_slot = (int)c->ring_index;
+            c->ring_index = (c->ring_index + 1) % 4;
+        }
+        if (seen > 4) c->ring_seen = 5;                            // saturate
+        return seen < 4;
+    }
+    r.n_slots = 2;
+    r.median_is_max = c->cfg.flavor == DIPSB_FLAVOR_ALT_RING2_MEDIAN;
+    r.write_slot = (int)c->ring_index;                            // texture_index, mod.rs:507-521
+    c->ring_index = (c->ring_index + 1) % 2;
+    r.snapshot = c->snapshot_pending ? 1 : 0;
+    c->snapshot_pending = false;
+    return false;                                                  // dips_alt always returns a computed frame
+}
+
 // The extra trailing frame of a per-frame shard on a layout the clip kernel cannot stream in place: wait for its arrival
 // with a one-thread kernel, then difference it as an ordinary one-frame call (the state plane chains it to frame n-1).
 static int32_t run_extra_frame(dipsb_ctx* c, const ShardExtra& x, uint64_t index) {
@@ -525,15 +561,52 @@ static int32_t run_extra_frame(dipsb_ctx* c, const ShardExtra& x, uint64_t index
 
 // `zero_padded`: the rows come from the library's own re-packed buffers -- pitch a multiple of 16 and zero bytes between the
 // end of a frame and its pitch -- so the clip kernel may round its last bulk copy of a frame up to 16 bytes.
+// Batch execution of the reference-exact flavours (DIPS_RING4 / ALT_RING2[_MEDIAN]) over a device-resident clip: the ring
+// state machine of dipsb_push_frame, frame by frame, through ring4_kernel (accumulators and per-frame scalars; no visual
+// output, no host copies).  The clip kernel implements the north-star semantics only: the median-of-4 ring needs 32 more
+// registers of state per thread than it has.
+static int32_t run_clip_ring(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first) {
+    const Geometry& g = c->g;
+    if (c->frames_processed + n > DIPSB_MAX_ACCUMULATED_FRAMES) return fail(c, DIPSB_ERR_STATE, "run_clip: the u32 sums would overflow; read the results and dipsb_reset");
+    if (stride < g.npx * g.bpp) return fail(c, DIPSB_ERR_INVALID, "run_clip: stride %llu smaller than a frame", (unsigned long long)stride);
+    int32_t rc = ensure_scalars(c, first + n);
+    if (rc) return rc;
+    if ((rc = ensure_acc_zero(c))) return rc;
+    CK(c, cudaMemsetAsync(c->d_sad + first, 0, n * sizeof(uint64_t), c->stream));
+    CK(c, cudaMemsetAsync(c->d_cnt + first, 0, n * sizeof(uint64_t), c->stream));
+    for (uint64_t k = 0; k < n; ++k) {
+        RingArgs r;
+        r.frame = d_frames + k * stride; r.pitch = (uint64_t)g.width * g.bpp; r.format = g.format; r.chan_byte = g.chan_byte;
+        if (windowed(c)) {
+            if ((rc = ensure_i2_scratch(c))) return rc;
+            if ((rc = filtered_plane(c, r.frame, g.format, c->i2_scratch + g.npx))) return rc;
+            r.i2src = c->i2_scratch + g.npx;
+        }
+        r.ring = c->ring; r.start = c->state[c->state_cur];
+        r.acc_sum = c->acc; r.acc_cnt = c->acc + g.n_elems; r.sad = c->d_sad + first + k; r.cnt = c->d_cnt + first + k;
+        r.out_rgba = nullptr;
+        r.tau = c->cfg.threshold; r.colorize = c->cfg.colorize; r.filter = c->cfg.filter; r.sig_scalar = c->cfg.sigmoid_scalar;
+        ring_next_frame(c, r);
+        CK(c, launch_ring(g, r, c->stream));
+    }
+    c->state_valid = true;
+    c->frames_processed += n;
+    c->scal_hi = std::max(c->scal_hi, first + n);
+    c->stream_index = first + n;
+    c->last_plan[1] = 0; c->last_plan[7] = 0;
+    return DIPSB_OK;
+}
+
 int32_t dipsb::run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first,
                                   bool zero_padded, const ShardExtra* extra) {
     const Geometry& g = c->g;
     if (n == 0) return DIPSB_OK;
     const ShardPush* push = (extra && extra->push.nranks) ? &extra->push : nullptr;
     bool* pushed = extra ? extra->pushed : nullptr;
+    const bool defer_fin = extra && extra->defer_finalize;
     if (extra && (!extra->frame || c->cfg.mode != DIPSB_MODE_PERFRAME)) extra = nullptr;   // no trailing frame
     const uint64_t n_scal = n + (extra ? 1 : 0);   // scalar rows this call produces
-    if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0) return fail(c, DIPSB_ERR_STATE, "run_clip: the ring flavours are streaming-only (dipsb_push_frame)");
+    if (c->cfg.flavor != DIPSB_FLAVOR_FRAME0) return run_clip_ring(c, d_frames, n, stride, first);
     if (n > 0x7FFFFFFFull) return fail(c, DIPSB_ERR_INVALID, "run_clip: too many frames in one call");
     if (c->frames_processed + n > DIPSB_MAX_ACCUMULATED_FRAMES)
         return fail(c, DIPSB_ERR_STATE, "run_clip: %llu frames accumulated, %llu more would overflow the u32 sums; read the results and dipsb_reset",
@@ -619,7 +692,8 @@ int32_t dipsb::run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_
             CK(c, cudaEventRecord(c->tev[c->tev_used + 1], c->stream));
             c->tev_used += 2;
         }
-        CK(c, launch_finalize_scalars(g, c->partials, (uint32_t)n_scal, words, c->d_sad + first, c->d_cnt + first, c->stream));
+        if (defer_fin) { c->fin.pending = true; c->fin.n = (uint32_t)n_scal; c->fin.words = words; c->fin.first = first; }
+        else CK(c, launch_finalize_scalars(g, c->partials, (uint32_t)n_scal, words, c->d_sad + first, c->d_cnt + first, c->stream));
         if (c->cfg.mode == DIPSB_MODE_PERFRAME) c->state_cur ^= 1;
         c->last_plan[1] = segs;
         c->last_plan[7] = 1;
@@ -860,30 +934,7 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
         r.acc_sum = c->acc; r.acc_cnt = c->acc + g.n_elems; r.sad = c->d_sad + idx; r.cnt = c->d_cnt + idx;
         r.out_rgba = want_rgba ? sl.d_out : nullptr;
         r.tau = c->cfg.threshold; r.colorize = c->cfg.colorize; r.filter = c->cfg.filter; r.sig_scalar = c->cfg.sigmoid_scalar;
-        r.grey_slot = -1; r.compute_start = 0; r.snapshot = 0; r.median_is_max = 0; r.do_diff = 1;
-        if (c->cfg.flavor == DIPSB_FLAVOR_DIPS_RING4) {
-            if (c->snapshot_pending) { c->ring_seen = 0; c->ring_index = 0; c->snapshot_pending = false; }   // restart the warm-up
-            r.n_slots = 4;
-            const uint32_t seen = ++c->ring_seen;                     // frames including this one
-            if (seen < 4) {                                            // dispatch() == None: passthrough (mod.rs:394-396)
-                r.write_slot = (int)seen - 1; r.do_diff = 0;
-            } else if (seen == 4) {                                    // pre-compute + first dispatch on slot 0 (mod.rs:177-214)
-                r.write_slot = 3; r.compute_start = 1; r.grey_slot = 0;
-            } else {                                                   // update_temporal_texture (bind_groups.rs:407-427)
-                r.write_slot = r.grey_slot = (int)c->ring_index;
-                c->ring_index = (c->ring_index + 1) % 4;
-            }
-            if (seen > 4) c->ring_seen = 5;                            // saturate
-            establishes = seen < 4;
-        } else {
-            r.n_slots = 2;
-            r.median_is_max = c->cfg.flavor == DIPSB_FLAVOR_ALT_RING2_MEDIAN;
-            r.write_slot = (int)c->ring_index;                        // texture_index, mod.rs:507-521
-            c->ring_index = (c->ring_index + 1) % 2;
-            r.snapshot = c->snapshot_pending ? 1 : 0;
-            c->snapshot_pending = false;
-            establishes = false;                                       // dips_alt always returns a computed frame
-        }
+        establishes = ring_next_frame(c, r);
     }
     c->state_valid = true;
     sl.out_direct = want_rgba && out_direct != nullptr;

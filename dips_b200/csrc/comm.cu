@@ -820,6 +820,9 @@ int32_t pass_run(dipsb_ctx* c, Pass& p) {
         for (int r = 0; r < m->nranks; ++r)
             x.recv[r] = reinterpret_cast<uint32_t*>(recv_area(m, m->win_peer[r], parity) + (uint64_t)m->rank * m->slot_bytes);
         p.extra.pushed = &p.pushed;
+        // overall mode: the scalars are nobody else's business -- finalise them after the peers have been told (pass_reduce);
+        // per-frame mode hands the boundary frame's scalars over with the stamp, so they have to exist first
+        p.extra.defer_finalize = c->cfg.mode == DIPSB_MODE_OVERALL && p.d_frames != nullptr;
     }
     const ShardExtra* extra = (p.has_extra || p.extra.push.nranks) ? &p.extra : nullptr;
     if (p.d_frames) return run_clip_on_stream(c, p.d_frames, p.n, p.stride, p.first, false, extra);
@@ -834,8 +837,9 @@ int32_t pass_run(dipsb_ctx* c, Pass& p) {
 int32_t pass_reduce(dipsb_ctx* c, Pass& p, int phase = 15) {
     Comm* m = c->comm;
     const Geometry& g = c->g;
-    if (m->nranks == 1) return DIPSB_OK;
+    if (m->nranks == 1) return finalize_pending(c);
     { int32_t zrc = ensure_acc_zero(c); if (zrc) return zrc; }   // (only a pass that never reached a clip kernel leaves it pending)
+    if (!use_p2p_reduce(m)) { int32_t frc = finalize_pending(c); if (frc) return frc; }
     const bool perframe = c->cfg.mode == DIPSB_MODE_PERFRAME;
     if (use_p2p_reduce(m)) {
         const int parity = (int)(m->epoch & 1);
@@ -870,6 +874,7 @@ int32_t pass_reduce(dipsb_ctx* c, Pass& p, int phase = 15) {
             else xchg_push_kernel<<<kXchgBlocks, kXchgThreads, 0, c->stream>>>(X);
             count_launch();
             CK(c, cudaGetLastError());
+            { int32_t frc = finalize_pending(c); if (frc) return frc; }   // behind the stamp, ahead of the wait for the peers
         }
         if (phase & 2) {
             xchg_reduce_kernel<<<kXchgBlocks, kXchgThreads, 0, c->stream>>>(X);

@@ -25,6 +25,7 @@ struct dipsb_ctx {
     bool state_valid = false;
     bool snapshot_pending = false;
     uint32_t* acc = nullptr;                   // u32[2*n_elems]: sum plane then count plane, internal order
+    struct { bool pending = false; uint32_t n = 0, words = 0; uint64_t first = 0; } fin;   // deferred finalize_scalars launch
     bool acc_zero_pending = false;             // dipsb_reset deferred the zeroing of `acc`: the next clip kernel does it in its
                                                // prologue, anything else that touches the planes calls ensure_acc_zero first
     uint32_t* planar = nullptr;                // u32[2*npx] scratch for get/set in pixel order
@@ -117,6 +118,9 @@ struct ShardExtra {
     // caller whether the kernel took it (it cannot on re-packed, segmented or per-frame-kernel paths)
     ShardPush push;
     bool* pushed = nullptr;
+    // leave the per-frame scalar finalisation of the call's (last) clip kernel to the caller (finalize_pending): the sharded
+    // pass tells its peers that the accumulators are on their way before it spends 8-20 us on its own scalars
+    bool defer_finalize = false;
 };
 
 // api.cu internals used by comm.cu
@@ -132,7 +136,8 @@ struct HostClipHooks {
 int32_t run_clip_host_impl(dipsb_ctx* c, const uint8_t* frames, uint64_t n, uint64_t stride, uint64_t first,
                            const HostClipHooks* hooks);
 int32_t ensure_scalars(dipsb_ctx* c, uint64_t upto);
-int32_t ensure_acc_zero(dipsb_ctx* c);      // materialise a deferred zeroing of the accumulator planes
+int32_t ensure_acc_zero(dipsb_ctx* c);
+int32_t finalize_pending(dipsb_ctx* c);     // run a deferred finalize_scalars launch (no-op when none is pending)      // materialise a deferred zeroing of the accumulator planes
 int bpp_of(int format);
 int bit_length(uint64_t v);
 // comm.cu: called by dipsb_destroy / geometry changes

@@ -73,7 +73,9 @@ enum dipsb_synth { DIPSB_SYNTH_UNIFORM = 0, DIPSB_SYNTH_SCENE = 1 };
  *                 pre_compute_shader.wgsl:212-227); dipsb_snapshot() makes the next frame store and return the grey
  *                 snapshot (dips_alt/src/lib.rs:222-225); until then the snapshot plane is zero.
  *   ALT_RING2_MEDIAN  the same with the in-bounds median (max of the two).
- * The ring flavours exist for drop-in visual parity; they are streaming-only (dipsb_run_clip_* needs FRAME0).
+ * The ring flavours exist for drop-in parity with the crates as shipped.  dipsb_run_clip_device / _host accept them too: the
+ * same state machine runs frame by frame over the device-resident clip (accumulators and scalars, no visual output) through
+ * the per-frame ring kernel -- the one-launch clip kernel implements the FRAME0 semantics only; sharded passes need FRAME0.
  */
 enum dipsb_flavor { DIPSB_FLAVOR_FRAME0 = 0, DIPSB_FLAVOR_DIPS_RING4 = 1, DIPSB_FLAVOR_ALT_RING2 = 2, DIPSB_FLAVOR_ALT_RING2_MEDIAN = 3 };
 

@@ -118,7 +118,7 @@ def test_dips_ring4_flavour_matches_reference_state_machine(oracle, filt, colori
                 assert _within(got, want, 3).all(), f"frame {t}: max diff {np.abs(got.astype(int) - want.astype(int)).max()}"
                 assert _within(got, want, 1).mean() >= 0.97
         with pytest.raises(dips_b200.DipsError):
-            ctx.run_clip_device(0, 1)                  # ring flavours are streaming-only
+            ctx.run_clip_device(0, 1)                  # a null clip is rejected (the batch call itself accepts ring flavours)
 
 
 @pytest.mark.parametrize("intended", [False, True])
@@ -361,3 +361,34 @@ def test_stage_and_dispatch_equal_push_frame(oracle):
             c.stage_frame(clip[1])                       # re-staging replaces the frame
             rc, _, st = c.dispatch_staged()
             assert rc == dips_b200.NOT_READY and st[0] == 0
+
+
+@pytest.mark.parametrize("flavor", [1, 2, 3])
+def test_batch_call_runs_the_ring_flavours(oracle, flavor):
+    """dipsb_run_clip_device / _host on a DIPS_RING4 / ALT_RING2[_MEDIAN] context: the reference-exact state machine over a
+    resident clip gives the accumulators and per-frame scalars of the same frames pushed one by one."""
+    import torch
+
+    import dips_b200
+    w, h, n, tau = 256, 144, 14, 10
+    clip = oracle.synth_clip(n, w, h, 1, profile=oracle.SYNTH_SCENE)
+    with dips_b200.Context(w, h, 1, 0, tau, flavor=flavor) as a:
+        for t in range(n):
+            a.push_frame(clip[t], want_rgba=False)
+        want_s, want_c = a.get_accumulators()
+        want_sad, want_cnt = a.get_scalars(0, n)
+    assert int(want_sad.sum()) > 0
+    dev = torch.from_numpy(clip).cuda()
+    for host in (False, True):
+        with dips_b200.Context(w, h, 1, 0, tau, flavor=flavor) as b:
+            if host:
+                b.run_clip_host(clip[:5], first_frame=0)
+                b.run_clip_host(clip[5:], first_frame=5)
+            else:
+                b.run_clip_device(dev.data_ptr(), 9, first_frame=0)
+                b.run_clip_device(dev.data_ptr() + 9 * clip.shape[1], n - 9, first_frame=9)       # the ring carries over
+            s, c = b.get_accumulators()
+            sad, cnt = b.get_scalars(0, n)
+            assert b.frames_processed == n and not b.last_plan()["tma_path"]
+        assert np.array_equal(s, want_s) and np.array_equal(c, want_c)
+        assert np.array_equal(sad, want_sad) and np.array_equal(cnt, want_cnt)
