@@ -630,6 +630,18 @@ class Bench:
                     info[name + ("_fps" if kind == "pageable" else "_pinned_fps")] = sn / (time.perf_counter() - t0)
         pin_in.close()
         pin_out.close()
+        # the same boundary without the Python binding: the C++ mirror of frame_callback / ComputeState and the raw C calls
+        exe = os.path.join(ROOT, "build", "stream_rate")
+        if os.path.exists(exe):
+            try:
+                import subprocess
+                r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=120)
+                if r.returncode == 0:
+                    info["native"] = json.loads(r.stdout.strip().splitlines()[-1])
+                    info["native"]["what"] = ("tools/native/stream_rate.cpp: mirror_frame_callback = dips::frame_callback over dips::ComputeState "
+                                              "(dips_b200/host/dips_host.hpp, add_texture + dispatch, fresh vector out per frame); the rest are the C entry points")
+            except Exception as e:      # a measurement aid must not take the bench line down
+                info["native"] = {"error": str(e)}
         return info
 
 

@@ -546,6 +546,56 @@ __global__ void spatial_median_kernel(const uint16_t* __restrict__ in, uint16_t*
     }
 }
 
+// The same median, tiled: a block of 32 x 8 threads filters a 64 x 8 pixel tile out of shared memory, every thread two
+// horizontally adjacent pixels packed in one u16x2 register.  The w*w packed taps stay in registers; each of the 9 steps of
+// the bitwise binary search counts "tap >= candidate" for both pixels with one VIADDMNMX.S16x2.RELU and one add per tap.
+// Even width only (a pair never straddles the right edge); odd widths take spatial_median_kernel.
+template <int w>
+__global__ void __launch_bounds__(256) spatial_median_tile_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t W, uint32_t H,
+                                                                  uint32_t one /* the constant 1, opaque to the compiler */) {
+    constexpr int r = w / 2, n = w * w, k = n / 2;
+    constexpr int kRows = 8 + 2 * r, kWords = 36;                 // tile columns x0-4 .. x0+67 as 36 words of two pixels
+    __shared__ uint32_t tile[kRows][kWords];
+    const uint32_t x0 = blockIdx.x * 64u, y0 = blockIdx.y * 8u;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(kRows * kWords); i += 256u) {
+        const uint32_t ry = i / kWords, j = i - ry * kWords;
+        const int y = (int)(y0 + ry) - r, x = (int)(x0 + 2u * j) - 4;      // x even: the pair is inside the frame or outside, never split
+        tile[ry][j] = (y >= 0 && y < (int)H && x >= 0 && x < (int)W) ? __ldg(reinterpret_cast<const uint32_t*>(in + (uint64_t)y * W + x)) : 0u;
+    }
+    __syncthreads();
+    const uint32_t t = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+    const uint32_t x = x0 + 2u * t, y = y0 + ty;
+    uint32_t v[n];
+#pragma unroll
+    for (int dy = 0; dy < w; ++dy) {
+        uint32_t q[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) q[i] = tile[ty + dy][t + i];
+#pragma unroll
+        for (int dx = -r; dx <= r; ++dx) {
+            // pixels (x+dx, x+1+dx) sit at tile columns 2t+4+dx, 2t+5+dx
+            const int c = 4 + dx;
+            v[dy * w + dx + r] = (c & 1) ? __funnelshift_r(q[(c - 1) / 2], q[(c + 1) / 2], 16) : q[c / 2];
+        }
+    }
+    uint32_t lo = 0u;                                             // per half: largest value with #(tap < value) <= k == sorted[k]
+#pragma unroll 1
+    for (int bit = 8; bit >= 0; --bit) {
+        const uint32_t cand = lo + (0x00010001u << bit);
+        const uint32_t one_minus_cand = __vsub2(0x00010001u, cand);
+        uint32_t ge = 0u;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {   // tap >= cand ? 1 : 0 per half (ALU pipe), summed with an IMAD (FMA pipe): the two pipes share the work
+            const uint32_t m = __viaddmin_s16x2_relu(v[i], one_minus_cand, 0x00010001u);
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(ge) : "r"(m), "r"(one));
+        }
+        // #(tap < cand) <= k  <=>  ge >= n - k
+        const uint32_t keep = __viaddmin_s16x2_relu(ge, (uint32_t)(((1 - (n - k)) & 0xFFFF) * 0x00010001u), 0x00010001u);
+        lo += keep << bit;
+    }
+    if (x < W && y < H) *reinterpret_cast<uint32_t*>(out + (uint64_t)y * W + x) = lo;
+}
+
 __global__ void median4_planes_kernel(const uint16_t* __restrict__ planes, uint64_t npx, uint16_t* __restrict__ out) {
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < npx; p += (uint64_t)gridDim.x * blockDim.x)
         out[p] = (uint16_t)upper_median4(planes[p], planes[npx + p], planes[2 * npx + p], planes[3 * npx + p]);
@@ -742,6 +792,17 @@ cudaError_t launch_frame(const Geometry& g, const FrameArgs& a, cudaStream_t s) 
     return cudaGetLastError();
 }
 cudaError_t launch_spatial_median(const Geometry& g, const uint16_t* in, uint16_t* out, int window, cudaStream_t s) {
+    if ((g.width & 1u) == 0 && (((uintptr_t)in | (uintptr_t)out) & 3u) == 0) {   // tiled, two pixels per thread
+        const dim3 grid((g.width + 63) / 64, (g.height + 7) / 8, 1);
+        switch (window) {
+            case 3: spatial_median_tile_kernel<3><<<grid, 256, 0, s>>>(in, out, g.width, g.height, 1u); break;
+            case 5: spatial_median_tile_kernel<5><<<grid, 256, 0, s>>>(in, out, g.width, g.height, 1u); break;
+            case 7: spatial_median_tile_kernel<7><<<grid, 256, 0, s>>>(in, out, g.width, g.height, 1u); break;
+            default: return cudaErrorInvalidValue;
+        }
+        count_launch();
+        return cudaGetLastError();
+    }
     switch (window) {
         case 3: spatial_median_kernel<3><<<grid_for(g.npx, g), kThreads, 0, s>>>(in, out, g.width, g.height); break;
         case 5: spatial_median_kernel<5><<<grid_for(g.npx, g), kThreads, 0, s>>>(in, out, g.width, g.height); break;

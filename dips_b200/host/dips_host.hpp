@@ -11,6 +11,8 @@
 // reference panics.
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <new>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -20,6 +22,18 @@
 #include "dips_b200.h"
 
 namespace dips {
+
+// The frame type both mirrors hand back: a std::vector of bytes whose allocator does not zero what the library is about to
+// overwrite (a value-initialising vector costs an 8 MB memset per 1080p frame -- the reference's `vec![0; n]` gets its zero
+// pages from calloc for free).
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using Frame = std::vector<uint8_t, default_init_allocator<uint8_t>>;
 
 enum class DiPsFilter { Unfiltered, Sigmoid, InverseSigmoid };   // dips/src/lib.rs:26-41
 enum class ChromaFilter { None, Red, Green, Blue };              // dips/src/lib.rs:44-61
@@ -69,10 +83,10 @@ class ComputeState {
     }
 
     // dips/src/gpu/mod.rs:306 -- empty while warming up
-    std::optional<std::vector<uint8_t>> dispatch() {
+    std::optional<Frame> dispatch() {
         if (!have_frame_ || !ctx_) return std::nullopt;
         have_frame_ = false;
-        std::vector<uint8_t> out(static_cast<size_t>(width_) * height_ * 4);
+        Frame out(static_cast<size_t>(width_) * height_ * 4);
         const int32_t rc = dipsb_dispatch_staged(ctx_, out.data(), &stats_);
         if (rc < 0) throw std::runtime_error(std::string("dipsb_dispatch_staged: ") + dipsb_last_error(ctx_));
         if (rc == DIPSB_NOT_READY) return std::nullopt;
@@ -103,10 +117,10 @@ class ComputeState {
 };
 
 // dips/src/lib.rs:233-246, verbatim shape
-inline std::vector<uint8_t> frame_callback(uint32_t width, uint32_t height, const uint8_t* frame_data, size_t len, ComputeState& compute) {
+inline Frame frame_callback(uint32_t width, uint32_t height, const uint8_t* frame_data, size_t len, ComputeState& compute) {
     compute.add_texture(width, height, frame_data, len);
-    if (auto new_frame = compute.dispatch()) return *new_frame;
-    return std::vector<uint8_t>(frame_data, frame_data + len);
+    if (auto new_frame = compute.dispatch()) return std::move(*new_frame);   // moved, as Rust moves the Vec out of the Option
+    return Frame(frame_data, frame_data + len);
 }
 
 // Page-locked frame buffer (dipsb_host_alloc): a decoder that writes here, and a caller that receives the difference frame
@@ -169,10 +183,10 @@ class DiPsCompute {
     ~DiPsCompute() { if (ctx_) dipsb_destroy(ctx_); }
 
     // dips_alt/src/dips_compute/mod.rs:498-503; snapshot == true is `Some(())`
-    std::vector<uint8_t> send_frame(const uint8_t* frame, size_t len, bool snapshot) {
+    dips::Frame send_frame(const uint8_t* frame, size_t len, bool snapshot) {
         if (len < static_cast<size_t>(width_) * height_ * 4) throw std::runtime_error("send_frame: frame smaller than width*height*4");
         if (snapshot) dipsb_snapshot(ctx_);
-        std::vector<uint8_t> out(static_cast<size_t>(width_) * height_ * 4);
+        dips::Frame out(static_cast<size_t>(width_) * height_ * 4);
         if (dipsb_push_frame(ctx_, frame, width_, height_, width_ * 4, DIPSB_FMT_RGBX8, out.data(), nullptr) < 0)
             throw std::runtime_error(std::string("dipsb_push_frame: ") + dipsb_last_error(ctx_));
         return out;
@@ -211,7 +225,7 @@ inline void run_dips_on_frames(DiPsCompute& compute, const uint8_t* frames, size
                                const std::vector<size_t>& refresh_markers, Sink&& sink) {
     SnapshotSchedule schedule(refresh_markers);
     for (size_t t = 0; t < n_frames; ++t) {
-        std::vector<uint8_t> out = compute.send_frame(frames + t * frame_len, frame_len, schedule.snapshot_now());
+        dips::Frame out = compute.send_frame(frames + t * frame_len, frame_len, schedule.snapshot_now());
         schedule.frame_sent();
         sink(t, out);
     }
