@@ -859,13 +859,15 @@ static bool host_pinned(const void* p) {
     return attr.type == cudaMemoryTypeHost;
 }
 
+static int32_t start_readback(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, uint8_t* out_rgba);
+
 // Stage one frame into `sl` and enqueue upload, kernel and read-back.  `overlap`: upload on the copy stream so that it runs
 // concurrently with the previous frame's kernel / read-back (pipelined mode); otherwise everything on the context's stream.
 // `out_direct`: page-locked caller buffer the difference frame is read back into (synchronous mode), `defer_out`: leave
 // the read-back to collect_frame.
 static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_t* px, uint32_t width, uint32_t height,
                             uint32_t stride, int32_t format, bool want_rgba, bool overlap, uint8_t* out_direct = nullptr,
-                            bool defer_out = false) {
+                            bool defer_out = false, dipsb_ctx::FrameSlot* prev = nullptr, uint8_t* prev_out = nullptr) {
     const Geometry& g = c->g;
     if (width != g.width || height != g.height) return fail(c, DIPSB_ERR_INVALID, "push_frame: %ux%u does not match the context's %ux%u", width, height, g.width, g.height);
     if (format < 0 || format > 3) return fail(c, DIPSB_ERR_INVALID, "push_frame: bad format %d", format);
@@ -878,6 +880,19 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
                     (unsigned long long)c->frames_processed);
     int32_t rc = ensure_slot(c, sl, fb);
     if (rc) return rc;
+    // Pipelined call with a page-locked frame: the two big transfers of the call go out before anything else -- this frame's
+    // upload on the copy stream, then the previous frame's read-back on the context's stream (ahead of this frame's kernel) --
+    // so that the ~40 us of bookkeeping below run under them instead of in front of them.
+    bool uploaded = false;
+    if (overlap && px && stride == row && host_pinned(px)) {
+        CK(c, cudaMemcpyAsync(sl.d_in, px, fb, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(c, cudaEventRecord(sl.ev_in[0], c->copy_stream));
+        uploaded = true;
+    }
+    if (prev) {
+        rc = start_readback(c, *prev, prev_out);
+        if (rc) return rc;
+    }
     rc = ensure_scalars(c, c->stream_index + 1);
     if (rc) return rc;
     if ((rc = ensure_acc_zero(c))) return rc;
@@ -891,7 +906,7 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     // page-locked, uploaded straight from the caller's buffer and the upload awaited before this call returns.
     // px == nullptr: the frame was staged and its upload started by dipsb_stage_frame (slot 0); only kernels and read-back follow
     const bool pre_staged = px == nullptr;
-    const bool in_direct = !pre_staged && stride == row && host_pinned(px);
+    const bool in_direct = uploaded || (!pre_staged && stride == row && host_pinned(px));
     // The synchronous call works in row bands: upload of band k+1 (copy stream), kernels of band k (the context's stream)
     // and read-back of band k-1 (read-back stream) run concurrently, and so do the CPU staging copies on either side.  In
     // the pipelined call the neighbouring frames already overlap and the extra launches only cost; a spatial window
@@ -948,6 +963,8 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
         // upload
         if (pre_staged) {
             CK(c, cudaStreamWaitEvent(c->stream, sl.ev_in[k], 0));   // recorded by dipsb_stage_frame behind the upload of band k
+        } else if (uploaded) {
+            CK(c, cudaStreamWaitEvent(c->stream, sl.ev_in[0], 0));
         } else {
             const uint8_t* src = px + (uint64_t)r0 * stride;
             if (!in_direct) {
@@ -1093,10 +1110,9 @@ extern "C" int32_t dipsb_push_frame_pipelined(dipsb_ctx* c, const uint8_t* px, u
     // output planes are requested for every frame in this mode (the caller decides at collection time); a caller that
     // hands in page-locked output buffers gets the read-back issued at collection, straight into its buffer
     if (out_rgba_prev) c->out_pinned_hint = host_pinned(out_rgba_prev);
-    // the previous frame's read-back goes first so that it overlaps this frame's upload (separate copy engines)
-    int32_t rc = start_readback(c, prev, out_rgba_prev);
-    if (rc) return rc;
-    rc = submit_frame(c, cur, px, width, height, stride, format, true, true, nullptr, c->out_pinned_hint);
+    // the previous frame's read-back and this frame's upload run side by side (separate copy engines); submit_frame issues both
+    // before it does anything else
+    int32_t rc = submit_frame(c, cur, px, width, height, stride, format, true, true, nullptr, c->out_pinned_hint, &prev, out_rgba_prev);
     if (rc) return rc;
     c->next_slot ^= 1;
     if (!prev.pending) return DIPSB_NOT_READY;          // first call: nothing to hand back yet

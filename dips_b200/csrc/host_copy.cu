@@ -60,6 +60,11 @@ class CopyPool {
 
     void copy(const CopyJob& job) {
         std::lock_guard<std::mutex> one_caller(callers_);
+        // The helpers only stay hot between copies while copies keep coming at a per-frame pace: a gap of more than a few
+        // spin windows since the previous copy means no streaming caller is active, and they go to sleep at once.
+        const auto now = std::chrono::steady_clock::now();
+        hot_.store(spin_us_ > 0 && now - last_copy_ < std::chrono::microseconds(8 * spin_us_), std::memory_order_relaxed);
+        last_copy_ = now;
         std::unique_lock<std::mutex> lk(m_);
         job_ = job; next_ = 0; done_ = 0;
         epoch_.fetch_add(1, std::memory_order_release);
@@ -81,7 +86,7 @@ class CopyPool {
     void run() {
         std::unique_lock<std::mutex> lk(m_);
         for (;;) {
-            if (!stop_ && next_ >= job_.parts && spin_us_ > 0) {
+            if (!stop_ && next_ >= job_.parts && spin_us_ > 0 && hot_.load(std::memory_order_relaxed)) {
                 // Stay hot for a moment: a per-frame caller comes back within a few hundred microseconds (upload, kernel,
                 // read-back), and a helper that went to sleep in between wakes too late to be of any use.
                 const uint64_t seen = epoch_.load(std::memory_order_relaxed);
@@ -113,6 +118,8 @@ class CopyPool {
     }
 
     const long spin_us_;
+    std::atomic<bool> hot_{false};
+    std::chrono::steady_clock::time_point last_copy_{};
     std::atomic<uint64_t> epoch_{0};
     std::mutex m_, callers_;
     std::condition_variable cv_, cv_done_;

@@ -318,9 +318,10 @@ int32_t dipsb_host_free(void *p);
 /*
  * The staging copy the frame calls use for ordinary host memory: rows of row_bytes from src (pitch spitch) to dst (pitch
  * dpitch) on a small persistent thread pool -- the caller plus DIPSB_COPY_THREADS-1 helpers (environment variable, default
- * min(4, cores/2); 1 = the calling thread only); copies under 1 MB stay on the caller.  After a copy the helpers poll for
- * DIPSB_COPY_SPIN_US microseconds (default 500, 0 = sleep at once) before they block, so that a per-frame caller finds them
- * awake.  Host only, no device involved.
+ * min(4, cores/2); 1 = the calling thread only); copies under 1 MB stay on the caller.  While copies follow each other at a
+ * per-frame pace (less than 8 x DIPSB_COPY_SPIN_US apart) the helpers poll for DIPSB_COPY_SPIN_US microseconds (default 500,
+ * 0 = never) after a copy before they block, so that a per-frame caller finds them awake; an isolated copy leaves them
+ * asleep.  Host only, no device involved.
  */
 int32_t dipsb_host_copy2d(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t row_bytes, uint64_t rows);
 uint32_t dipsb_host_copy_threads(void);

@@ -40,5 +40,23 @@ def main():
                   f"reset {t_reset:6.1f} us   reset+4-frame pass {t_run4:7.1f} us")
 
 
+def ring_rate():
+    """per-frame kernels back to back over a device-resident 1080p clip (batch call of the ring flavours): the u16 / u32 planes
+    stay in L2 between frames, unlike in an ncu launch list"""
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    w, h, fmt, n = 1920, 1080, 1, 200
+    fb = w * h * 4
+    clip = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
+    dips_b200.synth_fill_device(0, clip.data_ptr(), 0, n, w, h, fmt, stream=stream.cuda_stream)
+    for name, flavor, window in (("dips ring-of-4", dips_b200.FLAVOR_DIPS_RING4, 1), ("dips_alt ring-of-2", dips_b200.FLAVOR_ALT_RING2, 1),
+                                 ("frame0, 3x3 median", dips_b200.FLAVOR_FRAME0, 3), ("frame0, 7x7 median", dips_b200.FLAVOR_FRAME0, 7)):
+        with dips_b200.Context(w, h, fmt, 0, 32, flavor=flavor, spatial_window=window) as ctx:
+            ctx.set_stream(stream.cuda_stream)
+            t = timed(stream, lambda: (ctx.reset(), ctx.run_clip_device(clip.data_ptr(), n, fb, 0)), reps=3)
+            print(f"1080p RGBx8 batch, {name:20s}: {t / n:6.1f} us per frame ({n * 1e6 / t:8.0f} frames/s device-side)")
+
+
 if __name__ == "__main__":
+    ring_rate()
     main()
