@@ -1007,6 +1007,7 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
     CK(c, cudaMemcpyAsync(&sl.h_stat[0], c->d_sad + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, tail));
     CK(c, cudaMemcpyAsync(&sl.h_stat[1], c->d_cnt + idx, sizeof(uint64_t), cudaMemcpyDeviceToHost, tail));
     CK(c, cudaEventRecord(sl.ev_done, tail));
+    if (sl.out_deferred) CK(c, cudaEventRecord(sl.ev_k[0], c->stream));   // kernels and scalars of this frame done: its read-back may start
     sl.pending = true; sl.want_rgba = want_rgba; sl.idx = idx; sl.status = establishes ? DIPSB_NOT_READY : DIPSB_OK;
     c->stream_index = idx + 1;
     c->frames_processed += 1;
@@ -1019,8 +1020,11 @@ static int32_t submit_frame(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, const uint8_
 static int32_t start_readback(dipsb_ctx* c, dipsb_ctx::FrameSlot& sl, uint8_t* out_rgba) {
     if (!sl.pending || !sl.out_deferred || !out_rgba) return DIPSB_OK;
     const bool direct = host_pinned(out_rgba);
-    CK(c, cudaMemcpyAsync(direct ? out_rgba : sl.h_out, sl.d_out, c->g.npx * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaEventRecord(sl.ev_done, c->stream));
+    // on the read-back stream, behind the frame's own kernels only: on the context's stream the 8 MB copy would sit between
+    // the kernels of consecutive frames and make (read-back + kernels + scalar copies) the per-frame critical chain
+    CK(c, cudaStreamWaitEvent(c->out_stream, sl.ev_k[0], 0));
+    CK(c, cudaMemcpyAsync(direct ? out_rgba : sl.h_out, sl.d_out, c->g.npx * 4, cudaMemcpyDeviceToHost, c->out_stream));
+    CK(c, cudaEventRecord(sl.ev_done, c->out_stream));
     sl.out_deferred = false;
     sl.out_direct = direct;
     return DIPSB_OK;

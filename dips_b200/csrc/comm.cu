@@ -2,21 +2,23 @@
 //
 // The reference is single-adapter (dips/src/gpu/mod.rs:71-78 picks one wgpu adapter); the north star shards a long clip by
 // frame range over the 8 GPUs of one box.  Rank r of R owns frames [r*N/R, (r+1)*N/R) (dipsb_shard_range).  Per clip:
-//   * overall mode:   rank 0 builds the u16 reference plane from frame 0 and ncclBroadcast's it (2 B/px, less than the raw
-//                     frame) -- the only exchange before the pass;
+//   * overall mode:   rank 0 builds the u16 reference plane from frame 0 (2 B/px, less than the raw frame) and it travels as
+//                     scatter + all-gather over peer memory: rank 0's prime kernel stores slice k straight into rank k+1,
+//                     the other ranks forward their slices to each other -- the only exchange before the pass;
 //   * per-frame mode: NO exchange before the pass.  Every rank starts at once, primed from its own first frame (whose
 //                     difference is therefore missing); meanwhile its copy engine pushes that first frame over NVLink
 //                     into the previous rank's window, and the previous rank's clip kernel differences it as one extra
 //                     trailing frame (its producer warp waits for the arrival stamp right before the last TMA fetch).
 //                     The one-frame halo thus never sits on the critical path; the boundary frame's scalars travel back
 //                     with the accumulator exchange;
-//   * at the end:     the accumulators are combined by ONE kernel over peer memory (xchg_kernel): every rank packs its
-//                     partial sums (sum | count << bits in one u32 while a shard's totals fit, else two u32) and stores
-//                     them straight into the owner's window over NVLink (P2P stores, 512 B per warp), signals, waits for
-//                     its peers' signals and adds up the pixel range it owns -- a reduce-scatter; the totals stay sharded
-//                     by pixel range until somebody reads them (dipsb_gather_accumulators: the same pattern as an
-//                     all-gather).  Integer sums: bit-exact, order independent.
-// Fallback and comparison path: pack -> ncclAllReduce -> unpack (DIPSB_REDUCE_NCCL), and ncclSend/ncclRecv for the halo,
+//   * at the end:     the accumulators are combined by a reduce-scatter over peer memory: the clip kernel's last flush packs
+//                     the elements this rank does not own (sum | count << bits in one u32 while a shard's totals fit, else
+//                     two u32) and stores them straight into the owner's window over NVLink (xchg_push_kernel does the same
+//                     as a separate launch when the clip kernel cannot), one block stamps the peers, and xchg_reduce_kernel
+//                     waits for the peers' stamps and adds up the pixel range this rank owns; the totals stay sharded by pixel
+//                     range until somebody reads them (dipsb_gather_accumulators: the same pattern as an all-gather).
+//                     Integer sums: bit-exact, order independent.
+// Fallback and comparison path (DIPSB_REDUCE_NCCL): ncclBroadcast of the plane, pack -> ncclAllReduce -> unpack, and ncclSend/ncclRecv for the halo,
 // when peer memory cannot be mapped (cudaIpc* refused, no P2P) or on request.
 //
 // Two process models share all of this:
