@@ -61,6 +61,8 @@ def parse_args():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-stream", action="store_true")
     p.add_argument("--no-preflight", action="store_true")
+    p.add_argument("--no-numa-bind", action="store_true", help="N>1: leave the ranks' threads and host buffers wherever the scheduler puts them")
+    p.add_argument("--only-e2e", action="store_true", help="skip the device-resident measurement; print the e2e object alone (for host-side experiments)")
     p.add_argument("--no-comm-probes", dest="comm_probes", action="store_false")
     p.add_argument("--reduce", choices=["auto", "p2p", "nccl"], default="auto",
                    help="accumulator exchange: the library's peer-memory kernels or pack + ncclAllReduce + unpack")
@@ -253,6 +255,31 @@ def log(rank, *a):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+def bind_near_gpu(torch, local_rank: int):
+    """Multi-GPU runs only: keep this rank's threads (and so the page-locked host buffers they allocate and the library's
+    host-copy helpers they spawn) on the CPU socket the GPU hangs off.  Without it the ranks' host buffers land on whatever
+    node the scheduler picked and half of the 8 uploads cross the socket link.  Returns what was done, for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": None, "why": "the platform reports no NUMA node for the GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "why": "none of the node's CPUs are available to this process"}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus), "gpu": bdf}
+    except (OSError, ValueError, AttributeError) as e:
+        return {"node": None, "why": f"{type(e).__name__}: {e}"}
+
+
 class Bench:
     """One process = one GPU = one rank.  Holds the device buffer the synthetic shards are generated into."""
 
@@ -265,6 +292,7 @@ class Bench:
         self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
         torch.cuda.set_device(local_rank)
         self.dev = torch.device("cuda", local_rank)
+        self.host_numa = bind_near_gpu(torch, local_rank) if world > 1 and not args.no_numa_bind else None
         if world > 1:
             import datetime
             # gloo only carries the NCCL unique id, barriers and max-over-ranks of the timings; every collective of the data
@@ -302,6 +330,13 @@ class Bench:
         outs = [None] * self.world
         self.dist.all_gather_object(outs, x)
         return [float(v) for v in outs]
+
+    def gather_objects(self, x):
+        if self.world == 1:
+            return [x]
+        outs = [None] * self.world
+        self.dist.all_gather_object(outs, x)
+        return outs
 
     def unique_id(self) -> bytes:
         box = [self.lib.comm_unique_id() if self.rank == 0 else None]
@@ -568,8 +603,11 @@ class Bench:
                       " (pinned host clip, chunked H2D overlapped with the clip kernel) + dipsb_get_accumulators + dipsb_get_scalars",
                "h2d_GBps_per_gpu": frames * fb * self.args.e2e_steps / dt / 1e9,
                "h2d_GBps_aggregate": frames * fb * self.world * self.args.e2e_steps / dt / 1e9,
-               "limit": "host side: PCIe Gen5 x16 per GPU (~55 GB/s measured at N<=2); the aggregate over 4-8 GPUs is bounded by the host's "
-                        "root complexes / memory, not by the GPUs (SCALE_r01: 115 GB/s at N=4, 186 GB/s at N=8)"}
+               "limit": "host side: PCIe Gen5 x16 per GPU (54 GB/s measured alone, tools/native/pcie_probe.cu; 52 GB/s per GPU at N=4); "
+                        "the aggregate stops at 185-210 GB/s on this pool's hosts (single-node 32-vCPU VMs: 210 GB/s at N=4, 184 GB/s at N=8, "
+                        "no NUMA placement to choose), which is the host's memory / root complexes, not the GPUs"}
+        if self.host_numa is not None:
+            res["host_numa"] = self.gather_objects(self.host_numa)
         if self.world == 1:
             import numpy as np
             # the same call from ORDINARY host memory (what a caller without page-locked buffers has): every chunk is first
@@ -670,6 +708,13 @@ def main():
         log(rank, "preflight parity ok", json.dumps(parity["cases"]))
 
     # ---- headline workload ----------------------------------------------------------------------------------------
+    if args.only_e2e:
+        head, ctx, clip = B.measure(args.workload, wl, 3, 3, keep=True)
+        e2e = B.e2e(wl, ctx)
+        ctx.close()
+        if rank == 0:
+            out.write(json.dumps({"only_e2e": True, "n_gpus": world, "workload": args.workload, "e2e": e2e}) + "\n")
+        return 0
     head, ctx, clip = B.measure(args.workload, wl, args.steps, args.warmup, with_probe=True, keep=True)
     log(rank, f"{args.workload}: {head['value']:.0f} frames/s, {head['ms_per_step']:.3f} ms/step, kernel {head['roofline']['achieved']:.0f} GB/s "
               f"({time.perf_counter() - t_start:.0f} s)")
