@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libdips_b200.so")
-SOURCES = ["clip_kernel.cu", "aux_kernels.cu", "api.cu", "comm.cu", "host_copy.cu"]
+SOURCES = ["clip_kernel.cu", "aux_kernels.cu", "ring_clip.cu", "api.cu", "comm.cu", "host_copy.cu"]
 HEADERS = [os.path.join(CSRC, "dipsb_internal.h"), os.path.join(CSRC, "dipsb_ctx.h"), os.path.join(CSRC, "intensity.cuh"), os.path.join(ROOT, "include", "dips_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

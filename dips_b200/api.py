@@ -255,7 +255,7 @@ class Context:
         out = (C.c_uint32 * 8)()
         self._ck(self._lib.dipsb_last_plan(self._h, C.byref(out)))
         return dict(tiles=out[0], segments=out[1], threads=out[2], stages=out[3] & 0xFFFF, kernel=out[3] >> 16, blocks_per_sm=out[4],
-                    tile_px=out[5], smem_bytes=out[6] & 0xFFFFFF, regs=out[6] >> 24, tma_path=bool(out[7]))
+                    tile_px=out[5], smem_bytes=out[6] & 0xFFFFFF, regs=out[6] >> 24, tma_path=out[7] == 1, ring_clip=out[7] == 2)
 
     # -- state plane ------------------------------------------------------------------------------------------
     def prime_device(self, d_frame: int) -> None:

@@ -559,12 +559,43 @@ static int32_t run_extra_frame(dipsb_ctx* c, const ShardExtra& x, uint64_t index
     return run_clip_on_stream(c, x.frame, 1, (c->g.npx * c->g.bpp + 15) & ~15ull, index, true, nullptr);
 }
 
-// `zero_padded`: the rows come from the library's own re-packed buffers -- pitch a multiple of 16 and zero bytes between the
-// end of a frame and its pitch -- so the clip kernel may round its last bulk copy of a frame up to 16 bytes.
-// Batch execution of the reference-exact flavours (DIPS_RING4 / ALT_RING2[_MEDIAN]) over a device-resident clip: the ring
-// state machine of dipsb_push_frame, frame by frame, through ring4_kernel (accumulators and per-frame scalars; no visual
-// output, no host copies).  The clip kernel implements the north-star semantics only: the median-of-4 ring needs 32 more
-// registers of state per thread than it has.
+// Batch execution of the reference-exact flavours (DIPS_RING4 / ALT_RING2[_MEDIAN]) over a device-resident clip
+// (accumulators and per-frame scalars; no visual output, no host copies).  The frames that change what the ring machine
+// does -- the `dips` warm-up and start-plane frame, a frame that takes a snapshot -- go through the per-frame ring kernel,
+// exactly as dipsb_push_frame runs them; the steady state after them is one launch of ring_clip_kernel per run of frames
+// (ring in registers, every frame byte read once).  Spatial windows and layouts without aligned 8-pixel units stay per frame.
+static int32_t grow_partials(dipsb_ctx* c, uint64_t need) {
+    if (need <= c->partial_cap) return DIPSB_OK;
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->partials); c->partials = nullptr; c->partial_cap = 0;
+    CK(c, cudaMalloc(&c->partials, need * sizeof(uint32_t)));
+    c->partial_cap = need;
+    return DIPSB_OK;
+}
+static int32_t run_ring_steady(dipsb_ctx* c, const uint8_t* d_frames, uint64_t m, uint64_t stride, uint64_t first, uint32_t seg_frames) {
+    const Geometry& g = c->g;
+    const int ns = c->cfg.flavor == DIPSB_FLAVOR_DIPS_RING4 ? 4 : 2;
+    const uint32_t words = ring_clip_words_per_frame(g), pitch = (words + 3u) & ~3u;
+    // scalar scratch rows of one launch: at most 64 M words, a whole number of ring turns
+    const uint64_t max_rows = std::max<uint64_t>(8 * ns, ((64ull << 20) / pitch) / ns * ns);
+    for (uint64_t done = 0; done < m;) {
+        const uint64_t cnt = std::min(m - done, max_rows);
+        int32_t rc = grow_partials(c, cnt * pitch);
+        if (rc) return rc;
+        RingClipArgs a;
+        a.frames = d_frames + done * stride; a.stride = stride; a.n_frames = (uint32_t)cnt;
+        a.ring = c->ring; a.n_slots = ns; a.first_slot = (int)c->ring_index;
+        a.median_is_max = c->cfg.flavor == DIPSB_FLAVOR_ALT_RING2_MEDIAN;
+        a.start = c->state[c->state_cur];
+        a.acc_sum = c->acc; a.acc_cnt = c->acc + g.n_elems; a.partials = c->partials;
+        a.tau = c->cfg.threshold; a.seg_frames = seg_frames;
+        CK(c, launch_ring_clip(g, a, c->stream));
+        CK(c, launch_finalize_scalars(g, c->partials, (uint32_t)cnt, words, c->d_sad + first + done, c->d_cnt + first + done, c->stream));
+        c->ring_index = (uint32_t)((c->ring_index + cnt) % ns);
+        done += cnt;
+    }
+    return DIPSB_OK;
+}
 static int32_t run_clip_ring(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first) {
     const Geometry& g = c->g;
     if (c->frames_processed + n > DIPSB_MAX_ACCUMULATED_FRAMES) return fail(c, DIPSB_ERR_STATE, "run_clip: the u32 sums would overflow; read the results and dipsb_reset");
@@ -572,9 +603,16 @@ static int32_t run_clip_ring(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, 
     int32_t rc = ensure_scalars(c, first + n);
     if (rc) return rc;
     if ((rc = ensure_acc_zero(c))) return rc;
-    CK(c, cudaMemsetAsync(c->d_sad + first, 0, n * sizeof(uint64_t), c->stream));
-    CK(c, cudaMemsetAsync(c->d_cnt + first, 0, n * sizeof(uint64_t), c->stream));
-    for (uint64_t k = 0; k < n; ++k) {
+    // measurement / test hooks: DIPSB_RING_BATCH=0 keeps every frame on the per-frame kernel; DIPSB_RING_SEG_FRAMES forces
+    // the frame-segment length of ring_clip_kernel (small clips would otherwise run as one segment)
+    const char* env_batch = getenv("DIPSB_RING_BATCH");
+    const char* env_seg = getenv("DIPSB_RING_SEG_FRAMES");
+    const bool batchable = !windowed(c) && !(env_batch && env_batch[0] == '0') && ring_clip_available(g, d_frames, stride);
+    const uint64_t min_run = c->cfg.flavor == DIPSB_FLAVOR_DIPS_RING4 ? 8 : 4;
+    uint64_t k = 0;
+    for (; k < n; ++k) {
+        const bool steady = !c->snapshot_pending && (c->cfg.flavor != DIPSB_FLAVOR_DIPS_RING4 || c->ring_seen >= 4);
+        if (batchable && steady && n - k >= min_run) break;
         RingArgs r;
         r.frame = d_frames + k * stride; r.pitch = (uint64_t)g.width * g.bpp; r.format = g.format; r.chan_byte = g.chan_byte;
         if (windowed(c)) {
@@ -587,16 +625,24 @@ static int32_t run_clip_ring(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, 
         r.out_rgba = nullptr;
         r.tau = c->cfg.threshold; r.colorize = c->cfg.colorize; r.filter = c->cfg.filter; r.sig_scalar = c->cfg.sigmoid_scalar;
         ring_next_frame(c, r);
+        CK(c, cudaMemsetAsync(r.sad, 0, sizeof(uint64_t), c->stream));
+        CK(c, cudaMemsetAsync(r.cnt, 0, sizeof(uint64_t), c->stream));
         CK(c, launch_ring(g, r, c->stream));
+    }
+    if (k < n) {
+        if (c->cfg.flavor == DIPSB_FLAVOR_DIPS_RING4) c->ring_seen = 5;
+        if ((rc = run_ring_steady(c, d_frames + k * stride, n - k, stride, first + k, env_seg ? (uint32_t)strtoul(env_seg, nullptr, 10) : 0u))) return rc;
     }
     c->state_valid = true;
     c->frames_processed += n;
     c->scal_hi = std::max(c->scal_hi, first + n);
     c->stream_index = first + n;
-    c->last_plan[1] = 0; c->last_plan[7] = 0;
+    c->last_plan[1] = 0; c->last_plan[7] = k < n ? 2 : 0;
     return DIPSB_OK;
 }
 
+// `zero_padded`: the rows come from the library's own re-packed buffers -- pitch a multiple of 16 and zero bytes between the
+// end of a frame and its pitch -- so the clip kernel may round its last bulk copy of a frame up to 16 bytes.
 int32_t dipsb::run_clip_on_stream(dipsb_ctx* c, const uint8_t* d_frames, uint64_t n, uint64_t stride, uint64_t first,
                                   bool zero_padded, const ShardExtra* extra) {
     const Geometry& g = c->g;

@@ -155,6 +155,23 @@ struct RingArgs {
     uint64_t p_begin = 0, p_end = 0;   // see FrameArgs
 };
 cudaError_t launch_ring(const Geometry& g, const RingArgs& a, cudaStream_t s);
+// ring_clip.cu: the steady state of a reference-flavour ring over a run of frames in one launch (ring in registers)
+struct RingClipArgs {
+    const uint8_t* frames; uint64_t stride; uint32_t n_frames;
+    uint16_t* ring;              // n_slots planes of npx u16: loaded by the first frame segment, stored back by the last
+    int n_slots;                 // 4 (dips: slots hold grey-quantised I2) or 2 (dips_alt: raw I2)
+    int first_slot;              // slot the first frame overwrites; frame j overwrites (first_slot + j) % n_slots
+    int median_is_max;           // dips_alt only, see RingArgs
+    const uint16_t* start;       // start / snapshot plane, constant over the run
+    uint32_t* acc_sum; uint32_t* acc_cnt;
+    uint32_t* partials;          // u32[n_frames][pitch4(ring_clip_words_per_frame)]: sad | cnt<<20 per warp per frame
+    uint32_t tau;
+    uint32_t seg_frames = 0;     // frames per segment (0: planned from the occupancy); test hook
+};
+// 8-pixel units, aligned vector loads, 32-bit accumulator indices
+bool ring_clip_available(const Geometry& g, const uint8_t* frames, uint64_t stride);
+uint32_t ring_clip_words_per_frame(const Geometry& g);
+cudaError_t launch_ring_clip(const Geometry& g, const RingClipArgs& a, cudaStream_t s);
 // N4: correct spatial median (window 3/5/7, zero padded) of a u16 intensity plane; upper median of 4 planes
 cudaError_t launch_spatial_median(const Geometry& g, const uint16_t* in, uint16_t* out, int window, cudaStream_t s);
 cudaError_t launch_median4_planes(const Geometry& g, const uint16_t* planes, uint16_t* out, cudaStream_t s);

@@ -73,9 +73,10 @@ enum dipsb_synth { DIPSB_SYNTH_UNIFORM = 0, DIPSB_SYNTH_SCENE = 1 };
  *                 pre_compute_shader.wgsl:212-227); dipsb_snapshot() makes the next frame store and return the grey
  *                 snapshot (dips_alt/src/lib.rs:222-225); until then the snapshot plane is zero.
  *   ALT_RING2_MEDIAN  the same with the in-bounds median (max of the two).
- * The ring flavours exist for drop-in parity with the crates as shipped.  dipsb_run_clip_device / _host accept them too: the
- * same state machine runs frame by frame over the device-resident clip (accumulators and scalars, no visual output) through
- * the per-frame ring kernel -- the one-launch clip kernel implements the FRAME0 semantics only; sharded passes need FRAME0.
+ * The ring flavours exist for drop-in parity with the crates as shipped.  dipsb_run_clip_device / _host accept them too
+ * (accumulators and scalars, no visual output): the warm-up / start-plane / snapshot frames run frame by frame exactly as
+ * dipsb_push_frame runs them, the steady state after them in one launch per run of frames with the ring held in registers
+ * (ring_clip_kernel).  Per-frame calls and batch calls may be mixed on one context.  Sharded passes need FRAME0.
  */
 enum dipsb_flavor { DIPSB_FLAVOR_FRAME0 = 0, DIPSB_FLAVOR_DIPS_RING4 = 1, DIPSB_FLAVOR_ALT_RING2 = 2, DIPSB_FLAVOR_ALT_RING2_MEDIAN = 3 };
 
@@ -328,7 +329,8 @@ uint32_t dipsb_host_copy_threads(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t dipsb_launch_count(void);
 /* last clip kernel geometry, for reports: [0] tiles, [1] frame segments, [2] threads per block, [3] stages | kernel << 16, [4] blocks per
- * SM, [5] pixels per tile, [6] dynamic shared memory bytes | registers << 24, [7] 1 = TMA clip kernel / 0 = fallback */
+ * SM, [5] pixels per tile, [6] dynamic shared memory bytes | registers << 24, [7] 1 = TMA clip kernel / 2 = ring clip kernel
+ * (reference-flavour rings in registers) / 0 = per-frame kernels */
 int32_t dipsb_last_plan(const dipsb_ctx *ctx, uint32_t out[8]);
 /* optional device-side timing of the clip kernel alone (cudaEvent pairs on the context's stream around each launch).
  * dipsb_clip_kernel_time synchronises, returns the summed milliseconds and launch count since the last call, and resets. */

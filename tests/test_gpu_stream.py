@@ -392,3 +392,124 @@ def test_batch_call_runs_the_ring_flavours(oracle, flavor):
             assert b.frames_processed == n and not b.last_plan()["tma_path"]
         assert np.array_equal(s, want_s) and np.array_equal(c, want_c)
         assert np.array_equal(sad, want_sad) and np.array_equal(cnt, want_cnt)
+
+
+def _ring_twin(i2, flavor, tau, snapshot_before=()):
+    """Integer restatement of the ring machines of dipsb_push_frame on I2 planes (frames x pixels, int64): per-pixel sums and
+    counts, per-frame sad / cnt.  `dips` (flavor 1): 3 pass-through frames, start = grey(upper median of the first 4), ring
+    slots quantised to grey as they are overwritten (dips/src/gpu/mod.rs:170-216, bind_groups.rs:407-427,
+    dips_shader.wgsl:187-214).  `dips_alt` (2 / 3): ring of 2, min / max of the two, snapshot = grey(median) on request,
+    the snapshot frame contributes nothing (pre_compute_shader.wgsl:212-262)."""
+    n, npx = i2.shape
+    grey = lambda v: 2 * ((v + 1) >> 1)
+    s, c = np.zeros(npx, np.int64), np.zeros(npx, np.int64)
+    sad, cnt = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    if flavor == 1:
+        ring, start, idx, seen = np.zeros((4, npx), np.int64), None, 0, 0
+        for t in range(n):
+            if t in snapshot_before:
+                seen, idx = 0, 0
+            seen += 1
+            if seen < 4:
+                ring[seen - 1] = i2[t]
+                continue
+            if seen == 4:
+                ring[3] = i2[t]
+                start = grey(np.sort(ring, axis=0)[2])
+                ring[0] = grey(ring[0])
+            else:
+                ring[idx] = grey(i2[t])
+                idx = (idx + 1) % 4
+            d = np.abs(start - np.sort(ring, axis=0)[2])
+            s += d; c += d > tau; sad[t] = d.sum(); cnt[t] = (d > tau).sum()
+    else:
+        ring, snap, idx = np.zeros((2, npx), np.int64), np.zeros(npx, np.int64), 0
+        for t in range(n):
+            ring[idx] = i2[t]
+            idx ^= 1
+            med = ring.max(axis=0) if flavor == 3 else ring.min(axis=0)
+            if t in snapshot_before:
+                snap = grey(med)
+                continue
+            d = np.abs(snap - med)
+            s += d; c += d > tau; sad[t] = d.sum(); cnt[t] = (d > tau).sum()
+    return s, c, sad, cnt
+
+
+@pytest.mark.parametrize("flavor", [1, 2, 3])
+@pytest.mark.parametrize("fmt,chroma", [(0, 0), (1, 0), (1, 2), (2, 3), (3, 1), (0, 1)])
+def test_ring_clip_kernel_matches_integer_twin(oracle, monkeypatch, flavor, fmt, chroma):
+    """The one-launch ring kernel (ring_clip_kernel: ring slots in registers, frame segments that rebuild the ring from the
+    frames before them, packed accumulators flushed every 128 frames) against an independent numpy restatement and against
+    the per-frame kernel, over a clip long enough for three flushes, with snapshots between batch calls and with forced
+    short segments (ragged last one)."""
+    import torch
+
+    import dips_b200
+    w, h, n, tau = 200, 72, 301, 24
+    clip = oracle.synth_clip(n, w, h, fmt, profile=oracle.SYNTH_SCENE)
+    i2 = np.stack([oracle.i2_plane(clip[t], fmt, chroma) for t in range(n)]).astype(np.int64)
+    cuts = [0, 150, n]                                                    # two batch calls; a snapshot before the second
+    snaps = (2, 150) if flavor != 1 else (150,)
+    want = _ring_twin(i2, flavor, tau, snapshot_before=snaps)
+    assert int(want[2].sum()) > 0 and int(want[3].sum()) > 0
+    dev = torch.from_numpy(clip).cuda()
+    fb = clip.shape[1]
+
+    def run(ctx):
+        if flavor != 1:                                                   # dips_alt: frames 0, 1 and the snapshot frame 2 one by one
+            for t in range(3):
+                if t == 2:
+                    ctx.snapshot()
+                ctx.push_frame(clip[t], want_rgba=False)
+            ctx.run_clip_device(dev.data_ptr() + 3 * fb, cuts[1] - 3, first_frame=3)
+        else:
+            ctx.run_clip_device(dev.data_ptr(), cuts[1], first_frame=0)
+        ctx.snapshot()
+        ctx.run_clip_device(dev.data_ptr() + cuts[1] * fb, n - cuts[1], first_frame=cuts[1])
+        return ctx.get_accumulators() + ctx.get_scalars(0, n), ctx.last_plan()
+
+    for seg in (None, "36"):
+        if seg:
+            monkeypatch.setenv("DIPSB_RING_SEG_FRAMES", seg)
+        with dips_b200.Context(w, h, fmt, 0, tau, chroma=chroma, flavor=flavor) as ctx:
+            got, plan = run(ctx)
+        assert plan["ring_clip"] and not plan["tma_path"]
+        for g_, w_, name in zip(got, want, ("sum", "count", "sad", "cnt")):
+            assert np.array_equal(np.asarray(g_, dtype=np.int64).ravel(), w_), (name, seg)
+    monkeypatch.delenv("DIPSB_RING_SEG_FRAMES")
+    monkeypatch.setenv("DIPSB_RING_BATCH", "0")                           # the same calls through the per-frame kernel
+    with dips_b200.Context(w, h, fmt, 0, tau, chroma=chroma, flavor=flavor) as ctx:
+        got, plan = run(ctx)
+    assert not plan["ring_clip"]
+    for g_, w_, name in zip(got, want, ("sum", "count", "sad", "cnt")):
+        assert np.array_equal(np.asarray(g_, dtype=np.int64).ravel(), w_), (name, "per-frame")
+
+
+def test_ring_clip_kernel_mixes_with_per_frame_calls_and_odd_layouts(oracle):
+    """Per-frame calls after a batch call see the ring the batch left (stored back by the last segment); a geometry whose
+    pixel count is not a multiple of 8 and an unaligned clip base stay on the per-frame kernel and agree."""
+    import torch
+
+    import dips_b200
+    tau = 16
+    for (w, h, off) in ((128, 96, 0), (99, 51, 0), (128, 96, 4)):
+        n = 41
+        clip = oracle.synth_clip(n, w, h, 1, profile=oracle.SYNTH_SCENE)
+        i2 = np.stack([oracle.i2_plane(clip[t], 1, 0) for t in range(n)]).astype(np.int64)
+        want = _ring_twin(i2, 1, tau)
+        raw = torch.zeros(clip.size + 64, dtype=torch.uint8, device="cuda")
+        raw[off: off + clip.size] = torch.from_numpy(clip).cuda().view(-1)
+        base = raw.data_ptr() + off
+        with dips_b200.Context(w, h, 1, 0, tau, flavor=1) as ctx:
+            ctx.push_frame(clip[0], want_rgba=False)
+            ctx.push_frame(clip[1], want_rgba=False)
+            ctx.run_clip_device(base + 2 * clip.shape[1], 30, first_frame=2)
+            used = ctx.last_plan()["ring_clip"]
+            for t in range(32, n):
+                ctx.push_frame(clip[t], want_rgba=False)
+            s, c = ctx.get_accumulators()
+            sad, cnt = ctx.get_scalars(0, n)
+        assert used == ((w * h) % 8 == 0 and off % 16 == 0), (w, h, off)
+        assert np.array_equal(s.ravel(), want[0]) and np.array_equal(c.ravel(), want[1])
+        assert np.array_equal(np.asarray(sad, np.int64), want[2]) and np.array_equal(np.asarray(cnt, np.int64), want[3])

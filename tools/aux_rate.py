@@ -41,20 +41,31 @@ def main():
 
 
 def ring_rate():
-    """per-frame kernels back to back over a device-resident 1080p clip (batch call of the ring flavours): the u16 / u32 planes
-    stay in L2 between frames, unlike in an ncu launch list"""
+    """batch call of the ring flavours and of windowed contexts over a device-resident 1080p clip: ring_clip_kernel (one launch
+    per run of frames, ring in registers) next to the per-frame kernels back to back (DIPSB_RING_BATCH=0; their u16 / u32
+    planes stay in L2 between frames, unlike in an ncu launch list)"""
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    w, h, fmt, n = 1920, 1080, 1, 200
-    fb = w * h * 4
-    clip = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
-    dips_b200.synth_fill_device(0, clip.data_ptr(), 0, n, w, h, fmt, stream=stream.cuda_stream)
-    for name, flavor, window in (("dips ring-of-4", dips_b200.FLAVOR_DIPS_RING4, 1), ("dips_alt ring-of-2", dips_b200.FLAVOR_ALT_RING2, 1),
-                                 ("frame0, 3x3 median", dips_b200.FLAVOR_FRAME0, 3), ("frame0, 7x7 median", dips_b200.FLAVOR_FRAME0, 7)):
-        with dips_b200.Context(w, h, fmt, 0, 32, flavor=flavor, spatial_window=window) as ctx:
-            ctx.set_stream(stream.cuda_stream)
-            t = timed(stream, lambda: (ctx.reset(), ctx.run_clip_device(clip.data_ptr(), n, fb, 0)), reps=3)
-            print(f"1080p RGBx8 batch, {name:20s}: {t / n:6.1f} us per frame ({n * 1e6 / t:8.0f} frames/s device-side)")
+    for fmt_name, fmt, n in (("RGBx8", 1, 600), ("RGB8", 0, 600)):
+        w, h = 1920, 1080
+        fb = w * h * dips_b200.bytes_per_pixel(fmt)
+        clip = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
+        dips_b200.synth_fill_device(0, clip.data_ptr(), 0, n, w, h, fmt, stream=stream.cuda_stream)
+        for name, flavor, window in (("dips ring-of-4", dips_b200.FLAVOR_DIPS_RING4, 1), ("dips_alt ring-of-2", dips_b200.FLAVOR_ALT_RING2, 1),
+                                     ("frame0, 3x3 median", dips_b200.FLAVOR_FRAME0, 3), ("frame0, 7x7 median", dips_b200.FLAVOR_FRAME0, 7)):
+            if window > 1 and fmt != 1:
+                continue
+            for batch in ((True, False) if window == 1 else (False,)):
+                os.environ["DIPSB_RING_BATCH"] = "1" if batch else "0"
+                with dips_b200.Context(w, h, fmt, 0, 32, flavor=flavor, spatial_window=window) as ctx:
+                    ctx.set_stream(stream.cuda_stream)
+                    m = n if batch else 200
+                    t = timed(stream, lambda: (ctx.reset(), ctx.run_clip_device(clip.data_ptr(), m, fb, 0)), reps=3)
+                    how = "ring_clip_kernel" if ctx.last_plan()["ring_clip"] else "per-frame kernels"
+                    print(f"1080p {fmt_name} batch, {name:20s} {how:18s}: {t / m:6.2f} us per frame ({m * 1e6 / t:8.0f} frames/s, "
+                          f"{fb * m / t / 1e3:6.0f} GB/s of frame bytes)")
+        os.environ.pop("DIPSB_RING_BATCH", None)
+        del clip
 
 
 if __name__ == "__main__":
