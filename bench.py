@@ -683,6 +683,34 @@ class Bench:
         return info
 
 
+def ring_batch(B, tau=32, n=600):
+    """SURVEY row N1 in batch: the reference's ring-of-4 (`dips`) and ring-of-2 (`dips_alt`) semantics over a device-resident
+    1080p RGBx clip through dipsb_run_clip_device -- warm-up frames on the per-frame kernel, the steady state in one launch of
+    ring_clip_kernel.  Device-timed, the clip (5 GB) larger than L2."""
+    torch, lib = B.torch, B.lib
+    w, h, fmt = 1920, 1080, lib.FMT_RGBX8
+    fb = w * h * 4
+    clip = B.ensure_buf(n * fb)[: n * fb]
+    lib.synth_fill_device(B.local_rank, clip.data_ptr(), 0, n, w, h, fmt, SEED, lib.SYNTH_SCENE, B.stream.cuda_stream)
+    torch.cuda.synchronize()
+    res = {"geometry": f"1920x1080 RGBx8 x {n} frames, device-resident, accumulators + per-frame scalars", "unit": "frames/s"}
+    for name, flavor in (("dips_ring4", lib.FLAVOR_DIPS_RING4), ("dips_alt_ring2", lib.FLAVOR_ALT_RING2)):
+        with lib.Context(w, h, fmt, 0, tau, device=B.local_rank, flavor=flavor) as ctx:
+            ctx.set_stream(B.stream.cuda_stream)
+            ctx.reset(); ctx.run_clip_device(clip.data_ptr(), n, fb, 0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            reps = 5
+            e0.record(B.stream)
+            for _ in range(reps):
+                ctx.reset(); ctx.run_clip_device(clip.data_ptr(), n, fb, 0)
+            e1.record(B.stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            res[name] = {"value": n / ms * 1e3, "ms_per_clip": ms, "frame_GBps": n * fb / ms / 1e6, "ring_clip_kernel": bool(ctx.last_plan()["ring_clip"])}
+    return res
+
+
 def main():
     args = parse_args()
     out = _claim_stdout()
@@ -749,6 +777,7 @@ def main():
     stream_info = None
     if not args.no_stream and not args.no_e2e and world == 1:
         stream_info = B.stream_boundary()
+        stream_info["ring_batch"] = ring_batch(B)
 
     if rank == 0:
         line = {

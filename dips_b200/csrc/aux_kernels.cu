@@ -548,12 +548,31 @@ __global__ void spatial_median_kernel(const uint16_t* __restrict__ in, uint16_t*
 
 // The same median, tiled: a block of 32 x 8 threads filters a 64 x 8 pixel tile out of shared memory, every thread two
 // horizontally adjacent pixels packed in one u16x2 register.  The w*w packed taps stay in registers; each of the 9 steps of
-// the bitwise binary search counts "tap >= candidate" for both pixels with one VIADDMNMX.S16x2.RELU and one add per tap.
+// the bitwise binary search counts "tap >= candidate" for both pixels, and the count is split over the two instruction
+// pipes that issue side by side (measured, tools/native/pipe_rate.cu: VIADDMNMX 2 clk per warp and sub-partition, HFMA2 2 clk,
+// the two interleaved 1 clk per instruction; HSET2 and LOP3 queue behind VIADDMNMX on the ALU pipe, IMAD half does):
+//   * 2/3 of the taps: VIADDMNMX.S16x2.RELU gives 0/1 per half, summed two at a time by IADD3 (ALU pipe as well);
+//   * 1/3 of the taps are kept as the half-precision numbers 1024 + tap (bit pattern tap + 0x6400, exact): HFMA2.SAT
+//     computes clamp(tap - candidate + 1, 0, 1) exactly, HADD2 sums it onto 1024.0, whose bit pattern is 0x6400 + count;
+//   * half of the warps run the half-precision part first, the other half the integer part (see the loop).
+// ncu (profiles/r02_median7_ncu.txt): 1084 instructions per warp, ALU pipe 76 % busy, issue slots 73 % -- the kernel is bound
+// by the ALU pipe (VIADDMNMX and IADD3 both live there); other splits of the taps (1/2, 3/7) measure the same +-3 %.
 // Even width only (a pair never straddles the right edge); odd widths take spatial_median_kernel.
+__device__ __forceinline__ uint32_t hfma2_sat(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
 template <int w>
-__global__ void __launch_bounds__(256) spatial_median_tile_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t W, uint32_t H,
-                                                                  uint32_t one /* the constant 1, opaque to the compiler */) {
+__global__ void __launch_bounds__(256) spatial_median_tile_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t W, uint32_t H) {
     constexpr int r = w / 2, n = w * w, k = n / 2;
+    constexpr int nB = n - n / 3;                                 // taps counted on the ALU pipe; the rest in half precision on the FMA pipe
+    constexpr uint32_t kHalf1024 = 0x64006400u;                   // 1024.0 in both halves
     constexpr int kRows = 8 + 2 * r, kWords = 36;                 // tile columns x0-4 .. x0+67 as 36 words of two pixels
     __shared__ uint32_t tile[kRows][kWords];
     const uint32_t x0 = blockIdx.x * 64u, y0 = blockIdx.y * 8u;
@@ -574,8 +593,9 @@ __global__ void __launch_bounds__(256) spatial_median_tile_kernel(const uint16_t
 #pragma unroll
         for (int dx = -r; dx <= r; ++dx) {
             // pixels (x+dx, x+1+dx) sit at tile columns 2t+4+dx, 2t+5+dx
-            const int c = 4 + dx;
-            v[dy * w + dx + r] = (c & 1) ? __funnelshift_r(q[(c - 1) / 2], q[(c + 1) / 2], 16) : q[c / 2];
+            const int c = 4 + dx, i = dy * w + dx + r;
+            const uint32_t tap = (c & 1) ? __funnelshift_r(q[(c - 1) / 2], q[(c + 1) / 2], 16) : q[c / 2];
+            v[i] = i < nB ? tap : tap + kHalf1024;
         }
     }
     uint32_t lo = 0u;                                             // per half: largest value with #(tap < value) <= k == sorted[k]
@@ -583,12 +603,25 @@ __global__ void __launch_bounds__(256) spatial_median_tile_kernel(const uint16_t
     for (int bit = 8; bit >= 0; --bit) {
         const uint32_t cand = lo + (0x00010001u << bit);
         const uint32_t one_minus_cand = __vsub2(0x00010001u, cand);
-        uint32_t ge = 0u;
+        const uint32_t neg_cand_h = (cand + 0x63FF63FFu) | 0x80008000u;      // -(1023 + candidate) per half
+        // ptxas emits the two kinds as two runs, and the warps of a block advance in step: with every warp in the same run
+        // one pipe would idle at a time.  The two warps a block has on each sub-partition (warp w and w + 4) therefore take
+        // the runs in opposite order; each run starts from the other's count, which pins the order (1024 + count as a
+        // half-precision number is the bit pattern 0x6400 + count).
+        uint32_t ge;
+        auto count_int = [&](uint32_t from) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) {   // tap >= cand ? 1 : 0 per half (ALU pipe), summed with an IMAD (FMA pipe): the two pipes share the work
-            const uint32_t m = __viaddmin_s16x2_relu(v[i], one_minus_cand, 0x00010001u);
-            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(ge) : "r"(m), "r"(one));
-        }
+            for (int i = 0; i < nB; ++i) from += __viaddmin_s16x2_relu(v[i], one_minus_cand, 0x00010001u);
+            return from;
+        };
+        auto count_half = [&](uint32_t from) {
+            uint32_t acc = from + kHalf1024;
+#pragma unroll
+            for (int i = nB; i < n; ++i) acc = hadd2(acc, hfma2_sat(v[i], 0x3C003C00u, neg_cand_h));
+            return acc - kHalf1024;
+        };
+        if (ty & 4u) ge = count_int(count_half(0u));
+        else ge = count_half(count_int(0u));
         // #(tap < cand) <= k  <=>  ge >= n - k
         const uint32_t keep = __viaddmin_s16x2_relu(ge, (uint32_t)(((1 - (n - k)) & 0xFFFF) * 0x00010001u), 0x00010001u);
         lo += keep << bit;
@@ -795,9 +828,9 @@ cudaError_t launch_spatial_median(const Geometry& g, const uint16_t* in, uint16_
     if ((g.width & 1u) == 0 && (((uintptr_t)in | (uintptr_t)out) & 3u) == 0) {   // tiled, two pixels per thread
         const dim3 grid((g.width + 63) / 64, (g.height + 7) / 8, 1);
         switch (window) {
-            case 3: spatial_median_tile_kernel<3><<<grid, 256, 0, s>>>(in, out, g.width, g.height, 1u); break;
-            case 5: spatial_median_tile_kernel<5><<<grid, 256, 0, s>>>(in, out, g.width, g.height, 1u); break;
-            case 7: spatial_median_tile_kernel<7><<<grid, 256, 0, s>>>(in, out, g.width, g.height, 1u); break;
+            case 3: spatial_median_tile_kernel<3><<<grid, 256, 0, s>>>(in, out, g.width, g.height); break;
+            case 5: spatial_median_tile_kernel<5><<<grid, 256, 0, s>>>(in, out, g.width, g.height); break;
+            case 7: spatial_median_tile_kernel<7><<<grid, 256, 0, s>>>(in, out, g.width, g.height); break;
             default: return cudaErrorInvalidValue;
         }
         count_launch();
