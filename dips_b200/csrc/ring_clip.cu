@@ -31,6 +31,7 @@ namespace {
 
 constexpr int kRcThreads = 256;
 constexpr int kRcPx = 8;          // pixels per thread: 4 packed u16x2 registers per plane
+constexpr int kRcAhead = 2;       // frames between the register load and the L2 prefetch
 
 struct RingClipK {
     const uint8_t* frames; uint64_t stride; uint32_t n_frames, seg_frames;
@@ -60,6 +61,12 @@ __device__ __forceinline__ void load_px8(const uint8_t* p, bool active, uint32_t
     }
 }
 
+// pull the 128-byte lines of a later frame into L2 (one lane in four: consecutive lanes are 24 / 32 bytes apart): a thread
+// has registers for one frame in flight only, and HBM latency is longer than one frame's worth of math
+__device__ __forceinline__ void prefetch_l2(const uint8_t* p, uint32_t lane) {
+    if ((lane & 3u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // what a frame leaves in its ring slot: I2 of the 8 pixels, quantised to grey for `dips` (the rgba8unorm store of
 // dips_shader.wgsl:187: 2 * ((I2 + 1) >> 1) == (I2 + 1) & ~1; no carry between the halves, I2 <= 510)
 template <int FBPP, int CH, int NS>
@@ -78,7 +85,7 @@ __device__ __forceinline__ void slot_value(const uint32_t (&w)[2 * FBPP], uint32
 }
 
 template <int FBPP, int CH, int NS, int MEDMAX>
-__global__ void __launch_bounds__(kRcThreads, NS == 4 ? 4 : 5) ring_clip_kernel(const RingClipK K) {
+__global__ void __launch_bounds__(kRcThreads, (NS == 4 || FBPP == 4) ? 4 : 5) ring_clip_kernel(const RingClipK K) {
     const uint32_t unit = blockIdx.x * (uint32_t)kRcThreads + threadIdx.x;
     const bool active = unit < K.n_units;
     const uint32_t lane = threadIdx.x & 31u, gwarp = unit >> 5;
@@ -141,6 +148,7 @@ __global__ void __launch_bounds__(kRcThreads, NS == 4 ? 4 : 5) ring_clip_kernel(
         constexpr int S = decltype(slot_tag)::value;
         slot_value<FBPP, CH, NS>(w, r[S]);
         if (j + 1 < f1) load_px8<FBPP>(src + (uint64_t)(j + 1) * K.stride, active, w);   // next frame in flight under the math
+        if (j + 1 + kRcAhead < f1 && active) prefetch_l2(src + (uint64_t)(j + 1 + kRcAhead) * K.stride, lane);
         uint32_t d[4], m[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -165,6 +173,9 @@ __global__ void __launch_bounds__(kRcThreads, NS == 4 ? 4 : 5) ring_clip_kernel(
     };
 
     if (f0 < f1) load_px8<FBPP>(src + (uint64_t)f0 * K.stride, active, w);
+#pragma unroll
+    for (int a = 1; a <= kRcAhead; ++a)
+        if (f0 + a < f1 && active) prefetch_l2(src + (uint64_t)(f0 + a) * K.stride, lane);
     uint32_t j = f0, since = 0;
     for (; j + NS <= f1; j += NS) {
         step(std::integral_constant<int, 0>{}, j);
