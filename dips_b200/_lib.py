@@ -61,6 +61,8 @@ SYMBOLS = {
     "dipsb_get_frame_means": (_i32, [_vp, _u64, _u64, _vp]),
     "dipsb_host_alloc": (_i32, [_i32, _u64, C.POINTER(_vp)]),
     "dipsb_host_free": (_i32, [_vp]),
+    "dipsb_host_register": (_i32, [_i32, _vp, _u64]),
+    "dipsb_host_unregister": (_i32, [_vp]),
     "dipsb_host_copy2d": (_i32, [_vp, _u64, _vp, _u64, _u64, _u64]),
     "dipsb_host_copy_threads": (_u32, []),
     "dipsb_synth_fill_device": (_i32, [_i32, _vp, _u64, _u64, _u32, _u32, _i32, _u64, _i32, _vp]),

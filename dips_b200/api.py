@@ -149,6 +149,39 @@ class PinnedBuffer:
             pass
 
 
+class RegisteredBuffer:
+    """Page-locks a numpy array the caller owns, in place (dipsb_host_register), for as long as the object lives: frames
+    inside it take the direct copy-engine path of the frame calls.  close() (or a `with` block) unlocks it."""
+
+    def __init__(self, array: np.ndarray, device: int = 0):
+        if not array.flags["C_CONTIGUOUS"]:
+            raise ValueError("RegisteredBuffer needs a C-contiguous array")
+        self._lib = _lib.load()
+        self.array = array
+        self._p = C.c_void_p(array.ctypes.data)
+        rc = self._lib.dipsb_host_register(device, self._p, array.nbytes)
+        if rc != 0:
+            self._p = None
+            raise DipsError(rc, self._lib.dipsb_last_error(None).decode())
+
+    def close(self) -> None:
+        if self._p is not None:
+            self._lib.dipsb_host_unregister(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _make_config(lib, width, height, fmt, mode, threshold, chroma, device, colorize, filt, sigmoid_scalar, spatial_window,
                  flavor):
     cfg = _lib.Config()

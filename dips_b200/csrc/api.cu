@@ -1353,6 +1353,24 @@ extern "C" int32_t dipsb_host_free(void* p) {
     return DIPSB_OK;
 }
 
+extern "C" int32_t dipsb_host_register(int32_t device, void* p, uint64_t bytes) {
+    if (!p || bytes == 0) return fail(nullptr, DIPSB_ERR_INVALID, "host_register: null or empty range");
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DIPSB_ERR_CUDA, "host_register: no CUDA device %d", device); }
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, e == cudaErrorMemoryAllocation ? DIPSB_ERR_NOMEM : DIPSB_ERR_INVALID, "host_register(%p, %llu): %s", p, (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return DIPSB_OK;
+}
+
+extern "C" int32_t dipsb_host_unregister(void* p) {
+    if (!p) return fail(nullptr, DIPSB_ERR_INVALID, "host_unregister: null pointer");
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DIPSB_ERR_INVALID, "host_unregister(%p): %s", p, cudaGetErrorString(e)); }
+    return DIPSB_OK;
+}
+
 extern "C" int32_t dipsb_host_copy2d(void* dst, uint64_t dpitch, const void* src, uint64_t spitch, uint64_t row_bytes, uint64_t rows) {
     if (!rows || !row_bytes) return DIPSB_OK;
     if (!dst || !src || dpitch < row_bytes || spitch < row_bytes) return fail(nullptr, DIPSB_ERR_INVALID, "host_copy2d: null pointer or pitch smaller than a row");

@@ -317,6 +317,15 @@ int32_t dipsb_synth_fill_device(int32_t device, void *d_dst, uint64_t first_fram
 int32_t dipsb_host_alloc(int32_t device, uint64_t bytes, void **out);
 int32_t dipsb_host_free(void *p);
 /*
+ * The same for memory the caller already owns (a decoder's buffer pool, an mmap'ed file, a Vec kept for the whole run):
+ * page-lock [p, p + bytes) in place so that the frame calls take the direct path for any frame inside it.  Costs about a
+ * millisecond per 8 MB, so register buffers that are reused, once, not every frame.  The range must stay mapped until
+ * dipsb_host_unregister(p) (same p); unregistering memory that was not registered is an error, freeing registered memory
+ * without unregistering it leaves the pages locked until the process ends.
+ */
+int32_t dipsb_host_register(int32_t device, void *p, uint64_t bytes);
+int32_t dipsb_host_unregister(void *p);
+/*
  * The staging copy the frame calls use for ordinary host memory: rows of row_bytes from src (pitch spitch) to dst (pitch
  * dpitch) on a small persistent thread pool -- the caller plus DIPSB_COPY_THREADS-1 helpers (environment variable, default
  * min(4, cores/2); 1 = the calling thread only); copies under 1 MB stay on the caller.  While copies follow each other at a

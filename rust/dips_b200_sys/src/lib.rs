@@ -105,6 +105,8 @@ extern "C" {
     pub fn dipsb_get_frame_means(ctx: *mut dipsb_ctx, first: u64, n: u64, out: *mut f32) -> i32;
     pub fn dipsb_host_alloc(device: i32, bytes: u64, out: *mut *mut c_void) -> i32;
     pub fn dipsb_host_free(p: *mut c_void) -> i32;
+    pub fn dipsb_host_register(device: i32, p: *mut c_void, bytes: u64) -> i32;
+    pub fn dipsb_host_unregister(p: *mut c_void) -> i32;
     pub fn dipsb_host_copy2d(dst: *mut c_void, dpitch: u64, src: *const c_void, spitch: u64, row_bytes: u64, rows: u64) -> i32;
     pub fn dipsb_host_copy_threads() -> u32;
     pub fn dipsb_synth_fill_device(device: i32, d_dst: *mut c_void, first_frame: u64, n_frames: u64, width: u32, height: u32, format: i32, seed: u64, profile: i32, stream: *mut c_void) -> i32;

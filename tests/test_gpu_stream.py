@@ -513,3 +513,28 @@ def test_ring_clip_kernel_mixes_with_per_frame_calls_and_odd_layouts(oracle):
         assert used == ((w * h) % 8 == 0 and off % 16 == 0), (w, h, off)
         assert np.array_equal(s.ravel(), want[0]) and np.array_equal(c.ravel(), want[1])
         assert np.array_equal(np.asarray(sad, np.int64), want[2]) and np.array_equal(np.asarray(cnt, np.int64), want[3])
+
+
+def test_registered_caller_buffer_takes_the_direct_path(oracle):
+    """dipsb_host_register: a buffer the caller owns, page-locked in place, gives the same frames as ordinary memory (and is
+    recognised as page-locked by the frame calls); unregistering twice / registering nothing are errors, not crashes."""
+    import ctypes as C
+
+    import dips_b200
+    from dips_b200 import _lib
+    w, h, n = 320, 200, 6
+    clip = oracle.synth_clip(n, w, h, 1, profile=oracle.SYNTH_SCENE)
+    pool = np.empty((2, w * h * 4), np.uint8)                      # a two-buffer "decoder pool"
+    out_pool = np.empty((2, w * h * 4), np.uint8)
+    with dips_b200.Context(w, h, 1, 0, 12, colorize=True, filt=0) as a, dips_b200.Context(w, h, 1, 0, 12, colorize=True, filt=0) as b, \
+            dips_b200.RegisteredBuffer(pool) as rin, dips_b200.RegisteredBuffer(out_pool):
+        for t in range(n):
+            ra, oa, sa = a.push_frame(clip[t])
+            rin.array[t & 1] = clip[t]
+            rb, ob, sb = b.push_frame(pool[t & 1], out=out_pool[t & 1])
+            assert ra == rb and sa == sb and np.array_equal(oa, ob), t
+        assert np.array_equal(a.get_accumulators()[0], b.get_accumulators()[0])
+    lib = _lib.load()
+    assert lib.dipsb_host_unregister(C.c_void_p(pool.ctypes.data)) != 0          # already unregistered by the with block
+    assert lib.dipsb_host_register(0, None, 16) != 0 and lib.dipsb_host_register(0, C.c_void_p(pool.ctypes.data), 0) != 0
+    assert b"host_register" in lib.dipsb_last_error(None)
