@@ -435,12 +435,16 @@ class Bench:
             ctx.comm_check()
         acc_sum, acc_cnt = ctx.get_accumulators()
         tot = self.sum_over_ranks([int(sad.sum()), int(cnt.sum())])
-        assert int(acc_sum.astype(np.uint64).sum()) == tot[0] and int(acc_cnt.astype(np.uint64).sum()) == tot[1], \
-            f"{name}: checksum of checksums failed"
+        got = (int(acc_sum.astype(np.uint64).sum()), int(acc_cnt.astype(np.uint64).sum()))
+        # reported, not asserted: a failed identity must not take the measurements of the other rows down with it
+        checks = {"sum_of_maps_equals_sum_of_scalars": got[0] == tot[0] and got[1] == tot[1]}
+        if not checks["sum_of_maps_equals_sum_of_scalars"]:
+            checks["detail"] = f"maps {got} vs scalars {tuple(tot)}"
+            log(self.rank, f"{name}: CHECKSUM MISMATCH maps {got} vs scalars {tuple(tot)} (rank {self.rank}: scalars {int(sad.sum())}, {int(cnt.sum())})")
         if sharded:   # every rank must hold the same gathered maps
             sig = [int(acc_sum[::97].astype(np.uint64).sum()), int(acc_cnt[::89].astype(np.uint64).sum())]
             allsig = self.sum_over_ranks(sig)
-            assert allsig[0] == sig[0] * self.world and allsig[1] == sig[1] * self.world, f"{name}: gathered maps differ between ranks"
+            checks["gathered_maps_equal_on_all_ranks"] = allsig[0] == sig[0] * self.world and allsig[1] == sig[1] * self.world
             phases["gather_on_readout_ms"] = gather_ms
 
         # ---- sustained: back-to-back steps for >= sustained_s (the power-capped regime; short runs measure burst clocks) ----
@@ -503,7 +507,7 @@ class Bench:
         res = {"name": name, "value": value, "unit": "frames/s", "ms_per_step": ms_total / steps, "steps": steps,
                "hbm_GBps_per_gpu_whole_step": n_local * fb * steps / (ms_total / 1e3) / 1e9,
                "phases": phases, "roofline": roofline, "sustained": sustained, "clocks": clocks, "plan": plan,
-               "gpu_launches": int(launches) * self.world, "comm": ctx.comm_info() if sharded else None}
+               "gpu_launches": int(launches) * self.world, "comm": ctx.comm_info() if sharded else None, "checks": checks}
         if keep:
             return res, ctx, clip
         ctx.close()
@@ -786,7 +790,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_of(wl, world),
             "plan": head["plan"], "hbm_GBps_per_gpu_whole_step": head["hbm_GBps_per_gpu_whole_step"],
             "phases": head["phases"], "roofline": head["roofline"], "sustained": head["sustained"], "cpu_baseline": cpu, "e2e": e2e,
-            "configs": rows, "multi_gpu_parity": parity, "comm": head["comm"], "stream": stream_info,
+            "configs": rows, "multi_gpu_parity": parity, "comm": head["comm"], "stream": stream_info, "checks": head["checks"],
             "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
         }
         print(json.dumps(line), file=out, flush=True)
