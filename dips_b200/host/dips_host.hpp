@@ -144,6 +144,22 @@ class PinnedFrame {
     size_t len_ = 0;
 };
 
+// The same for a buffer the caller already owns and reuses (a decoder's buffer pool, the vector the output is collected in):
+// page-locked in place for the lifetime of this object (dipsb_host_register / dipsb_host_unregister).  The memory must
+// outlive it.
+class RegisteredFrames {
+  public:
+    RegisteredFrames(void* p, size_t len, int32_t device = 0) : ptr_(p) {
+        if (dipsb_host_register(device, p, len) != DIPSB_OK) throw std::runtime_error(dipsb_last_error(nullptr));
+    }
+    ~RegisteredFrames() { dipsb_host_unregister(ptr_); }
+    RegisteredFrames(const RegisteredFrames&) = delete;
+    RegisteredFrames& operator=(const RegisteredFrames&) = delete;
+
+  private:
+    void* ptr_ = nullptr;
+};
+
 }  // namespace dips
 
 namespace dips_alt {

@@ -303,6 +303,32 @@ where
     }
 }
 
+/// Page-locks a buffer the caller already owns and reuses (a decoder's buffer pool, the `Vec` the output is collected in)
+/// in place, for the lifetime of the guard (`dipsb_host_register` / `dipsb_host_unregister`): frames inside it take the
+/// direct copy-engine path of `dipsb_push_frame*`.  About a millisecond per 8 MB: once per buffer, not per frame.
+pub struct RegisteredFrames<'a> {
+    ptr: *mut std::ffi::c_void,
+    _buf: std::marker::PhantomData<&'a mut [u8]>,
+}
+
+impl<'a> RegisteredFrames<'a> {
+    pub fn new(device: i32, buf: &'a mut [u8]) -> anyhow::Result<Self> {
+        let p = buf.as_mut_ptr() as *mut std::ffi::c_void;
+        let rc = unsafe { sys::dipsb_host_register(device, p, buf.len() as u64) };
+        if rc != 0 {
+            let msg = unsafe { CStr::from_ptr(sys::dipsb_last_error(ptr::null())) };
+            anyhow::bail!("dipsb_host_register failed ({rc}): {}", msg.to_string_lossy());
+        }
+        Ok(Self { ptr: p, _buf: std::marker::PhantomData })
+    }
+}
+
+impl Drop for RegisteredFrames<'_> {
+    fn drop(&mut self) {
+        unsafe { sys::dipsb_host_unregister(self.ptr) };
+    }
+}
+
 /// Page-locked host buffer (`dipsb_host_alloc`).  A decoder that writes its frames here -- and a caller that receives
 /// the difference frame here -- lets `dipsb_push_frame*` skip its two staging copies (the role of the mapped gst buffer
 /// in dips/src/frame_extractor.rs:216-226).  Derefs to a byte slice.
