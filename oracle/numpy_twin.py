@@ -59,6 +59,62 @@ def run_clip(frames, fmt, mode, tau, chroma=0, state=None):
                 sad=d.sum(1).astype(np.uint64), cnt=m.sum(1).astype(np.uint64), state=out_state.astype(np.uint16))
 
 
+def ring_clip(i2, flavor, tau, snapshot_before=(), want_planes=False):
+    """Integer restatement of the reference's temporal rings over a clip of I2 planes (frames x pixels): per-pixel sums and
+    counts, per-frame sad / cnt -- what dipsb_run_clip_* returns on a ring-flavour context.
+    flavor 1, `dips` (dips/src/gpu/mod.rs:170-216, bind_groups.rs:407-427, dips_shader.wgsl:187-214, pre_compute_shader.wgsl:
+    103-131): 3 pass-through frames, start = grey(upper median of the first 4), every later frame overwrites the oldest ring
+    slot with its grey-quantised intensity, D = |start - sorted4(ring)[2]|; a frame index in `snapshot_before` restarts the
+    warm-up.  flavor 2 / 3, `dips_alt` (dips_alt/src/dips_compute/shaders/pre_compute_shader.wgsl:212-262): ring of 2,
+    min (as shipped) / max (in-bounds median) of the two, D = |snapshot - median|; at a frame index in `snapshot_before` the
+    snapshot becomes grey(median) and the frame contributes nothing.  grey(v) = 2 * ((v + 1) >> 1): the rgba8unorm store of an
+    intensity, in I2 units.  With want_planes the signed S = start - median of every frame is returned too (None where no
+    difference is produced)."""
+    i2 = np.asarray(i2, dtype=np.int64)
+    n, npx = i2.shape
+    grey = lambda v: 2 * ((v + 1) >> 1)
+    s, c = np.zeros(npx, np.int64), np.zeros(npx, np.int64)
+    sad, cnt = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    planes = [None] * n
+
+    def account(t, signed):
+        d = np.abs(signed)
+        s[:] += d
+        c[:] += d > tau
+        sad[t] = d.sum()
+        cnt[t] = (d > tau).sum()
+        planes[t] = signed
+
+    if flavor == 1:
+        ring, start, idx, seen = np.zeros((4, npx), np.int64), None, 0, 0
+        for t in range(n):
+            if t in snapshot_before:
+                seen, idx = 0, 0
+            seen += 1
+            if seen < 4:
+                ring[seen - 1] = i2[t]
+                continue
+            if seen == 4:
+                ring[3] = i2[t]
+                start = grey(np.sort(ring, axis=0)[2])
+                ring[0] = grey(ring[0])
+            else:
+                ring[idx] = grey(i2[t])
+                idx = (idx + 1) % 4
+            account(t, start - np.sort(ring, axis=0)[2])
+    else:
+        ring, snap, idx = np.zeros((2, npx), np.int64), np.zeros(npx, np.int64), 0
+        for t in range(n):
+            ring[idx] = i2[t]
+            idx ^= 1
+            med = ring.max(axis=0) if flavor == 3 else ring.min(axis=0)
+            if t in snapshot_before:
+                snap = grey(med)
+                continue
+            account(t, snap - med)
+    return (s, c, sad, cnt, planes) if want_planes else (s, c, sad, cnt)
+
+
 def mix64(z):
     z &= MASK64
     z ^= z >> 30

@@ -395,45 +395,10 @@ def test_batch_call_runs_the_ring_flavours(oracle, flavor):
 
 
 def _ring_twin(i2, flavor, tau, snapshot_before=()):
-    """Integer restatement of the ring machines of dipsb_push_frame on I2 planes (frames x pixels, int64): per-pixel sums and
-    counts, per-frame sad / cnt.  `dips` (flavor 1): 3 pass-through frames, start = grey(upper median of the first 4), ring
-    slots quantised to grey as they are overwritten (dips/src/gpu/mod.rs:170-216, bind_groups.rs:407-427,
-    dips_shader.wgsl:187-214).  `dips_alt` (2 / 3): ring of 2, min / max of the two, snapshot = grey(median) on request,
-    the snapshot frame contributes nothing (pre_compute_shader.wgsl:212-262)."""
-    n, npx = i2.shape
-    grey = lambda v: 2 * ((v + 1) >> 1)
-    s, c = np.zeros(npx, np.int64), np.zeros(npx, np.int64)
-    sad, cnt = np.zeros(n, np.int64), np.zeros(n, np.int64)
-    if flavor == 1:
-        ring, start, idx, seen = np.zeros((4, npx), np.int64), None, 0, 0
-        for t in range(n):
-            if t in snapshot_before:
-                seen, idx = 0, 0
-            seen += 1
-            if seen < 4:
-                ring[seen - 1] = i2[t]
-                continue
-            if seen == 4:
-                ring[3] = i2[t]
-                start = grey(np.sort(ring, axis=0)[2])
-                ring[0] = grey(ring[0])
-            else:
-                ring[idx] = grey(i2[t])
-                idx = (idx + 1) % 4
-            d = np.abs(start - np.sort(ring, axis=0)[2])
-            s += d; c += d > tau; sad[t] = d.sum(); cnt[t] = (d > tau).sum()
-    else:
-        ring, snap, idx = np.zeros((2, npx), np.int64), np.zeros(npx, np.int64), 0
-        for t in range(n):
-            ring[idx] = i2[t]
-            idx ^= 1
-            med = ring.max(axis=0) if flavor == 3 else ring.min(axis=0)
-            if t in snapshot_before:
-                snap = grey(med)
-                continue
-            d = np.abs(snap - med)
-            s += d; c += d > tau; sad[t] = d.sum(); cnt[t] = (d > tau).sum()
-    return s, c, sad, cnt
+    """oracle/numpy_twin.py::ring_clip -- the integer restatement of the two ring machines (checked against the oracle's f32
+    restatement of the shaders in tests/test_oracle_ring_twin.py)"""
+    from oracle import numpy_twin
+    return numpy_twin.ring_clip(i2, flavor, tau, snapshot_before)
 
 
 @pytest.mark.parametrize("flavor", [1, 2, 3])
