@@ -1,3 +1,5 @@
+"""Two frames through a 7x7 windowed context at 1080p: the command profiles/r02_median7_ncu.txt was captured on
+(ncu --set full -k regex:spatial_median -c 1 python tools/median_snippet.py)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, dips_b200
